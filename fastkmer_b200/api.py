@@ -1,0 +1,319 @@
+"""ctypes binding of libfastkmer_b200.so (C ABI: include/fastkmer_b200.h)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libfastkmer_b200.so")
+
+FKM_OK, FKM_EINVAL, FKM_ECUDA, FKM_EIO, FKM_ENOMEM, FKM_EOVERFLOW = 0, -1, -2, -3, -4, -5
+
+
+class FkmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("fastkmer_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class fkm_config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("k", "m", "x", "max_b", "sequence_type", "use_ht", "write",
+                                         "use_kryo_serializer", "use_custom_partitioner", "num_partition_tasks")] + \
+               [("dataset", C.c_char_p), ("output_directory", C.c_char_p), ("prefix", C.c_char_p)]
+
+
+class fkm_stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("n_positions", "n_bases", "n_kmers", "n_superkmers", "superkmer_bytes",
+                                          "n_distinct", "total_count", "digest_sum", "digest_xor", "n_nonempty_bins",
+                                          "h2d_bytes", "d2h_bytes", "gpu_launches", "n_batches")] + \
+               [("ms_total", C.c_double), ("ms_stage", C.c_double * 8)]
+
+
+class fkm_synth(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("seed_genome", "seed_reads", "seed_errors", "genome_len", "n_reads",
+                                          "read_len", "first_read")]
+
+
+class Stats(dict):
+    """fkm_stats as a dict (plus attribute access)."""
+    __getattr__ = dict.__getitem__
+
+
+_lib = None
+
+
+def lib_path():
+    return _SO
+
+
+def load_library():
+    """Loads the CUDA library.  Fails loudly when it has not been built — there is no other path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise FkmError(FKM_ECUDA, "%s is missing: build it with `make -C fastkmer_b200/csrc` "
+                                  "(or __graft_entry__.build()); there is no CPU fallback" % _SO)
+    lib = C.CDLL(_SO)
+    vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int32
+    cfgp, stp = C.POINTER(fkm_config), C.POINTER(fkm_stats)
+    sig = {
+        "fkm_last_error": (C.c_char_p, []),
+        "fkm_ctx_create": (C.c_int, [C.c_int, vp, C.POINTER(vp)]),
+        "fkm_ctx_destroy": (None, [vp]),
+        "fkm_ctx_sync": (C.c_int, [vp]),
+        "fkm_ctx_set": (C.c_int, [vp, C.c_char_p, C.c_double]),
+        "fkm_derive": (C.c_int, [cfgp, C.POINTER(i32), C.c_char_p, C.c_size_t]),
+        "fkm_execute_job": (C.c_int, [vp, cfgp, stp]),
+        "fkm_count_fasta": (C.c_int, [vp, cfgp, vp, u64, C.POINTER(vp), stp]),
+        "fkm_count_packed_host": (C.c_int, [vp, cfgp, vp, vp, u64, C.POINTER(vp), stp]),
+        "fkm_count_packed_device": (C.c_int, [vp, cfgp, vp, vp, u64, C.POINTER(vp), stp]),
+        "fkm_pack_fasta": (C.c_int, [vp, u64, vp, vp, u64, C.POINTER(u64), C.POINTER(u64)]),
+        "fkm_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
+        "fkm_host_free": (None, [vp]),
+        "fkm_result_size": (u64, [vp]),
+        "fkm_result_num_bins": (i32, [vp]),
+        "fkm_result_sorted": (i32, [vp]),
+        "fkm_result_bin_offsets": (C.c_int, [vp, vp]),
+        "fkm_result_copy": (C.c_int, [vp, vp, vp, vp, vp]),
+        "fkm_result_write": (C.c_int, [vp, C.c_char_p]),
+        "fkm_result_free": (None, [vp]),
+        "fkm_synth_fasta_host": (C.c_int, [C.POINTER(fkm_synth), vp, u64, C.POINTER(u64)]),
+        "fkm_synth_packed_device": (C.c_int, [vp, C.POINTER(fkm_synth), C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]),
+        "fkm_device_free": (C.c_int, [vp, vp]),
+        "fkm_debug_window_bins": (C.c_int, [vp, cfgp, vp, vp, u64, vp]),
+        "fkm_total_launches": (u64, []),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(lib, name)
+        f.restype, f.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc != FKM_OK:
+        raise FkmError(rc, load_library().fkm_last_error().decode("utf-8", "replace"))
+
+
+def _cfg(configuration):
+    """TestConfiguration -> fkm_config (strings kept alive on the returned struct)."""
+    c = fkm_config()
+    c.k, c.m, c.x, c.max_b = configuration.k, configuration.m, configuration.x, configuration.max_b
+    c.sequence_type = configuration.sequenceType
+    c.use_ht, c.write = int(bool(configuration.useHT)), int(bool(configuration.write))
+    c.use_kryo_serializer = int(bool(configuration.useKryoSerializer))
+    c.use_custom_partitioner = int(bool(configuration.useCustomPartitioner))
+    c.num_partition_tasks = configuration.numPartitionTasks
+    c.dataset = (configuration.dataset or "").encode()
+    c.output_directory = (configuration.outputDirectory or "").encode()
+    c.prefix = (configuration.prefix or "").encode()
+    return c
+
+
+def _stats(st):
+    d = Stats()
+    for name, _ in fkm_stats._fields_:
+        v = getattr(st, name)
+        d[name] = list(v) if name == "ms_stage" else v
+    return d
+
+
+def derive(configuration):
+    """(b, outputDir) as the library derives them (test/package.scala:32-33)."""
+    lib = load_library()
+    b = C.c_int32()
+    buf = C.create_string_buffer(8192)
+    _check(lib.fkm_derive(C.byref(_cfg(configuration)), C.byref(b), buf, len(buf)))
+    return b.value, buf.value.decode()
+
+
+def pack_fasta(fasta: bytes):
+    """Host-side FASTA -> (bases u64[], invalid u32[], n_positions, n_bases); no GPU needed."""
+    lib = load_library()
+    arr = np.frombuffer(fasta, dtype=np.uint8)
+    n_pos, n_bases = C.c_uint64(), C.c_uint64()
+    _check(lib.fkm_pack_fasta(arr.ctypes.data, arr.size, None, None, 0, C.byref(n_pos), C.byref(n_bases)))
+    nw = (n_pos.value + 31) // 32
+    bases = np.zeros(max(nw, 1), dtype=np.uint64)
+    inv = np.zeros(max(nw, 1), dtype=np.uint32)
+    _check(lib.fkm_pack_fasta(arr.ctypes.data, arr.size, bases.ctypes.data, inv.ctypes.data, nw * 32,
+                              C.byref(n_pos), C.byref(n_bases)))
+    return bases[:nw], inv[:nw], n_pos.value, n_bases.value
+
+
+def _synth(spec):
+    s = fkm_synth()
+    s.seed_genome, s.seed_reads, s.seed_errors = spec["seeds"]
+    s.genome_len, s.n_reads, s.read_len = spec["genome_len"], spec["n_reads"], spec["read_len"]
+    s.first_read = spec.get("first_read", 0)
+    return s
+
+
+def synth_fasta(spec, out=None) -> np.ndarray:
+    """SURVEY §8(d) synthetic reads as FASTA text (uint8 array).  spec: dict(seeds=(G,R,E), genome_len, n_reads,
+    read_len[, first_read]).  `out` may be a preallocated uint8 array (e.g. pinned)."""
+    lib = load_library()
+    s = _synth(spec)
+    n = C.c_uint64()
+    _check(lib.fkm_synth_fasta_host(C.byref(s), None, 0, C.byref(n)))
+    if out is None:
+        out = np.empty(n.value, dtype=np.uint8)
+    _check(lib.fkm_synth_fasta_host(C.byref(s), out.ctypes.data, out.size, C.byref(n)))
+    return out[:n.value]
+
+
+class CountResult:
+    """Per-bin (canonical k-mer, count) arrays held on the device; numpy views on demand."""
+
+    def __init__(self, handle, k):
+        self._h = handle
+        self.k = k
+        self._cache = None
+
+    def __len__(self):
+        return int(load_library().fkm_result_size(self._h))
+
+    @property
+    def num_bins(self):
+        return int(load_library().fkm_result_num_bins(self._h))
+
+    @property
+    def sorted(self):
+        return bool(load_library().fkm_result_sorted(self._h))
+
+    def bin_offsets(self):
+        off = np.zeros(self.num_bins + 1, dtype=np.uint64)
+        _check(load_library().fkm_result_bin_offsets(self._h, off.ctypes.data))
+        return off
+
+    def arrays(self):
+        """dict(bin int32[], hi u64[], lo u64[], cnt u32[]) in the library's bin-major order."""
+        if self._cache is None:
+            n = len(self)
+            bin_ = np.empty(n, dtype=np.int32)
+            hi = np.empty(n, dtype=np.uint64)
+            lo = np.empty(n, dtype=np.uint64)
+            cnt = np.empty(n, dtype=np.uint32)
+            _check(load_library().fkm_result_copy(self._h, bin_.ctypes.data, hi.ctypes.data, lo.ctypes.data, cnt.ctypes.data))
+            self._cache = {"bin": bin_, "hi": hi, "lo": lo, "cnt": cnt}
+        return self._cache
+
+    def sorted_arrays(self):
+        """Same, sorted by (bin, k-mer): the order parity is defined on."""
+        a = self.arrays()
+        order = np.lexsort((a["lo"], a["hi"], a["bin"]))
+        return {k_: v[order] for k_, v in a.items()}
+
+    def write(self, out_dir: str):
+        _check(load_library().fkm_result_write(self._h, out_dir.encode()))
+
+    def free(self):
+        if self._h:
+            load_library().fkm_result_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """One per (process, GPU).  stream: a raw cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
+
+    def __init__(self, device=-1, stream=None):
+        lib = load_library()
+        h = C.c_void_p()
+        _check(lib.fkm_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(h)))
+        self._h = h
+        self._dev_bufs = []
+
+    def set(self, name, value):
+        _check(load_library().fkm_ctx_set(self._h, name.encode(), float(value)))
+
+    def sync(self):
+        _check(load_library().fkm_ctx_sync(self._h))
+
+    def close(self):
+        if self._h:
+            for p in self._dev_bufs:
+                load_library().fkm_device_free(self._h, p)
+            self._dev_bufs = []
+            load_library().fkm_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- the drop-in call (SparkBinKmerCounter.scala:989)
+    def execute_job(self, configuration) -> Stats:
+        st = fkm_stats()
+        cfg = _cfg(configuration)
+        _check(load_library().fkm_execute_job(self._h, C.byref(cfg), C.byref(st)))
+        return _stats(st)
+
+    # ---- in-memory variants
+    def count_fasta(self, configuration, fasta, want_result=True):
+        """fasta: bytes or uint8 numpy array (host).  -> (CountResult | None, Stats)"""
+        arr = np.frombuffer(fasta, dtype=np.uint8) if isinstance(fasta, (bytes, bytearray)) else fasta
+        st, cfg, h = fkm_stats(), _cfg(configuration), C.c_void_p()
+        _check(load_library().fkm_count_fasta(self._h, C.byref(cfg), arr.ctypes.data, arr.size,
+                                              C.byref(h) if want_result else None, C.byref(st)))
+        return (CountResult(h, configuration.k) if want_result else None), _stats(st)
+
+    def count_packed_host(self, configuration, bases, inv, n_positions, want_result=True):
+        st, cfg, h = fkm_stats(), _cfg(configuration), C.c_void_p()
+        _check(load_library().fkm_count_packed_host(self._h, C.byref(cfg), bases.ctypes.data, inv.ctypes.data, n_positions,
+                                                    C.byref(h) if want_result else None, C.byref(st)))
+        return (CountResult(h, configuration.k) if want_result else None), _stats(st)
+
+    def count_packed_device(self, configuration, d_bases, d_inv, n_positions, want_result=True):
+        """d_bases / d_inv: raw device pointers (ints) in the library's packed layout."""
+        st, cfg, h = fkm_stats(), _cfg(configuration), C.c_void_p()
+        _check(load_library().fkm_count_packed_device(self._h, C.byref(cfg), C.c_void_p(d_bases), C.c_void_p(d_inv), n_positions,
+                                                      C.byref(h) if want_result else None, C.byref(st)))
+        return (CountResult(h, configuration.k) if want_result else None), _stats(st)
+
+    def synth_packed_device(self, spec):
+        """-> (d_bases, d_inv, n_positions): synthetic reads generated in device memory (freed with the context)."""
+        s = _synth(spec)
+        b, i, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        _check(load_library().fkm_synth_packed_device(self._h, C.byref(s), C.byref(b), C.byref(i), C.byref(n)))
+        self._dev_bufs += [b, i]
+        return b.value, i.value, n.value
+
+    def free_device(self, ptr):
+        for p in list(self._dev_bufs):
+            if p.value == ptr:
+                self._dev_bufs.remove(p)
+        _check(load_library().fkm_device_free(self._h, C.c_void_p(ptr)))
+
+    def window_bins(self, configuration, bases, inv, n_positions):
+        out = np.empty(max(n_positions, 1), dtype=np.int32)
+        cfg = _cfg(configuration)
+        _check(load_library().fkm_debug_window_bins(self._h, C.byref(cfg), bases.ctypes.data, inv.ctypes.data, n_positions, out.ctypes.data))
+        return out[:n_positions]
+
+
+def host_alloc(nbytes) -> np.ndarray:
+    """Pinned host memory as a uint8 numpy array (kept alive by the returned array's base)."""
+    lib = load_library()
+    p = C.c_void_p()
+    _check(lib.fkm_host_alloc(nbytes, C.byref(p)))
+    buf = (C.c_uint8 * nbytes).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=np.uint8)
+    arr_ptr = p.value
+
+    class _Owner:
+        def __del__(self_inner):
+            lib.fkm_host_free(C.c_void_p(arr_ptr))
+    host_alloc._owners.append((_Owner(), buf))
+    return arr
+
+
+host_alloc._owners = []

@@ -1,0 +1,171 @@
+// fkm_host.cpp — host side of the path: FASTA record split + 2-bit packing (replaces
+// the FASTdoop record readers, SBKC:62-65,1009-1012), the per-bin text writer
+// (SBKC:550-606 sort path, SBKC:715-734 HT path) and the synthetic FASTA generator.
+#include "fkm_host.h"
+#include "fkm_common.h"
+#include "../../include/fastkmer_b200.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cerrno>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <sys/stat.h>
+#include <thread>
+#include <vector>
+
+int fkm_read_file(const char* path, std::vector<uint8_t>& out) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return fkm_set_error(FKM_EIO, "cannot open %s: %s", path, strerror(errno));
+    fseek(f, 0, SEEK_END);
+    long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    if (n < 0) { fclose(f); return fkm_set_error(FKM_EIO, "cannot size %s", path); }
+    out.resize((size_t)n);
+    size_t got = n ? fread(out.data(), 1, (size_t)n, f) : 0;
+    fclose(f);
+    if (got != (size_t)n) return fkm_set_error(FKM_EIO, "short read on %s", path);
+    return FKM_OK;
+}
+
+// Record split: a record starts at a '>' that begins a line; its
+// header runs to the end of that line; the value is every following byte up to
+// the next header with '\n' removed (SBKC:63-64 replaceAll("\n","")) and nothing
+// else stripped.  Bytes before the first header are ignored.  Each record is laid
+// out as its bytes followed by ONE invalid separator position.
+extern "C" int fkm_pack_fasta(const uint8_t* t, uint64_t n, uint64_t* bases, uint32_t* invalid,
+                              uint64_t cap_positions, uint64_t* n_positions, uint64_t* n_bases) {
+    static int8_t code[256]; static bool init = false;
+    if (!init) { for (int i = 0; i < 256; i++) code[i] = -1; code['A'] = 0; code['C'] = 1; code['G'] = 2; code['T'] = 3; init = true; }
+    uint64_t p = 0, nb = 0;
+    uint64_t bw = 0; uint32_t iw = 0;
+    const bool write = bases != nullptr;
+    auto put = [&](int c) {            // c in 0..3, or -1 for an invalid position
+        if (write) {
+            bw = (bw << 2) | (uint64_t)(c < 0 ? 0 : c); iw = (iw << 1) | (c < 0 ? 1u : 0u);
+            if ((p & 31) == 31) { bases[p >> 5] = bw; invalid[p >> 5] = iw; bw = 0; iw = 0; }
+        }
+        p++;
+    };
+    uint64_t i = 0; bool bol = true;
+    while (i < n && !(bol && t[i] == '>')) { bol = (t[i] == '\n'); i++; }
+    while (i < n) {
+        while (i < n && t[i] != '\n') i++;          // header line
+        if (i < n) i++;
+        bol = true;
+        while (i < n && !(bol && t[i] == '>')) {
+            uint8_t c = t[i];
+            bol = (c == '\n');
+            if (c != '\n') {
+                if (write && p >= cap_positions) return fkm_set_error(FKM_EINVAL, "packed buffer too small");
+                put(code[c]); nb++;
+            }
+            i++;
+        }
+        if (write && p >= cap_positions) return fkm_set_error(FKM_EINVAL, "packed buffer too small");
+        put(-1);                                     // record separator
+    }
+    if (write && (p & 31)) {                         // flush the partial word, tail positions invalid
+        unsigned rem = 32 - (unsigned)(p & 31);
+        bases[p >> 5] = bw << (2 * rem); invalid[p >> 5] = (iw << rem) | ((1u << rem) - 1u);
+    }
+    if (n_positions) *n_positions = p;
+    if (n_bases) *n_bases = nb;
+    return FKM_OK;
+}
+
+static int mkdir_p(const std::string& dir) {
+    std::string cur;
+    for (size_t i = 0; i <= dir.size(); i++) {
+        if (i == dir.size() || dir[i] == '/') {
+            if (!cur.empty() && cur != "/") {
+                if (mkdir(cur.c_str(), 0777) != 0 && errno != EEXIST) return -1;
+            }
+        }
+        if (i < dir.size()) cur += dir[i];
+    }
+    return 0;
+}
+
+int fkm_write_bins(const char* out_dir, int32_t B, int32_t k, int sorted, const uint64_t* out_base,
+                   const uint64_t* hi, const uint64_t* lo, const uint32_t* cnt) {
+    if (mkdir_p(out_dir) != 0) return fkm_set_error(FKM_EIO, "cannot create %s: %s", out_dir, strerror(errno));
+    std::atomic<int> next(0); std::atomic<int> failed(0);
+    unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    auto work = [&]() {
+        std::string buf;
+        for (;;) {
+            int b = next.fetch_add(1);
+            if (b >= B) break;
+            uint64_t a = out_base[b], e = out_base[b + 1];
+            if (a == e) continue;                                        // only non-empty bins get a file (SBKC:548,711)
+            buf.clear(); buf.reserve((size_t)(e - a) * (size_t)(k + 12) + 4);
+            char line[96];
+            for (uint64_t i = a; i < e; i++) {
+                unsigned __int128 v = ((unsigned __int128)hi[i] << 64) | lo[i];
+                for (int j = 0; j < k; j++) line[j] = "ACGT"[(unsigned)(v >> (2 * (k - 1 - j))) & 3u];   // UTIL:416-454
+                int len = k + snprintf(line + k, sizeof line - (size_t)k, "\t%u\n", cnt[i]);             // SBKC:581,729
+                buf.append(line, (size_t)len);
+            }
+            if (sorted) buf += "EOF";                                    // SBKC:606, no newline
+            std::string path = std::string(out_dir) + "/bin" + std::to_string(b);
+            FILE* f = fopen(path.c_str(), "wb");
+            if (!f || fwrite(buf.data(), 1, buf.size(), f) != buf.size()) failed = 1;
+            if (f) fclose(f);
+        }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; t++) th.emplace_back(work);
+    work();
+    for (auto& q : th) q.join();
+    if (failed) return fkm_set_error(FKM_EIO, "failed writing bin files under %s", out_dir);
+    return FKM_OK;
+}
+
+// SURVEY §8(d) synthetic reads as FASTA text: '>r<global index>\n<seq>\n'
+extern "C" int fkm_synth_fasta_host(const fkm_synth* s, uint8_t* out, uint64_t cap, uint64_t* n_bytes) {
+    if (!s || s->genome_len < s->read_len || s->read_len == 0) return fkm_set_error(FKM_EINVAL, "bad synthetic spec");
+    fkm::SynthSpec S{s->seed_genome, s->seed_reads, s->seed_errors, s->genome_len, s->n_reads, s->read_len, s->first_read};
+    auto hdr_len = [](uint64_t r) { uint64_t d = 1; while (r >= 10) { r /= 10; d++; } return 3 + d; };   // '>' 'r' digits '\n'
+    // sizes: prefix of header lengths is needed for parallel fill
+    const uint64_t R = S.R, L = S.L;
+    unsigned nt = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
+    std::vector<uint64_t> start(nt + 1, 0);
+    std::vector<uint64_t> first(nt + 1, 0);
+    for (unsigned t = 0; t <= nt; t++) first[t] = R * t / nt;
+    for (unsigned t = 0; t < nt; t++) {
+        uint64_t bytes = 0;
+        for (uint64_t r = first[t]; r < first[t + 1]; ) {       // runs of equal digit count
+            uint64_t g = S.first_read + r, d = hdr_len(g);
+            uint64_t lim = 10; while (lim <= g) lim *= 10;      // first index with one more digit
+            uint64_t e = std::min<uint64_t>(first[t + 1], r + (lim - g));
+            bytes += (e - r) * (d + L + 1);
+            r = e;
+        }
+        start[t + 1] = start[t] + bytes;
+    }
+    if (n_bytes) *n_bytes = start[nt];
+    if (!out) return FKM_OK;
+    if (cap < start[nt]) return fkm_set_error(FKM_EINVAL, "FASTA buffer too small");
+    auto work = [&](unsigned t) {
+        uint8_t* p = out + start[t];
+        char num[32];
+        for (uint64_t r = first[t]; r < first[t + 1]; r++) {
+            uint64_t g = S.first_read + r, pos, strand;
+            int n = snprintf(num, sizeof num, ">r%llu\n", (unsigned long long)g);
+            memcpy(p, num, (size_t)n); p += n;
+            fkm::synth_read(S, g, pos, strand);
+            for (uint64_t j = 0; j < L; j++) {
+                bool bad; uint32_t b = fkm::synth_base(S, g, j, pos, strand, bad);
+                *p++ = bad ? 'N' : (uint8_t)"ACGT"[b];
+            }
+            *p++ = '\n';
+        }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& q : th) q.join();
+    return FKM_OK;
+}

@@ -1,0 +1,821 @@
+// fkm_kernels.cuh — hand-written sm_100a kernels of the k-mer counting path.
+//
+// Stage map (SURVEY.md §2 "kernel inventory"; reference sites in brackets):
+//   k_scan<MODE>      K1+K2+K4  sliding window, signature, bin, super-k-mer records
+//                               [SBKC:75-157, UTIL:46-100,310-357,686-695]
+//   k_count_ht        K5+K6a    canonical k-mers -> open-addressing tables   [SBKC:694-705]
+//   k_compact_ht      K6a       tables -> dense per-bin (k-mer,count)        [SBKC:723-730]
+//   k_expand          K5        canonical k-mers -> key array (sort path)    [SBKC:484-524]
+//   k_radix_*         K6b       segmented LSD radix sort                     [SBKC:540-542]
+//   k_rle_*           K6b       run-length count of sorted keys              [SBKC:566-597]
+//   k_digest          K7        order-independent digest of the result
+//   k_synth           —         synthetic reads of SURVEY §8(d), packed, on device
+//
+// Layouts.  Input: `bases` 32 positions per u64, first position in the two MSBs;
+// `inv` 32 positions per u32, first position in the MSB.  All records of the
+// input are concatenated with ONE invalid separator position after each record,
+// so short reads and long sequences are the same problem: count every k-window
+// that holds no invalid position.
+//
+// Super-k-mer record (the "shuffle" payload).  NARROW (k <= 32): 16 bytes, two
+// u64 {w0,w1}: 60 bases MSB-first in w0[63:0],w1[63:8]; w1[7:0] = number of
+// k-mers n (1..61-k).  WIDE (32 < k <= 64): 32 bytes, four u64: 124 bases, n in
+// w3[7:0] (1..125-k).  A record holds n consecutive k-windows that share one
+// signature, i.e. n+k-1 bases.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "fkm_common.h"
+
+namespace fkm {
+
+static constexpr uint32_t kInvalidMin = 0xFFFFFFFFu;
+static constexpr int kScanThreads = 256;
+static constexpr int kSmemHistMaxB = 4096;
+
+struct __align__(16) key128 { uint64_t lo, hi; };
+struct __align__(16) SlotN { uint64_t key; uint32_t cnt; uint32_t pad; };
+struct __align__(32) SlotW { key128 key; uint32_t cnt; uint32_t pad[3]; };
+
+template <bool WIDE> struct Traits;
+template <> struct Traits<false> {
+    typedef uint64_t Key; typedef SlotN Slot;
+    static constexpr int kRecWords = 2, kRecBases = 60;
+};
+template <> struct Traits<true> {
+    typedef key128 Key; typedef SlotW Slot;
+    static constexpr int kRecWords = 4, kRecBases = 124;
+};
+
+// ------------------------------------------------------------------ small helpers
+__device__ __forceinline__ uint64_t swap_pairs(uint64_t x) {
+    return ((x & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((x & 0x5555555555555555ull) << 1);
+}
+// reverse complement of a right-aligned len-mer (len <= 32)
+__device__ __forceinline__ uint64_t revcomp64(uint64_t x, int len) {
+    return swap_pairs(__brevll(~x)) >> (64 - 2 * len);
+}
+__device__ __forceinline__ key128 revcomp128(key128 x, int len) {          // 32 < len <= 64
+    uint64_t rh = swap_pairs(__brevll(~x.lo)), rl = swap_pairs(__brevll(~x.hi));
+    int s = 128 - 2 * len;                                                  // 0..62
+    key128 r;
+    r.lo = s ? ((rl >> s) | (rh << (64 - s))) : rl;
+    r.hi = rh >> s;
+    return r;
+}
+__device__ __forceinline__ bool key_less(key128 a, key128 b) { return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo); }
+__device__ __forceinline__ bool key_eq(key128 a, key128 b) { return a.hi == b.hi && a.lo == b.lo; }
+__device__ __forceinline__ bool key_eq(uint64_t a, uint64_t b) { return a == b; }
+
+// norm of an m-mer given the value v and its reverse complement r (UTIL:46-100,
+// closed form of SURVEY App. A.5: allowed <=> no "AA" inside and prefix != "ACA").
+__device__ __forceinline__ bool mmer_allowed(uint32_t v, int m, uint32_t mmask) {
+    uint32_t nz = (v | (v >> 1)) & 0x55555555u;
+    uint32_t a = ~nz & 0x55555555u & mmask;
+    return ((a & (a >> 2)) == 0u) && ((v >> (2 * m - 6)) != 4u);
+}
+__device__ __forceinline__ uint32_t mmer_norm(uint32_t v, uint32_t r, int m, uint32_t mmask) {
+    uint32_t dflt = mmask + 1u;
+    uint32_t a = mmer_allowed(v, m, mmask) ? v : dflt;
+    uint32_t b = mmer_allowed(r, m, mmask) ? r : dflt;
+    return min(a, b);
+}
+
+// 64 bits starting at bit position `pos` of an MSB-first u32 bit array
+__device__ __forceinline__ uint64_t bits64_at(const uint32_t* a, uint32_t pos) {
+    uint32_t wi = pos >> 5, sh = pos & 31;
+    uint32_t w0 = a[wi], w1 = a[wi + 1], w2 = a[wi + 2];
+    uint32_t hi = __funnelshift_l(w1, w0, sh), lo = __funnelshift_l(w2, w1, sh);
+    return ((uint64_t)hi << 32) | lo;
+}
+// 64 bits (32 bases) starting at base position `pos` of an MSB-first u64 base array
+__device__ __forceinline__ uint64_t bases64_at(const uint64_t* a, uint32_t pos) {
+    uint32_t wi = pos >> 5, sh = 2 * (pos & 31);
+    uint64_t w0 = a[wi], w1 = a[wi + 1];
+    return sh ? ((w0 << sh) | (w1 >> (64 - sh))) : w0;
+}
+
+// ------------------------------------------------------------------ K1: scan
+struct ScanParams {
+    const uint64_t* bases; const uint32_t* inv;
+    uint64_t n_pos;                 // positions in the input
+    uint64_t n_words;               // u64 words in bases (= u32 words in inv)
+    int k, m, w;                    // w = k-m+1 m-mers per window
+    int nb;                         // blocks of w positions per thread
+    int wpad;                       // w rounded up to odd (bank-conflict-free stride)
+    uint32_t T;                     // window starts per tile = 256*nb*w
+    uint64_t n_tiles;
+    uint32_t B;
+    int cap;                        // max k-mers per record
+    int smem_hist;                  // 1: per-CTA histogram in shared memory (B <= 4096)
+    unsigned long long* hist_rec;   // [B] records per bin            (MODE 0)
+    unsigned long long* hist_kmer;  // [B] k-mers per bin             (MODE 0)
+    const unsigned long long* bin_base;   // [B+1] record offsets     (MODE 1)
+    unsigned long long* cursor;     // [B]                            (MODE 1)
+    void* records;                  //                                (MODE 1)
+    int32_t* dbg_bins;              // [n_pos]                        (MODE 2)
+};
+
+// Iterator over consecutive window starts of a tile; yields the window's
+// signature value (minimum norm over its w m-mers) or kInvalidMin.
+struct WinIter {
+    const uint32_t* s_h; const uint32_t* s_g; const uint32_t* s_inv;
+    int k, w, wpad;
+    int i, blk, off, bad_end; uint32_t invw;
+    __device__ __forceinline__ void init(int i0) {
+        i = i0; blk = i0 / w; off = i0 - blk * w;
+        bad_end = 0;
+        if (k > 1) {
+            uint64_t bits = bits64_at(s_inv, (uint32_t)i0) >> (64 - (k - 1));   // positions i0 .. i0+k-2
+            if (bits) bad_end = i0 + (k - 2 - (__ffsll((long long)bits) - 1)) + 1;
+        }
+        invw = s_inv[(i0 + k - 1) >> 5];
+    }
+    __device__ __forceinline__ uint32_t value() {
+        int p = i + k - 1;
+        if ((invw >> (31 - (p & 31))) & 1u) bad_end = p + 1;
+        if (i < bad_end) return kInvalidMin;
+        uint32_t h = s_h[blk * wpad + off];
+        uint32_t g = off ? s_g[(blk + 1) * wpad + off - 1] : s_g[blk * wpad + w - 1];
+        return min(h, g);
+    }
+    __device__ __forceinline__ void advance() {
+        i++; off++;
+        if (off == w) { off = 0; blk++; }
+        int p = i + k - 1;
+        if ((p & 31) == 0) invw = s_inv[p >> 5];
+    }
+};
+
+// MODE 0: histogram (records and k-mers per bin).  MODE 1: scatter the records.
+// MODE 2: per-window bin ids (test hook).
+//
+// One CTA per tile of T window starts (persistent, grid-strided).  Phase 1: each
+// thread rolls the forward and reverse-complement m-mer over blocks of w
+// positions, stores norm values and their in-block prefix minima; phase 2 turns
+// the norm values into in-block suffix minima (van Herk / Gil-Werman: the minimum
+// over any w consecutive positions is min(suffix[i], prefix[i+w-1])).  Phase 3:
+// each thread walks its chunk of windows, starts a run wherever the signature
+// value changes, extends it (possibly past its chunk) and emits <= cap k-mers per
+// record.  Runs are cut at tile boundaries; the reference's own cutting rule
+// (SBKC:102-136) is not observable.
+template <bool WIDE, int MODE>
+__global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int k = P.k, m = P.m, w = P.w, wpad = P.wpad, nb = P.nb;
+    const uint32_t T = P.T;
+    const int nblk = kScanThreads * nb + 1;
+    const uint32_t nwords = (T + (uint32_t)k + 31u) / 32u + 6u;
+    uint64_t* s_bases = reinterpret_cast<uint64_t*>(smem_raw);
+    uint32_t* s_inv = reinterpret_cast<uint32_t*>(s_bases + nwords);
+    uint32_t* s_h = s_inv + nwords + (nwords & 1u);
+    uint32_t* s_g = s_h + (size_t)nblk * wpad;
+    uint32_t* s_hist_rec = s_g + (size_t)nblk * wpad;
+    uint32_t* s_hist_kmer = s_hist_rec + P.B;
+    const uint32_t mmask = (m == 16) ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1u);
+
+    if (MODE == 0 && P.smem_hist) {
+        for (uint32_t b = tid; b < P.B; b += kScanThreads) { s_hist_rec[b] = 0; s_hist_kmer[b] = 0; }
+    }
+
+    for (uint64_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        const uint64_t t0 = tile * (uint64_t)T;
+        const uint64_t word0 = t0 >> 5;
+        __syncthreads();                       // previous tile fully consumed
+        for (uint32_t j = tid; j < nwords; j += kScanThreads) {
+            uint64_t gw = word0 + j;
+            bool in = gw < P.n_words;
+            s_bases[j] = in ? P.bases[gw] : 0ull;
+            uint32_t iv = in ? P.inv[gw] : 0xFFFFFFFFu;
+            // positions >= n_pos are invalid
+            uint64_t p0 = gw << 5;
+            if (p0 + 32 > P.n_pos) iv |= (p0 >= P.n_pos) ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (uint32_t)(P.n_pos - p0));
+            s_inv[j] = iv;
+        }
+        __syncthreads();
+
+        // ---- phase 1+2: norm values, in-block prefix (g) and suffix (h) minima
+        const int nmine = nb + (tid == kScanThreads - 1 ? 1 : 0);
+        for (int jb = 0; jb < nmine; jb++) {
+            const int blk = tid * nb + jb;
+            const uint32_t q0 = (uint32_t)blk * (uint32_t)w;
+            uint32_t v = (uint32_t)(bases64_at(s_bases, q0) >> (64 - 2 * m));
+            uint32_t r = (uint32_t)revcomp64(v, m);
+            uint32_t q = q0 + (uint32_t)m;                      // next base to enter
+            uint64_t bw = s_bases[q >> 5];
+            uint32_t* hrow = s_h + blk * wpad;
+            uint32_t* grow = s_g + blk * wpad;
+            uint32_t g = kInvalidMin;
+            for (int off = 0; off < w; off++) {
+                uint32_t nv = mmer_norm(v, r, m, mmask);
+                g = min(g, nv);
+                hrow[off] = nv; grow[off] = g;
+                uint32_t b = (uint32_t)(bw >> (62 - 2 * (q & 31))) & 3u;
+                v = ((v << 2) | b) & mmask;
+                r = (r >> 2) | ((3u - b) << (2 * m - 2));
+                q++;
+                if ((q & 31) == 0) bw = s_bases[q >> 5];
+            }
+            uint32_t h = hrow[w - 1];
+            for (int off = w - 2; off >= 0; off--) { h = min(h, hrow[off]); hrow[off] = h; }
+        }
+        __syncthreads();
+
+        // ---- phase 3: runs of equal signature value -> records
+        const int Ct = nb * w;
+        const int c0 = tid * Ct, c1 = c0 + Ct;
+        WinIter it; it.s_h = s_h; it.s_g = s_g; it.s_inv = s_inv; it.k = k; it.w = w; it.wpad = wpad;
+        if (MODE == 2) {
+            it.init(c0);
+            for (int i = c0; i < c1; i++) {
+                uint32_t v = it.value();
+                uint64_t gp = t0 + (uint64_t)i;
+                if (gp < P.n_pos) P.dbg_bins[gp] = (v == kInvalidMin) ? -1 : (int32_t)hash_to_bucket(v, P.B);
+                it.advance();
+            }
+            continue;
+        }
+        uint32_t prev = kInvalidMin;
+        if (c0 > 0) { it.init(c0 - 1); prev = it.value(); it.advance(); }
+        else it.init(0);
+        uint32_t cur = it.value();
+        while (it.i < c1) {
+            if (cur != kInvalidMin && cur != prev) {
+                const int a = it.i;
+                uint32_t nxt;
+                do {
+                    it.advance();
+                    nxt = (it.i < (int)T) ? it.value() : kInvalidMin;
+                } while (nxt == cur);
+                const int e = it.i;                            // run = windows [a, e)
+                const uint32_t bin = hash_to_bucket(cur, P.B);
+                for (int s = a; s < e; s += P.cap) {
+                    const int n = min(P.cap, e - s);
+                    if (MODE == 0) {
+                        if (P.smem_hist) { atomicAdd(&s_hist_rec[bin], 1u); atomicAdd(&s_hist_kmer[bin], (uint32_t)n); }
+                        else { atomicAdd(&P.hist_rec[bin], 1ull); atomicAdd(&P.hist_kmer[bin], (unsigned long long)n); }
+                    } else {
+                        const unsigned long long slot = P.bin_base[bin] + atomicAdd(&P.cursor[bin], 1ull);
+                        const uint32_t j = (uint32_t)s >> 5, sh = 2u * ((uint32_t)s & 31u);
+                        if constexpr (!WIDE) {
+                            uint64_t w0 = s_bases[j], w1 = s_bases[j + 1], w2 = s_bases[j + 2];
+                            uint64_t r0 = sh ? ((w0 << sh) | (w1 >> (64 - sh))) : w0;
+                            uint64_t r1 = sh ? ((w1 << sh) | (w2 >> (64 - sh))) : w1;
+                            r1 = (r1 & ~0xFFull) | (uint64_t)n;
+                            reinterpret_cast<ulonglong2*>(P.records)[slot] = make_ulonglong2(r0, r1);
+                        } else {
+                            uint64_t x0 = s_bases[j], x1 = s_bases[j + 1], x2 = s_bases[j + 2], x3 = s_bases[j + 3], x4 = s_bases[j + 4];
+                            uint64_t r0 = sh ? ((x0 << sh) | (x1 >> (64 - sh))) : x0;
+                            uint64_t r1 = sh ? ((x1 << sh) | (x2 >> (64 - sh))) : x1;
+                            uint64_t r2 = sh ? ((x2 << sh) | (x3 >> (64 - sh))) : x2;
+                            uint64_t r3 = sh ? ((x3 << sh) | (x4 >> (64 - sh))) : x3;
+                            r3 = (r3 & ~0xFFull) | (uint64_t)n;
+                            ulonglong2* dst = reinterpret_cast<ulonglong2*>(P.records) + 2 * slot;
+                            dst[0] = make_ulonglong2(r0, r1);
+                            dst[1] = make_ulonglong2(r2, r3);
+                        }
+                    }
+                }
+                prev = cur; cur = nxt;
+                // the window at it.i (value nxt) is evaluated by the next loop turn
+            } else {
+                prev = cur;
+                it.advance();
+                cur = (it.i < c1) ? it.value() : kInvalidMin;
+            }
+        }
+    }
+
+    if (MODE == 0 && P.smem_hist) {
+        __syncthreads();
+        for (uint32_t b = tid; b < P.B; b += kScanThreads) {
+            uint32_t r = s_hist_rec[b];
+            if (r) { atomicAdd(&P.hist_rec[b], (unsigned long long)r); atomicAdd(&P.hist_kmer[b], (unsigned long long)s_hist_kmer[b]); }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ record -> k-mers
+// Walks the n canonical k-mers of one record; F(key) is called once per k-mer.
+template <typename F>
+__device__ __forceinline__ void for_each_kmer_narrow(uint64_t w0, uint64_t w1, int k, F&& f) {
+    const int n = (int)(w1 & 0xFFull);
+    w1 &= ~0xFFull;
+    const int s = 64 - 2 * k;
+    uint64_t fwd = w0 >> s;
+    uint64_t rc = revcomp64(fwd, k);
+    for (int j = 0;;) {
+        f(min(fwd, rc));
+        if (++j == n) break;
+        w0 = (w0 << 2) | (w1 >> 62); w1 <<= 2;
+        fwd = w0 >> s;
+        rc = (rc >> 2) | ((3ull - (fwd & 3ull)) << (2 * k - 2));
+    }
+}
+template <typename F>
+__device__ __forceinline__ void for_each_kmer_wide(uint64_t w0, uint64_t w1, uint64_t w2, uint64_t w3, int k, F&& f) {
+    const int n = (int)(w3 & 0xFFull);
+    w3 &= ~0xFFull;
+    const int s = 128 - 2 * k;                 // 0..62
+    key128 fwd;
+    fwd.hi = w0 >> s; fwd.lo = s ? ((w0 << (64 - s)) | (w1 >> s)) : w1;
+    key128 rc = revcomp128(fwd, k);
+    for (int j = 0;;) {
+        f(key_less(rc, fwd) ? rc : fwd);
+        if (++j == n) break;
+        w0 = (w0 << 2) | (w1 >> 62); w1 = (w1 << 2) | (w2 >> 62); w2 = (w2 << 2) | (w3 >> 62); w3 <<= 2;
+        fwd.hi = w0 >> s; fwd.lo = s ? ((w0 << (64 - s)) | (w1 >> s)) : w1;
+        uint64_t nb = 3ull - (fwd.lo & 3ull);
+        rc.lo = (rc.lo >> 2) | (rc.hi << 62);
+        rc.hi = (rc.hi >> 2) | (nb << (2 * k - 66));
+    }
+}
+
+// largest b in [lo, hi) with base[b] <= r   (base ascending, base[lo] <= r < base[hi])
+__device__ __forceinline__ int find_bin(const unsigned long long* base, int lo, int hi, unsigned long long r) {
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (base[mid] <= r) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// ------------------------------------------------------------------ K6a: hash-table count
+__device__ __forceinline__ key128 cas128(key128* addr, key128 cmp, key128 val) {
+    key128 old;
+    asm volatile("{\n\t.reg .b128 c, v, o;\n\t"
+                 "mov.b128 c, {%2, %3};\n\t"
+                 "mov.b128 v, {%4, %5};\n\t"
+                 "atom.global.cas.b128 o, [%6], c, v;\n\t"
+                 "mov.b128 {%0, %1}, o;\n\t}"
+                 : "=l"(old.lo), "=l"(old.hi)
+                 : "l"(cmp.lo), "l"(cmp.hi), "l"(val.lo), "l"(val.hi), "l"(addr) : "memory");
+    return old;
+}
+
+struct CountParams {
+    const void* records;
+    unsigned long long rec_lo, rec_hi;          // record range of this batch
+    const unsigned long long* bin_base;         // [B+1] global record offsets
+    int bin_lo, bin_hi;                         // bins of this batch
+    void* table;                                // slots of this batch
+    const unsigned long long* tbl_base;         // [bin_hi-bin_lo+1] slot offsets inside `table`
+    unsigned long long* bin_distinct;           // [B] distinct k-mers per bin (claims)
+    int* overflow;                              // set when a probe sequence exceeds max_probe
+    int k; int max_probe;
+};
+
+// returns 1 if this call claimed a new slot, 0 if the key was present, -1 on overflow
+__device__ __forceinline__ int ht_insert(SlotN* tbl, unsigned long long size, uint64_t key, int max_probe) {
+    unsigned long long slot = __umul64hi(mix64(key), size);
+    for (int probe = 0; probe < max_probe; probe++) {
+        SlotN* s = tbl + slot;
+        uint64_t cur = __ldcg(&s->key);
+        int claimed = 0;
+        if (cur == ~0ull) {
+            cur = atomicCAS((unsigned long long*)&s->key, ~0ull, (unsigned long long)key);
+            if (cur == ~0ull) { cur = key; claimed = 1; }
+        }
+        if (cur == key) { atomicAdd(&s->cnt, 1u); return claimed; }
+        if (++slot == size) slot = 0;
+    }
+    return -1;
+}
+__device__ __forceinline__ int ht_insert(SlotW* tbl, unsigned long long size, key128 key, int max_probe) {
+    unsigned long long slot = __umul64hi(mix64(key.lo ^ mix64(key.hi)), size);
+    const key128 empty = {~0ull, ~0ull};
+    for (int probe = 0; probe < max_probe; probe++) {
+        SlotW* s = tbl + slot;
+        key128 cur;
+        cur.lo = __ldcg(&s->key.lo); cur.hi = __ldcg(&s->key.hi);
+        int claimed = 0;
+        // a half equal to all-ones may be a torn read of a slot being claimed: let the CAS decide
+        if (cur.lo == ~0ull || cur.hi == ~0ull) {
+            cur = cas128(&s->key, empty, key);
+            if (key_eq(cur, empty)) { cur = key; claimed = 1; }
+        }
+        if (key_eq(cur, key)) { atomicAdd(&s->cnt, 1u); return claimed; }
+        if (++slot == size) slot = 0;
+    }
+    return -1;
+}
+
+// One thread per super-k-mer record: roll the forward / reverse-complement
+// k-mer, take the canonical one, insert into the bin's table (counts start at
+// 0xFFFFFFFF because the table is cleared with an all-ones memset: real = cnt+1).
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_count_ht(const CountParams P) {
+    typedef typename Traits<WIDE>::Slot Slot;
+    const unsigned long long r = P.rec_lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int bin = -1; unsigned int claims = 0; bool ovf = false;
+    if (r < P.rec_hi) {
+        bin = find_bin(P.bin_base, P.bin_lo, P.bin_hi, r);
+        const unsigned long long tb = P.tbl_base[bin - P.bin_lo];
+        const unsigned long long size = P.tbl_base[bin - P.bin_lo + 1] - tb;
+        Slot* tbl = reinterpret_cast<Slot*>(P.table) + tb;
+        if constexpr (!WIDE) {
+            ulonglong2 rec = reinterpret_cast<const ulonglong2*>(P.records)[r];
+            for_each_kmer_narrow(rec.x, rec.y, P.k, [&](uint64_t key) {
+                int c = ht_insert(reinterpret_cast<SlotN*>(tbl), size, key, P.max_probe);
+                if (c < 0) ovf = true; else claims += (unsigned)c;
+            });
+        } else {
+            const ulonglong2* src = reinterpret_cast<const ulonglong2*>(P.records) + 2 * r;
+            ulonglong2 a = src[0], b = src[1];
+            for_each_kmer_wide(a.x, a.y, b.x, b.y, P.k, [&](key128 key) {
+                int c = ht_insert(reinterpret_cast<SlotW*>(tbl), size, key, P.max_probe);
+                if (c < 0) ovf = true; else claims += (unsigned)c;
+            });
+        }
+    }
+    if (ovf) *P.overflow = 1;
+    // warp-aggregated claim counts (records are bin-major, so a warp is almost always one bin)
+    int uniform;
+    __match_all_sync(0xFFFFFFFFu, bin, &uniform);
+    if (uniform) {
+        unsigned int tot = __reduce_add_sync(0xFFFFFFFFu, claims);
+        if ((threadIdx.x & 31) == 0 && bin >= 0 && tot) atomicAdd(&P.bin_distinct[bin], (unsigned long long)tot);
+    } else if (bin >= 0 && claims) {
+        atomicAdd(&P.bin_distinct[bin], (unsigned long long)claims);
+    }
+}
+
+struct CompactParams {
+    const void* table; unsigned long long n_slots;        // batch table space; every 1024-slot tile lies in one bin
+    const unsigned long long* tbl_base; int n_bins; int bin_lo;
+    const unsigned long long* out_base;                    // [B+1] global output offsets (entries)
+    unsigned long long out_origin;                         // global offset of the first entry of this batch's arrays
+    unsigned long long* out_cursor;                        // [B]
+    void* out_keys; uint32_t* out_cnt;                     // global output arrays
+};
+// table -> dense output.  Order inside a bin is slot order up to tile permutation
+// (the reference's HT order is fastutil's iteration order: unspecified, SBKC:723).
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_compact_ht(const CompactParams P) {
+    typedef typename Traits<WIDE>::Slot Slot;
+    typedef typename Traits<WIDE>::Key Key;
+    __shared__ unsigned int s_warp[8];
+    __shared__ unsigned long long s_base;
+    const unsigned long long tile0 = (unsigned long long)blockIdx.x * 1024ull;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const Slot* tbl = reinterpret_cast<const Slot*>(P.table);
+    Key keys[4]; uint32_t cnts[4]; unsigned int have = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        unsigned long long s = tile0 + (unsigned long long)j * 256ull + threadIdx.x;
+        cnts[j] = 0xFFFFFFFFu;
+        if (s < P.n_slots) {
+            if constexpr (!WIDE) {
+                ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&tbl[s]);
+                *reinterpret_cast<uint64_t*>(&keys[j]) = v.x; cnts[j] = (uint32_t)v.y;
+                if (v.x != ~0ull) have |= 1u << j;
+            } else {
+                const ulonglong2* p = reinterpret_cast<const ulonglong2*>(&tbl[s]);
+                ulonglong2 kv = p[0]; ulonglong2 cv = p[1];
+                key128 kk; kk.lo = kv.x; kk.hi = kv.y;
+                *reinterpret_cast<key128*>(&keys[j]) = kk; cnts[j] = (uint32_t)cv.x;
+                if (!(kv.x == ~0ull && kv.y == ~0ull)) have |= 1u << j;
+            }
+        }
+    }
+    unsigned int c = __popc(have);
+    unsigned int incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { unsigned int t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned int wbase = 0, total = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { unsigned int t = s_warp[i]; if (i < warp) wbase += t; total += t; }
+    if (total == 0) return;
+    if (threadIdx.x == 0) {
+        int bin_local = find_bin(P.tbl_base, 0, P.n_bins, tile0);
+        int bin = P.bin_lo + bin_local;
+        s_base = P.out_base[bin] - P.out_origin + atomicAdd(&P.out_cursor[bin], (unsigned long long)total);
+    }
+    __syncthreads();
+    unsigned long long o = s_base + wbase + (incl - c);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if (have & (1u << j)) {
+            reinterpret_cast<Key*>(P.out_keys)[o] = keys[j];
+            P.out_cnt[o] = cnts[j] + 1u;
+            o++;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ K5 (sort path): expand
+struct ExpandParams {
+    const void* records; unsigned long long rec_lo, rec_hi;
+    const unsigned long long* bin_base; int bin_lo, bin_hi;
+    const unsigned long long* key_base;       // [bin_hi-bin_lo+1] key offsets inside the batch key array
+    unsigned long long* key_cursor;           // [B]
+    void* keys; int k;
+};
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_expand(const ExpandParams P) {
+    const unsigned long long r = P.rec_lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= P.rec_hi) return;
+    const int bin = find_bin(P.bin_base, P.bin_lo, P.bin_hi, r);
+    if constexpr (!WIDE) {
+        ulonglong2 rec = reinterpret_cast<const ulonglong2*>(P.records)[r];
+        const int n = (int)(rec.y & 0xFFull);
+        unsigned long long o = P.key_base[bin - P.bin_lo] + atomicAdd(&P.key_cursor[bin], (unsigned long long)n);
+        uint64_t* dst = reinterpret_cast<uint64_t*>(P.keys);
+        for_each_kmer_narrow(rec.x, rec.y, P.k, [&](uint64_t key) { dst[o++] = key; });
+    } else {
+        const ulonglong2* src = reinterpret_cast<const ulonglong2*>(P.records) + 2 * r;
+        ulonglong2 a = src[0], b = src[1];
+        const int n = (int)(b.y & 0xFFull);
+        unsigned long long o = P.key_base[bin - P.bin_lo] + atomicAdd(&P.key_cursor[bin], (unsigned long long)n);
+        key128* dst = reinterpret_cast<key128*>(P.keys);
+        for_each_kmer_wide(a.x, a.y, b.x, b.y, P.k, [&](key128 key) { dst[o++] = key; });
+    }
+}
+
+// ------------------------------------------------------------------ K6b: segmented LSD radix sort
+// Segments = bins of the batch.  Tiles of 2048 keys never straddle a segment.
+static constexpr int kSortTile = 2048;
+struct SortParams {
+    const void* in; void* out;
+    const unsigned long long* seg_base;      // [n_seg+1] key offsets
+    const unsigned int* tile_seg;            // [n_tiles] segment of each tile
+    const unsigned int* seg_tile0;           // [n_seg+1] first tile of each segment
+    unsigned int* tile_hist;                 // [n_tiles*256]
+    unsigned int n_tiles; int n_seg; int shift;   // digit = (key >> shift) & 255
+};
+template <bool WIDE> __device__ __forceinline__ unsigned int digit_of(typename Traits<WIDE>::Key key, int shift);
+template <> __device__ __forceinline__ unsigned int digit_of<false>(uint64_t key, int shift) { return (unsigned int)(key >> shift) & 255u; }
+template <> __device__ __forceinline__ unsigned int digit_of<true>(key128 key, int shift) {
+    return (unsigned int)((shift >= 64) ? (key.hi >> (shift - 64)) : (key.lo >> shift)) & 255u;
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_radix_hist(const SortParams P) {
+    typedef typename Traits<WIDE>::Key Key;
+    __shared__ unsigned int s_h[256];
+    const unsigned int t = blockIdx.x;
+    const unsigned int seg = P.tile_seg[t];
+    const unsigned long long lo = P.seg_base[seg] + (unsigned long long)(t - P.seg_tile0[seg]) * kSortTile;
+    const unsigned long long hi = min(lo + (unsigned long long)kSortTile, P.seg_base[seg + 1]);
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    const Key* in = reinterpret_cast<const Key*>(P.in);
+    for (unsigned long long i = lo + threadIdx.x; i < hi; i += 256) atomicAdd(&s_h[digit_of<WIDE>(in[i], P.shift)], 1u);
+    __syncthreads();
+    P.tile_hist[(size_t)t * 256 + threadIdx.x] = s_h[threadIdx.x];
+}
+
+// one CTA per segment, thread d owns digit d: tile_hist[t][d] <- exclusive offset of
+// (digit d, tile t) inside the segment (digit-major, tile-minor).
+__global__ void __launch_bounds__(256) k_radix_scan(const SortParams P) {
+    __shared__ unsigned int s_tot[256];
+    const int seg = blockIdx.x;
+    const unsigned int t0 = P.seg_tile0[seg], t1 = P.seg_tile0[seg + 1];
+    const int d = threadIdx.x;
+    unsigned int tot = 0;
+    for (unsigned int t = t0; t < t1; t++) tot += P.tile_hist[(size_t)t * 256 + d];
+    s_tot[d] = tot;
+    __syncthreads();
+    // exclusive scan over digits (256 values) — simple Hillis-Steele in shared memory
+    unsigned int v = tot;
+    for (int o = 1; o < 256; o <<= 1) {
+        unsigned int add = (d >= o) ? s_tot[d - o] : 0u;
+        __syncthreads();
+        v += add; s_tot[d] = v;
+        __syncthreads();
+    }
+    unsigned int run = v - tot;
+    for (unsigned int t = t0; t < t1; t++) {
+        unsigned int c = P.tile_hist[(size_t)t * 256 + d];
+        P.tile_hist[(size_t)t * 256 + d] = run;
+        run += c;
+    }
+}
+
+// stable scatter of one tile: warp `wi` owns keys [wi*256, wi*256+256) of the tile
+// in 8 rounds of 32; ranks come from match.any peer masks and per-warp digit counters.
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_radix_scatter(const SortParams P) {
+    typedef typename Traits<WIDE>::Key Key;
+    __shared__ unsigned int s_wc[8][256];
+    __shared__ unsigned int s_off[256];
+    const unsigned int t = blockIdx.x;
+    const unsigned int seg = P.tile_seg[t];
+    const unsigned long long seg0 = P.seg_base[seg];
+    const unsigned long long lo = seg0 + (unsigned long long)(t - P.seg_tile0[seg]) * kSortTile;
+    const unsigned long long hi = min(lo + (unsigned long long)kSortTile, P.seg_base[seg + 1]);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 8 * 256; i += 256) (&s_wc[0][0])[i] = 0;
+    s_off[threadIdx.x] = P.tile_hist[(size_t)t * 256 + threadIdx.x];
+    __syncthreads();
+    const Key* in = reinterpret_cast<const Key*>(P.in);
+    Key* out = reinterpret_cast<Key*>(P.out);
+    Key keys[8]; unsigned int rank[8]; unsigned int dig[8];
+#pragma unroll
+    for (int rd = 0; rd < 8; rd++) {
+        const unsigned long long i = lo + (unsigned long long)(warp * 256 + rd * 32 + lane);
+        const bool ok = i < hi;
+        if (ok) keys[rd] = in[i];
+        const unsigned int d = ok ? digit_of<WIDE>(keys[rd], P.shift) : (256u + (unsigned)lane);
+        const unsigned int peers = __match_any_sync(0xFFFFFFFFu, d);
+        unsigned int old = 0;
+        if (ok) old = s_wc[warp][d];
+        __syncwarp();
+        if (ok && (peers & ((1u << lane) - 1u)) == 0u) s_wc[warp][d] = old + __popc(peers);
+        __syncwarp();
+        rank[rd] = old + __popc(peers & ((1u << lane) - 1u));
+        dig[rd] = d;
+    }
+    __syncthreads();
+    {   // exclusive prefix over the 8 warps for digit = threadIdx.x
+        unsigned int run = 0;
+#pragma unroll
+        for (int wi = 0; wi < 8; wi++) { unsigned int c = s_wc[wi][threadIdx.x]; s_wc[wi][threadIdx.x] = run; run += c; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rd = 0; rd < 8; rd++) {
+        if (dig[rd] < 256u) out[seg0 + s_off[dig[rd]] + s_wc[warp][dig[rd]] + rank[rd]] = keys[rd];
+    }
+}
+
+// ------------------------------------------------------------------ K6b: run-length count of sorted keys
+struct RleParams {
+    const void* keys;                        // sorted inside each segment
+    const unsigned long long* seg_base; const unsigned int* tile_seg; const unsigned int* seg_tile0;
+    unsigned int n_tiles; int bin_lo;
+    unsigned int* tile_heads;                // [n_tiles+1] heads per tile, then exclusive scan in place
+    unsigned long long* bin_distinct;        // [B]
+    unsigned long long out_off;              // global entry offset of this batch
+    void* out_keys; uint32_t* out_cnt;       // global output
+    unsigned long long* first_idx;           // [D_batch+1] scratch: batch-relative index of each run head
+    unsigned long long n_keys;               // keys in batch
+};
+template <bool WIDE, int PASS>   // PASS 0: count heads per tile; PASS 1: write heads
+__global__ void __launch_bounds__(256) k_rle(const RleParams P) {
+    typedef typename Traits<WIDE>::Key Key;
+    __shared__ unsigned int s_warp[8];
+    const unsigned int t = blockIdx.x;
+    const unsigned int seg = P.tile_seg[t];
+    const unsigned long long seg0 = P.seg_base[seg];
+    const unsigned long long lo = seg0 + (unsigned long long)(t - P.seg_tile0[seg]) * kSortTile;
+    const unsigned long long hi = min(lo + (unsigned long long)kSortTile, P.seg_base[seg + 1]);
+    const Key* keys = reinterpret_cast<const Key*>(P.keys);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // thread owns 8 consecutive keys (blocked) so that ranks follow key order
+    const unsigned long long i0 = lo + (unsigned long long)threadIdx.x * 8ull;
+    unsigned int flags = 0;
+    Key prev;
+    if (i0 < hi && i0 > seg0) prev = keys[i0 - 1];
+    Key mine[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const unsigned long long i = i0 + j;
+        if (i < hi) {
+            mine[j] = keys[i];
+            bool head = (i == seg0) || !key_eq(mine[j], prev);
+            if (head) flags |= 1u << j;
+            prev = mine[j];
+        }
+    }
+    unsigned int c = __popc(flags), incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { unsigned int v = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += v; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned int wbase = 0, total = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { unsigned int v = s_warp[i]; if (i < warp) wbase += v; total += v; }
+    if (PASS == 0) {
+        if (threadIdx.x == 0) {
+            P.tile_heads[t] = total;
+            if (total) atomicAdd(&P.bin_distinct[P.bin_lo + (int)seg], (unsigned long long)total);
+        }
+    } else {
+        unsigned long long o = (unsigned long long)P.tile_heads[t] + wbase + (incl - c);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (flags & (1u << j)) {
+                reinterpret_cast<Key*>(P.out_keys)[P.out_off + o] = mine[j];
+                P.first_idx[o] = i0 + j;
+                o++;
+            }
+        }
+    }
+}
+// exclusive scan of a u32 array in place by one CTA; a[n] receives the total
+__global__ void __launch_bounds__(1024) k_scan_u32(unsigned int* a, unsigned int n) {
+    __shared__ unsigned int s_w[32];
+    __shared__ unsigned int s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (unsigned int base = 0; base < n; base += 1024) {
+        unsigned int i = base + threadIdx.x;
+        unsigned int v = (i < n) ? a[i] : 0u, incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { unsigned int t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        unsigned int wb = 0, tot = 0;
+        for (int j = 0; j < 32; j++) { unsigned int t = s_w[j]; if (j < warp) wb += t; tot += t; }
+        unsigned int carry = s_carry;
+        if (i < n) a[i] = carry + wb + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) a[n] = s_carry;
+}
+// counts of the runs: cnt[j] = first[j+1] - first[j], first[D] = n_keys
+__global__ void k_rle_counts(const unsigned long long* first, unsigned long long n_heads, unsigned long long n_keys,
+                             uint32_t* out_cnt, unsigned long long out_off) {
+    unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_heads) return;
+    unsigned long long nxt = (j + 1 < n_heads) ? first[j + 1] : n_keys;
+    out_cnt[out_off + j] = (uint32_t)(nxt - first[j]);
+}
+
+// exclusive scan over bins [bin_lo, bin_hi) of bin_distinct -> out_base (global
+// offsets continue from out_base[bin_lo], which the host has set).  One CTA.
+__global__ void __launch_bounds__(256) k_bin_offsets(const unsigned long long* bin_distinct, unsigned long long* out_base,
+                                                     int bin_lo, int bin_hi, unsigned long long* batch_total) {
+    __shared__ unsigned long long s_w[8];
+    __shared__ unsigned long long s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = out_base[bin_lo];
+    __syncthreads();
+    const unsigned long long start = s_carry;
+    for (int base = bin_lo; base < bin_hi; base += 256) {
+        int b = base + threadIdx.x;
+        unsigned long long v = (b < bin_hi) ? bin_distinct[b] : 0ull, incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        unsigned long long wb = 0, tot = 0;
+        for (int j = 0; j < 8; j++) { unsigned long long t = s_w[j]; if (j < warp) wb += t; tot += t; }
+        unsigned long long carry = s_carry;
+        if (b < bin_hi) out_base[b + 1] = carry + wb + incl;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *batch_total = s_carry - start;
+}
+
+// ------------------------------------------------------------------ K7: digest
+struct DigestParams {
+    const void* keys; const uint32_t* cnt; const unsigned long long* out_base; int B;
+    unsigned long long n; unsigned long long origin;  // entries in this chunk, global offset of its first entry
+    unsigned long long* acc;                          // acc[0]=sum(h*cnt) acc[1]=xor(mix(h+cnt)) acc[2]=sum(cnt)
+};
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_digest(const DigestParams P) {
+    typedef typename Traits<WIDE>::Key Key;
+    unsigned long long s = 0, x = 0, c = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        int bin = find_bin(P.out_base, 0, P.B, P.origin + i);
+        uint64_t hi, lo;
+        if constexpr (!WIDE) { hi = 0; lo = reinterpret_cast<const uint64_t*>(P.keys)[i]; }
+        else { key128 kk = reinterpret_cast<const key128*>(P.keys)[i]; hi = kk.hi; lo = kk.lo; }
+        uint32_t n = P.cnt[i];
+        uint64_t h = entry_hash((uint32_t)bin, hi, lo);
+        s += h * (uint64_t)n; x ^= mix64(h + n); c += n;
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        s += __shfl_xor_sync(0xFFFFFFFFu, s, d); x ^= __shfl_xor_sync(0xFFFFFFFFu, x, d); c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&P.acc[0], s); atomicXor(&P.acc[1], x); atomicAdd(&P.acc[2], c); }
+}
+
+// ------------------------------------------------------------------ synthetic reads
+struct SynthParams { SynthSpec S; uint64_t n_pos, n_words; uint64_t* bases; uint32_t* inv; };
+// one thread per 32 positions; position p -> read p/(L+1), offset p%(L+1); offset L is the separator
+__global__ void __launch_bounds__(256) k_synth(const SynthParams P) {
+    uint64_t wi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= P.n_words) return;
+    const uint64_t L = P.S.L;
+    uint64_t p = wi << 5;
+    uint64_t r = p / (L + 1), j = p - r * (L + 1);
+    uint64_t pos = 0, strand = 0; bool have = false;
+    uint64_t bw = 0; uint32_t iw = 0;
+    for (int t = 0; t < 32; t++, p++) {
+        uint32_t b = 0; bool bad = true;
+        if (p < P.n_pos && j < L) {
+            if (!have) { synth_read(P.S, P.S.first_read + r, pos, strand); have = true; }
+            b = synth_base(P.S, P.S.first_read + r, j, pos, strand, bad);
+            if (bad) b = 0;
+        }
+        bw = (bw << 2) | b; iw = (iw << 1) | (bad ? 1u : 0u);
+        if (++j == L + 1) { j = 0; r++; have = false; }
+    }
+    P.bases[wi] = bw; P.inv[wi] = iw;
+}
+
+}  // namespace fkm

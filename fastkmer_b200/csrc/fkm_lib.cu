@@ -1,0 +1,607 @@
+// fkm_lib.cu — host pipeline and C ABI (include/fastkmer_b200.h) of the B200 path.
+//
+// Replaces everything behind SparkBinKmerCounter.executeJob (SBKC:989-1046):
+//   mapPartitions(getSuperKmers)        -> k_scan<MODE 0> (exact bin histogram) + k_scan<MODE 1> (scatter)
+//   reduceByKey(_ ++ _)  (the shuffle)  -> bin-major record buffer sized by the exact histogram
+//   foreachPartition(extractKXmersHT)   -> k_count_ht + k_compact_ht over batches of bins
+//   foreachPartition(extractKXmers)     -> k_expand + segmented radix sort + k_rle
+// There is no CPU fallback: every entry point needs a CUDA device.
+#include "fkm_kernels.cuh"
+#include "fkm_host.h"
+#include "../../include/fastkmer_b200.h"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace fkm;
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+
+int fkm_set_error(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fkm_set_error(e_ == cudaErrorMemoryAllocation ? FKM_ENOMEM : FKM_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
+#define CKL() do { g_launches++; ctx->job_launches++; CK(cudaGetLastError()); } while (0)
+
+struct fkm_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int n_sm = 0;
+    size_t smem_optin = 0;
+    double table_budget_bytes = 4.0 * (1ull << 30);
+    double sort_budget_keys = 256.0 * (1 << 20);
+    double load_factor = 0.6;
+    uint64_t job_launches = 0;
+    cudaEvent_t ev[10];
+};
+
+struct Chunk { void* keys = nullptr; uint32_t* cnt = nullptr; uint64_t n = 0; };
+struct fkm_result {
+    int device = 0;
+    int32_t B = 0, k = 0; bool wide = false; bool sorted = false;
+    std::vector<Chunk> chunks;
+    std::vector<uint64_t> out_base;      // B+1
+    uint64_t total = 0;
+};
+
+extern "C" const char* fkm_last_error(void) { return g_err.c_str(); }
+extern "C" uint64_t fkm_total_launches(void) { return g_launches.load(); }
+
+extern "C" int fkm_ctx_create(int device, void* stream, fkm_ctx** out) {
+    if (!out) return fkm_set_error(FKM_EINVAL, "out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fkm_set_error(FKM_ECUDA, "no CUDA device (%s); fastkmer_b200 has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0) CK(cudaGetDevice(&device));
+    if (device >= n) return fkm_set_error(FKM_EINVAL, "device %d out of range (%d devices)", device, n);
+    CK(cudaSetDevice(device));
+    fkm_ctx* c = new fkm_ctx();
+    c->device = device;
+    if (stream) c->stream = (cudaStream_t)stream;
+    else { CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, device));
+    c->n_sm = p.multiProcessorCount; c->smem_optin = p.sharedMemPerBlockOptin;
+    for (auto& ev : c->ev) CK(cudaEventCreate(&ev));
+    *out = c;
+    return FKM_OK;
+}
+extern "C" void fkm_ctx_destroy(fkm_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (auto& ev : c->ev) cudaEventDestroy(ev);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+extern "C" int fkm_ctx_sync(fkm_ctx* c) { CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->stream)); return FKM_OK; }
+extern "C" int fkm_ctx_set(fkm_ctx* c, const char* name, double v) {
+    if (!c || !name) return fkm_set_error(FKM_EINVAL, "null argument");
+    if (!strcmp(name, "table_budget_bytes")) c->table_budget_bytes = v;
+    else if (!strcmp(name, "sort_budget_keys")) c->sort_budget_keys = v;
+    else if (!strcmp(name, "load_factor")) c->load_factor = v;
+    else return fkm_set_error(FKM_EINVAL, "unknown knob %s", name);
+    return FKM_OK;
+}
+
+static int validate(const fkm_config* cfg, int32_t* B) {
+    if (!cfg) return fkm_set_error(FKM_EINVAL, "cfg is NULL");
+    if (cfg->m < 3 || cfg->m > 15) return fkm_set_error(FKM_EINVAL, "m=%d unsupported (3 <= m <= 15; UTIL:78 overflows Int beyond 15)", cfg->m);
+    if (cfg->k < cfg->m || cfg->k > 64) return fkm_set_error(FKM_EINVAL, "k=%d unsupported (m <= k <= 64)", cfg->k);
+    if (cfg->max_b < 1) return fkm_set_error(FKM_EINVAL, "B=%d must be >= 1", cfg->max_b);
+    if (!cfg->use_ht && cfg->x < 1) return fkm_set_error(FKM_EINVAL, "x=%d: the reference's sort path fails for x < 1 (SBKC:495-508)", cfg->x);
+    int64_t b = std::min<int64_t>((int64_t)1 << (2 * cfg->m), (int64_t)cfg->max_b);     // TCFG:32
+    *B = (int32_t)b;
+    return FKM_OK;
+}
+
+extern "C" int fkm_derive(const fkm_config* cfg, int32_t* b, char* out_dir, size_t cap) {
+    int32_t B = 0; int rc = validate(cfg, &B); if (rc) return rc;
+    if (b) *b = B;
+    if (out_dir) {
+        std::string s = std::string(cfg->output_directory ? cfg->output_directory : "") + (cfg->prefix ? cfg->prefix : "") +
+                        "k" + std::to_string(cfg->k) + "_m" + std::to_string(cfg->m) + "_x" + std::to_string(cfg->x) +
+                        "_b" + std::to_string(B) + "_s" + std::to_string(cfg->sequence_type);       // TCFG:33
+        if (s.size() + 1 > cap) return fkm_set_error(FKM_EINVAL, "out_dir buffer too small");
+        memcpy(out_dir, s.c_str(), s.size() + 1);
+    }
+    return FKM_OK;
+}
+
+extern "C" int fkm_host_alloc(size_t bytes, void** out) { CK(cudaMallocHost(out, bytes)); return FKM_OK; }
+extern "C" void fkm_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ------------------------------------------------------------------ scan setup
+struct ScanSetup { ScanParams P; size_t smem; int grid; };
+template <bool WIDE, int MODE>
+static int scan_setup(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const void* d_bases, const void* d_inv, uint64_t n_pos, ScanSetup* S) {
+    ScanParams& P = S->P;
+    memset(&P, 0, sizeof P);
+    P.bases = (const uint64_t*)d_bases; P.inv = (const uint32_t*)d_inv;
+    P.n_pos = n_pos; P.n_words = (n_pos + 31) / 32;
+    P.k = cfg->k; P.m = cfg->m; P.w = cfg->k - cfg->m + 1;
+    P.nb = std::max(1, (40 + P.w / 2) / P.w);
+    P.wpad = P.w | 1;
+    P.T = (uint32_t)(kScanThreads * P.nb * P.w);
+    P.n_tiles = (n_pos + P.T - 1) / P.T;
+    P.B = (uint32_t)B;
+    P.cap = (cfg->k > 32) ? (125 - cfg->k) : (61 - cfg->k);
+    P.smem_hist = (MODE == 0 && B <= kSmemHistMaxB) ? 1 : 0;
+    const uint32_t nwords = (P.T + (uint32_t)P.k + 31u) / 32u + 6u;
+    const int nblk = kScanThreads * P.nb + 1;
+    S->smem = (size_t)nwords * 8 + (size_t)(nwords + (nwords & 1u)) * 4 + (size_t)nblk * P.wpad * 8 + (P.smem_hist ? (size_t)B * 8 : 0);
+    if (S->smem > ctx->smem_optin) return fkm_set_error(FKM_EINVAL, "scan tile needs %zu B shared memory > %zu", S->smem, ctx->smem_optin);
+    CK(cudaFuncSetAttribute(k_scan<WIDE, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan<WIDE, MODE>, kScanThreads, S->smem));
+    if (occ < 1) occ = 1;
+    S->grid = (int)std::min<uint64_t>(P.n_tiles, (uint64_t)ctx->n_sm * occ);
+    if (S->grid < 1) S->grid = 1;
+    return FKM_OK;
+}
+
+static inline uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------ the pipeline
+template <bool WIDE>
+static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const void* d_bases, const void* d_inv,
+                        uint64_t n_pos, fkm_result* res, fkm_stats* st) {
+    typedef typename Traits<WIDE>::Key Key;
+    typedef typename Traits<WIDE>::Slot Slot;
+    cudaStream_t s = ctx->stream;
+    const int rec_bytes = Traits<WIDE>::kRecWords * 8;
+    res->B = B; res->k = cfg->k; res->wide = WIDE; res->sorted = !cfg->use_ht; res->device = ctx->device;
+    res->out_base.assign((size_t)B + 1, 0);
+
+    unsigned long long *d_hist_rec = nullptr, *d_hist_kmer = nullptr, *d_bin_base = nullptr, *d_cursor = nullptr,
+                       *d_distinct = nullptr, *d_out_base = nullptr, *d_small = nullptr, *d_tbl_base = nullptr;
+    void* d_records = nullptr; void* d_table = nullptr; int* d_ovf = nullptr;
+    void *d_keysA = nullptr, *d_keysB = nullptr; unsigned int *d_tile_seg = nullptr, *d_seg_tile0 = nullptr, *d_tile_hist = nullptr, *d_tile_heads = nullptr;
+    unsigned long long* d_first = nullptr;
+    int rc = FKM_OK;
+    // everything below frees through this lambda
+    auto cleanup = [&]() {
+        cudaFree(d_hist_rec); cudaFree(d_hist_kmer); cudaFree(d_bin_base); cudaFree(d_cursor); cudaFree(d_distinct);
+        cudaFree(d_out_base); cudaFree(d_small); cudaFree(d_tbl_base); cudaFree(d_records); cudaFree(d_table); cudaFree(d_ovf);
+        cudaFree(d_keysA); cudaFree(d_keysB); cudaFree(d_tile_seg); cudaFree(d_seg_tile0); cudaFree(d_tile_hist); cudaFree(d_tile_heads); cudaFree(d_first);
+    };
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); \
+    return fkm_set_error(e_ == cudaErrorMemoryAllocation ? FKM_ENOMEM : FKM_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } } while (0)
+#define CKLC() do { g_launches++; ctx->job_launches++; CKC(cudaGetLastError()); } while (0)
+
+    const size_t bB = (size_t)B * 8;
+    CKC(cudaMalloc(&d_hist_rec, bB)); CKC(cudaMalloc(&d_hist_kmer, bB)); CKC(cudaMalloc(&d_bin_base, bB + 8));
+    CKC(cudaMalloc(&d_cursor, bB)); CKC(cudaMalloc(&d_distinct, bB)); CKC(cudaMalloc(&d_out_base, bB + 8));
+    CKC(cudaMalloc(&d_small, 64)); CKC(cudaMalloc(&d_ovf, 4)); CKC(cudaMalloc(&d_tbl_base, bB + 8));
+    CKC(cudaMemsetAsync(d_hist_rec, 0, bB, s)); CKC(cudaMemsetAsync(d_hist_kmer, 0, bB, s));
+    CKC(cudaMemsetAsync(d_cursor, 0, bB, s)); CKC(cudaMemsetAsync(d_distinct, 0, bB, s));
+    CKC(cudaMemsetAsync(d_out_base, 0, bB + 8, s)); CKC(cudaMemsetAsync(d_small, 0, 64, s));
+
+    // ---- stage 1: exact histogram (records and k-mers per bin)
+    CKC(cudaEventRecord(ctx->ev[0], s));
+    std::vector<unsigned long long> h_rec((size_t)B), h_kmer((size_t)B), h_base((size_t)B + 1);
+    {
+        ScanSetup S; rc = scan_setup<WIDE, 0>(ctx, cfg, B, d_bases, d_inv, n_pos, &S); if (rc) { cleanup(); return rc; }
+        S.P.hist_rec = d_hist_rec; S.P.hist_kmer = d_hist_kmer;
+        if (n_pos) { k_scan<WIDE, 0><<<S.grid, kScanThreads, S.smem, s>>>(S.P); CKLC(); }
+    }
+    CKC(cudaEventRecord(ctx->ev[1], s));
+    CKC(cudaMemcpyAsync(h_rec.data(), d_hist_rec, bB, cudaMemcpyDeviceToHost, s));
+    CKC(cudaMemcpyAsync(h_kmer.data(), d_hist_kmer, bB, cudaMemcpyDeviceToHost, s));
+    CKC(cudaStreamSynchronize(s));
+    st->d2h_bytes += 2 * bB;
+    uint64_t n_rec = 0, n_kmers = 0, nonempty = 0;
+    for (int b = 0; b < B; b++) { h_base[(size_t)b] = n_rec; n_rec += h_rec[(size_t)b]; n_kmers += h_kmer[(size_t)b]; nonempty += h_rec[(size_t)b] ? 1 : 0; }
+    h_base[(size_t)B] = n_rec;
+    st->n_kmers = n_kmers; st->n_superkmers = n_rec; st->superkmer_bytes = n_rec * rec_bytes; st->n_nonempty_bins = nonempty;
+
+    // ---- stage 2: scatter super-k-mer records, bin-major (the "shuffle")
+    CKC(cudaMalloc(&d_records, std::max<size_t>(16, (size_t)n_rec * rec_bytes)));
+    CKC(cudaMemcpyAsync(d_bin_base, h_base.data(), bB + 8, cudaMemcpyHostToDevice, s));
+    st->h2d_bytes += bB + 8;
+    {
+        ScanSetup S; rc = scan_setup<WIDE, 1>(ctx, cfg, B, d_bases, d_inv, n_pos, &S); if (rc) { cleanup(); return rc; }
+        S.P.bin_base = d_bin_base; S.P.cursor = d_cursor; S.P.records = d_records;
+        if (n_rec) { k_scan<WIDE, 1><<<S.grid, kScanThreads, S.smem, s>>>(S.P); CKLC(); }
+    }
+    CKC(cudaEventRecord(ctx->ev[2], s));
+
+    // ---- stage 3/4: per-bin exact count, batches of consecutive bins
+    uint64_t out_total = 0;
+    float ms_count = 0, ms_compact = 0;
+    if (cfg->use_ht) {
+        const uint64_t budget_slots = std::max<uint64_t>(1024, (uint64_t)(ctx->table_budget_bytes / sizeof(Slot)));
+        double rho = 1.0;                         // estimate of distinct / k-mers, learnt from the first batch
+        uint64_t table_cap = 0;
+        std::vector<unsigned long long> tb;
+        int lo = 0;
+        while (lo < B) {
+            bool retried = false;
+            double use_rho = rho;
+            int hi;
+            for (;;) {
+                // plan [lo, hi)
+                tb.clear(); tb.push_back(0);
+                hi = lo; uint64_t slots = 0;
+                while (hi < B) {
+                    uint64_t want = (uint64_t)((double)h_kmer[(size_t)hi] * use_rho / ctx->load_factor) + 1;
+                    uint64_t sz = h_kmer[(size_t)hi] ? round_up(std::max<uint64_t>(want, 1024), 1024) : 0;
+                    if (hi > lo && slots + sz > budget_slots) break;
+                    slots += sz; tb.push_back(slots); hi++;
+                    if (lo == 0 && rho == 1.0 && hi - lo >= std::max(1, B / 64) && slots * sizeof(Slot) > (64ull << 20)) break;   // small first batch to learn rho
+                }
+                if (slots > table_cap) {
+                    cudaFree(d_table); d_table = nullptr;
+                    CKC(cudaMalloc(&d_table, (size_t)slots * sizeof(Slot)));
+                    table_cap = slots;
+                }
+                CKC(cudaEventRecord(ctx->ev[6], s));
+                CKC(cudaMemsetAsync(d_table, 0xFF, (size_t)slots * sizeof(Slot), s));
+                CKC(cudaMemsetAsync(d_ovf, 0, 4, s));
+                CKC(cudaMemcpyAsync(d_tbl_base, tb.data(), tb.size() * 8, cudaMemcpyHostToDevice, s));
+                st->h2d_bytes += tb.size() * 8;
+                CountParams C;
+                C.records = d_records; C.rec_lo = h_base[(size_t)lo]; C.rec_hi = h_base[(size_t)hi];
+                C.bin_base = d_bin_base; C.bin_lo = lo; C.bin_hi = hi; C.table = d_table; C.tbl_base = d_tbl_base;
+                C.bin_distinct = d_distinct; C.overflow = d_ovf; C.k = cfg->k; C.max_probe = 512;
+                const uint64_t nr = C.rec_hi - C.rec_lo;
+                if (nr) { k_count_ht<WIDE><<<(unsigned)((nr + 255) / 256), 256, 0, s>>>(C); CKLC(); }
+                k_bin_offsets<<<1, 256, 0, s>>>(d_distinct, d_out_base, lo, hi, d_small); CKLC();
+                CKC(cudaEventRecord(ctx->ev[7], s));
+                unsigned long long batch_total = 0; int ovf = 0;
+                CKC(cudaMemcpyAsync(&batch_total, d_small, 8, cudaMemcpyDeviceToHost, s));
+                CKC(cudaMemcpyAsync(&ovf, d_ovf, 4, cudaMemcpyDeviceToHost, s));
+                CKC(cudaStreamSynchronize(s));
+                st->d2h_bytes += 12;
+                { float ms; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); ms_count += ms; }
+                if (ovf) {
+                    if (retried && use_rho >= 1.0) { cleanup(); return fkm_set_error(FKM_ECUDA, "hash table overflow at full size (bins %d..%d)", lo, hi); }
+                    CKC(cudaMemsetAsync(d_distinct + lo, 0, (size_t)(hi - lo) * 8, s));
+                    use_rho = retried ? 1.0 : std::min(1.0, use_rho * 2.0); retried = true;
+                    continue;
+                }
+                // learn rho from what we saw
+                uint64_t nk = 0; for (int b = lo; b < hi; b++) nk += h_kmer[(size_t)b];
+                if (nk > 100000) rho = std::min(1.0, (double)batch_total / (double)nk * 1.25 + 0.02);
+                Chunk ch; ch.n = batch_total;
+                if (batch_total) {
+                    CKC(cudaMalloc(&ch.keys, (size_t)batch_total * sizeof(Key)));
+                    cudaError_t e2 = cudaMalloc(&ch.cnt, (size_t)batch_total * 4);
+                    if (e2 != cudaSuccess) { cudaFree(ch.keys); CKC(e2); }
+                    res->chunks.push_back(ch);
+                    CompactParams Q;
+                    Q.table = d_table; Q.n_slots = slots; Q.tbl_base = d_tbl_base; Q.n_bins = hi - lo; Q.bin_lo = lo;
+                    Q.out_base = d_out_base; Q.out_cursor = d_cursor; Q.out_origin = out_total;
+                    Q.out_keys = ch.keys; Q.out_cnt = ch.cnt;
+                    CKC(cudaMemsetAsync(d_cursor + lo, 0, (size_t)(hi - lo) * 8, s));
+                    CKC(cudaEventRecord(ctx->ev[6], s));
+                    k_compact_ht<WIDE><<<(unsigned)((slots + 1023) / 1024), 256, 0, s>>>(Q); CKLC();
+                    CKC(cudaEventRecord(ctx->ev[7], s));
+                    CKC(cudaStreamSynchronize(s));
+                    { float ms; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); ms_compact += ms; }
+                }
+                out_total += batch_total;
+                st->n_batches++;
+                break;
+            }
+            lo = hi;
+        }
+    } else {
+        const uint64_t budget_keys = std::max<uint64_t>(kSortTile, (uint64_t)ctx->sort_budget_keys);
+        const int n_pass = (2 * cfg->k + 7) / 8;
+        uint64_t key_cap = 0, tile_cap = 0, first_cap = 0;
+        std::vector<unsigned long long> kb; std::vector<unsigned int> tseg, st0;
+        int lo = 0;
+        while (lo < B) {
+            kb.clear(); kb.push_back(0); tseg.clear(); st0.clear(); st0.push_back(0);
+            int hi = lo; uint64_t nk = 0;
+            while (hi < B) {
+                uint64_t c = h_kmer[(size_t)hi];
+                if (hi > lo && nk + c > budget_keys) break;
+                nk += c; kb.push_back(nk);
+                uint64_t nt = (c + kSortTile - 1) / kSortTile;
+                for (uint64_t t = 0; t < nt; t++) tseg.push_back((unsigned)(hi - lo));
+                st0.push_back((unsigned)tseg.size());
+                hi++;
+            }
+            const uint64_t n_tiles = tseg.size();
+            const int n_seg = hi - lo;
+            if (n_tiles == 0) {          // only empty bins: just carry the output offset forward
+                k_bin_offsets<<<1, 256, 0, s>>>(d_distinct, d_out_base, lo, hi, d_small); CKLC();
+                lo = hi;
+                continue;
+            }
+            if (nk > key_cap) {
+                cudaFree(d_keysA); cudaFree(d_keysB); d_keysA = d_keysB = nullptr;
+                CKC(cudaMalloc(&d_keysA, (size_t)nk * sizeof(Key))); CKC(cudaMalloc(&d_keysB, (size_t)nk * sizeof(Key)));
+                key_cap = nk;
+            }
+            if (n_tiles > tile_cap) {
+                cudaFree(d_tile_seg); cudaFree(d_tile_hist); cudaFree(d_tile_heads); d_tile_seg = d_tile_hist = d_tile_heads = nullptr;
+                CKC(cudaMalloc(&d_tile_seg, (size_t)n_tiles * 4)); CKC(cudaMalloc(&d_tile_hist, (size_t)n_tiles * 256 * 4));
+                CKC(cudaMalloc(&d_tile_heads, (size_t)(n_tiles + 1) * 4));
+                tile_cap = n_tiles;
+            }
+            if (!d_seg_tile0) CKC(cudaMalloc(&d_seg_tile0, ((size_t)B + 1) * 4));
+            CKC(cudaMemcpyAsync(d_tbl_base, kb.data(), kb.size() * 8, cudaMemcpyHostToDevice, s));
+            CKC(cudaMemcpyAsync(d_tile_seg, tseg.data(), (size_t)n_tiles * 4, cudaMemcpyHostToDevice, s));
+            CKC(cudaMemcpyAsync(d_seg_tile0, st0.data(), st0.size() * 4, cudaMemcpyHostToDevice, s));
+            st->h2d_bytes += kb.size() * 8 + n_tiles * 4 + st0.size() * 4;
+            CKC(cudaEventRecord(ctx->ev[6], s));
+            ExpandParams E;
+            E.records = d_records; E.rec_lo = h_base[(size_t)lo]; E.rec_hi = h_base[(size_t)hi];
+            E.bin_base = d_bin_base; E.bin_lo = lo; E.bin_hi = hi; E.key_base = d_tbl_base; E.key_cursor = d_cursor; E.keys = d_keysA; E.k = cfg->k;
+            CKC(cudaMemsetAsync(d_cursor + lo, 0, (size_t)(hi - lo) * 8, s));
+            const uint64_t nr = E.rec_hi - E.rec_lo;
+            k_expand<WIDE><<<(unsigned)((nr + 255) / 256), 256, 0, s>>>(E); CKLC();
+            SortParams Q;
+            Q.seg_base = d_tbl_base; Q.tile_seg = d_tile_seg; Q.seg_tile0 = d_seg_tile0; Q.tile_hist = d_tile_hist;
+            Q.n_tiles = (unsigned)n_tiles; Q.n_seg = n_seg;
+            void* in = d_keysA; void* out = d_keysB;
+            for (int p = 0; p < n_pass; p++) {
+                Q.in = in; Q.out = out; Q.shift = 8 * p;
+                k_radix_hist<WIDE><<<(unsigned)n_tiles, 256, 0, s>>>(Q); CKLC();
+                k_radix_scan<<<n_seg, 256, 0, s>>>(Q); CKLC();
+                k_radix_scatter<WIDE><<<(unsigned)n_tiles, 256, 0, s>>>(Q); CKLC();
+                std::swap(in, out);
+            }
+            CKC(cudaEventRecord(ctx->ev[7], s));
+            RleParams R;
+            R.keys = in; R.seg_base = d_tbl_base; R.tile_seg = d_tile_seg; R.seg_tile0 = d_seg_tile0; R.n_tiles = (unsigned)n_tiles;
+            R.bin_lo = lo; R.tile_heads = d_tile_heads; R.bin_distinct = d_distinct; R.out_off = 0; R.n_keys = nk;
+            R.out_keys = nullptr; R.out_cnt = nullptr; R.first_idx = nullptr;
+            k_rle<WIDE, 0><<<(unsigned)n_tiles, 256, 0, s>>>(R); CKLC();
+            k_scan_u32<<<1, 1024, 0, s>>>(d_tile_heads, (unsigned)n_tiles); CKLC();
+            k_bin_offsets<<<1, 256, 0, s>>>(d_distinct, d_out_base, lo, hi, d_small); CKLC();
+            unsigned long long batch_total = 0;
+            CKC(cudaMemcpyAsync(&batch_total, d_small, 8, cudaMemcpyDeviceToHost, s));
+            CKC(cudaStreamSynchronize(s));
+            st->d2h_bytes += 8;
+            Chunk ch; ch.n = batch_total;
+            CKC(cudaMalloc(&ch.keys, (size_t)batch_total * sizeof(Key)));
+            cudaError_t e2 = cudaMalloc(&ch.cnt, (size_t)batch_total * 4);
+            if (e2 != cudaSuccess) { cudaFree(ch.keys); CKC(e2); }
+            res->chunks.push_back(ch);
+            if (batch_total + 1 > first_cap) {
+                cudaFree(d_first); d_first = nullptr;
+                CKC(cudaMalloc(&d_first, (size_t)(batch_total + 1) * 8));
+                first_cap = batch_total + 1;
+            }
+            R.out_keys = ch.keys; R.out_cnt = ch.cnt; R.first_idx = d_first;
+            k_rle<WIDE, 1><<<(unsigned)n_tiles, 256, 0, s>>>(R); CKLC();
+            k_rle_counts<<<(unsigned)((batch_total + 255) / 256), 256, 0, s>>>(d_first, batch_total, nk, ch.cnt, 0); CKLC();
+            CKC(cudaEventRecord(ctx->ev[8], s));
+            CKC(cudaStreamSynchronize(s));
+            { float ms; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); ms_count += ms; cudaEventElapsedTime(&ms, ctx->ev[7], ctx->ev[8]); ms_compact += ms; }
+            out_total += batch_total;
+            st->n_batches++;
+            lo = hi;
+        }
+    }
+    CKC(cudaEventRecord(ctx->ev[3], s));
+
+    // ---- stage 5: digest + bookkeeping
+    CKC(cudaMemcpyAsync(res->out_base.data(), d_out_base, bB + 8, cudaMemcpyDeviceToHost, s));
+    CKC(cudaMemsetAsync(d_small, 0, 64, s));
+    {
+        uint64_t origin = 0;
+        for (const Chunk& ch : res->chunks) {
+            if (!ch.n) continue;
+            DigestParams D;
+            D.keys = ch.keys; D.cnt = ch.cnt; D.out_base = d_out_base; D.B = B; D.n = ch.n; D.origin = origin; D.acc = d_small;
+            int grid = (int)std::min<uint64_t>((ch.n + 255) / 256, (uint64_t)ctx->n_sm * 8);
+            k_digest<WIDE><<<grid, 256, 0, s>>>(D); CKLC();
+            origin += ch.n;
+        }
+    }
+    unsigned long long acc[3] = {0, 0, 0};
+    CKC(cudaMemcpyAsync(acc, d_small, 24, cudaMemcpyDeviceToHost, s));
+    CKC(cudaEventRecord(ctx->ev[4], s));
+    CKC(cudaStreamSynchronize(s));
+    st->d2h_bytes += bB + 8 + 24;
+    res->total = out_total;
+    // empty trailing bins keep the running offset
+    for (int b = 0; b < B; b++) if (res->out_base[(size_t)b + 1] < res->out_base[(size_t)b]) res->out_base[(size_t)b + 1] = res->out_base[(size_t)b];
+    st->n_distinct = out_total; st->digest_sum = acc[0]; st->digest_xor = acc[1]; st->total_count = acc[2];
+    float ms;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); st->ms_stage[1] = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); st->ms_stage[2] = ms;
+    st->ms_stage[3] = ms_count; st->ms_stage[4] = ms_compact;
+    cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); st->ms_stage[5] = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]); st->ms_stage[7] = ms;      // whole device pipeline
+    cleanup();
+    if (st->total_count != st->n_kmers)
+        return fkm_set_error(FKM_ECUDA, "internal check failed: sum of counts %llu != valid k-windows %llu",
+                             (unsigned long long)st->total_count, (unsigned long long)st->n_kmers);
+    return FKM_OK;
+#undef CKC
+#undef CKLC
+}
+
+static int count_device(fkm_ctx* ctx, const fkm_config* cfg, const void* d_bases, const void* d_inv, uint64_t n_pos,
+                        fkm_result** out, fkm_stats* stats) {
+    int32_t B = 0; int rc = validate(cfg, &B); if (rc) return rc;
+    if (!ctx) return fkm_set_error(FKM_EINVAL, "ctx is NULL");
+    CK(cudaSetDevice(ctx->device));
+    fkm_stats local; fkm_stats* st = stats ? stats : &local;
+    const uint64_t keep_h2d = st->h2d_bytes, keep_bases = st->n_bases; const double keep_ms0 = st->ms_stage[0];
+    memset(st, 0, sizeof *st);
+    st->h2d_bytes = keep_h2d; st->n_bases = keep_bases; st->ms_stage[0] = keep_ms0;
+    st->n_positions = n_pos;
+    ctx->job_launches = 0;
+    auto t0 = std::chrono::steady_clock::now();
+    fkm_result* res = new fkm_result();
+    rc = (cfg->k > 32) ? run_pipeline<true>(ctx, cfg, B, d_bases, d_inv, n_pos, res, st)
+                       : run_pipeline<false>(ctx, cfg, B, d_bases, d_inv, n_pos, res, st);
+    st->gpu_launches = ctx->job_launches;
+    st->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (rc) { fkm_result_free(res); return rc; }
+    if (out) *out = res; else fkm_result_free(res);
+    return FKM_OK;
+}
+
+extern "C" int fkm_count_packed_device(fkm_ctx* ctx, const fkm_config* cfg, const void* d_bases, const void* d_inv,
+                                       uint64_t n_pos, fkm_result** out, fkm_stats* stats) {
+    if (stats) { stats->h2d_bytes = 0; stats->n_bases = 0; stats->ms_stage[0] = 0; }
+    return count_device(ctx, cfg, d_bases, d_inv, n_pos, out, stats);
+}
+
+extern "C" int fkm_count_packed_host(fkm_ctx* ctx, const fkm_config* cfg, const uint64_t* bases, const uint32_t* inv,
+                                     uint64_t n_pos, fkm_result** out, fkm_stats* stats) {
+    if (!ctx) return fkm_set_error(FKM_EINVAL, "ctx is NULL");
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t nw = (n_pos + 31) / 32;
+    void *d_b = nullptr, *d_i = nullptr;
+    CK(cudaMalloc(&d_b, std::max<size_t>(8, nw * 8)));
+    cudaError_t e = cudaMalloc(&d_i, std::max<size_t>(4, nw * 4));
+    if (e != cudaSuccess) { cudaFree(d_b); CK(e); }
+    auto t0 = std::chrono::steady_clock::now();
+    cudaMemcpyAsync(d_b, bases, nw * 8, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_i, inv, nw * 4, cudaMemcpyHostToDevice, ctx->stream);
+    e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { cudaFree(d_b); cudaFree(d_i); CK(e); }
+    fkm_stats local; fkm_stats* st = stats ? stats : &local;
+    st->h2d_bytes = nw * 12; st->n_bases = 0;
+    st->ms_stage[0] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    int rc = count_device(ctx, cfg, d_b, d_i, n_pos, out, st);
+    cudaFree(d_b); cudaFree(d_i);
+    return rc;
+}
+
+extern "C" int fkm_count_fasta(fkm_ctx* ctx, const fkm_config* cfg, const uint8_t* fasta, uint64_t n_bytes,
+                               fkm_result** out, fkm_stats* stats) {
+    if (!ctx) return fkm_set_error(FKM_EINVAL, "ctx is NULL");
+    int32_t B = 0; int rc = validate(cfg, &B); if (rc) return rc;
+    auto t0 = std::chrono::steady_clock::now();
+    uint64_t n_pos = 0, n_bases = 0;
+    rc = fkm_pack_fasta(fasta, n_bytes, nullptr, nullptr, 0, &n_pos, &n_bases); if (rc) return rc;
+    const uint64_t nw = (n_pos + 31) / 32;
+    uint64_t* hb = nullptr; uint32_t* hi = nullptr;
+    CK(cudaMallocHost((void**)&hb, std::max<size_t>(8, nw * 8)));
+    cudaError_t e = cudaMallocHost((void**)&hi, std::max<size_t>(4, nw * 4));
+    if (e != cudaSuccess) { cudaFreeHost(hb); CK(e); }
+    rc = fkm_pack_fasta(fasta, n_bytes, hb, hi, nw * 32, &n_pos, &n_bases);
+    fkm_stats local; fkm_stats* st = stats ? stats : &local;
+    if (!rc) {
+        double ms_pack = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        rc = fkm_count_packed_host(ctx, cfg, hb, hi, n_pos, out, st);
+        st->n_bases = n_bases; st->ms_stage[0] += ms_pack; st->ms_total += ms_pack;
+    }
+    cudaFreeHost(hb); cudaFreeHost(hi);
+    return rc;
+}
+
+extern "C" int fkm_execute_job(fkm_ctx* ctx, const fkm_config* cfg, fkm_stats* stats) {
+    int32_t B = 0; int rc = validate(cfg, &B); if (rc) return rc;
+    if (!cfg->dataset) return fkm_set_error(FKM_EINVAL, "dataset path is NULL");
+    std::vector<uint8_t> text;
+    rc = fkm_read_file(cfg->dataset, text); if (rc) return rc;
+    fkm_result* res = nullptr;
+    fkm_stats local; fkm_stats* st = stats ? stats : &local;
+    rc = fkm_count_fasta(ctx, cfg, text.data(), text.size(), &res, st); if (rc) return rc;
+    if (cfg->write) {                                        // writers are lazy in the reference: nothing is created when !write (SBKC:552-554)
+        char dir[4096];
+        rc = fkm_derive(cfg, nullptr, dir, sizeof dir);
+        auto t0 = std::chrono::steady_clock::now();
+        if (!rc) rc = fkm_result_write(res, dir);
+        st->ms_stage[6] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        st->ms_total += st->ms_stage[6];
+    }
+    fkm_result_free(res);
+    return rc;
+}
+
+// ------------------------------------------------------------------ results
+extern "C" uint64_t fkm_result_size(const fkm_result* r) { return r ? r->total : 0; }
+extern "C" int32_t fkm_result_num_bins(const fkm_result* r) { return r ? r->B : 0; }
+extern "C" int32_t fkm_result_sorted(const fkm_result* r) { return r && r->sorted ? 1 : 0; }
+extern "C" int fkm_result_bin_offsets(const fkm_result* r, uint64_t* offsets) {
+    if (!r || !offsets) return fkm_set_error(FKM_EINVAL, "null argument");
+    memcpy(offsets, r->out_base.data(), r->out_base.size() * 8);
+    return FKM_OK;
+}
+extern "C" int fkm_result_copy(const fkm_result* r, int32_t* bin, uint64_t* key_hi, uint64_t* key_lo, uint32_t* count) {
+    if (!r) return fkm_set_error(FKM_EINVAL, "null result");
+    CK(cudaSetDevice(r->device));
+    uint64_t o = 0;
+    std::vector<uint64_t> tmp;
+    for (const Chunk& ch : r->chunks) {
+        if (!ch.n) continue;
+        if (count) CK(cudaMemcpy(count + o, ch.cnt, ch.n * 4, cudaMemcpyDeviceToHost));
+        if (key_hi || key_lo) {
+            if (!r->wide) {
+                if (key_lo) CK(cudaMemcpy(key_lo + o, ch.keys, ch.n * 8, cudaMemcpyDeviceToHost));
+                if (key_hi) memset(key_hi + o, 0, ch.n * 8);
+            } else {
+                tmp.resize(ch.n * 2);
+                CK(cudaMemcpy(tmp.data(), ch.keys, ch.n * 16, cudaMemcpyDeviceToHost));
+                for (uint64_t i = 0; i < ch.n; i++) { if (key_lo) key_lo[o + i] = tmp[2 * i]; if (key_hi) key_hi[o + i] = tmp[2 * i + 1]; }
+            }
+        }
+        o += ch.n;
+    }
+    if (bin)
+        for (int b = 0; b < r->B; b++)
+            for (uint64_t i = r->out_base[(size_t)b]; i < r->out_base[(size_t)b + 1]; i++) bin[i] = b;
+    return FKM_OK;
+}
+extern "C" int fkm_result_write(const fkm_result* r, const char* out_dir) {
+    if (!r || !out_dir) return fkm_set_error(FKM_EINVAL, "null argument");
+    std::vector<uint64_t> hi(r->total), lo(r->total); std::vector<uint32_t> cnt(r->total);
+    int rc = fkm_result_copy(r, nullptr, hi.data(), lo.data(), cnt.data()); if (rc) return rc;
+    return fkm_write_bins(out_dir, r->B, r->k, r->sorted, r->out_base.data(), hi.data(), lo.data(), cnt.data());
+}
+extern "C" void fkm_result_free(fkm_result* r) {
+    if (!r) return;
+    cudaSetDevice(r->device);
+    for (Chunk& ch : r->chunks) { cudaFree(ch.keys); cudaFree(ch.cnt); }
+    delete r;
+}
+
+// ------------------------------------------------------------------ synthetic data, test hooks
+extern "C" int fkm_synth_packed_device(fkm_ctx* ctx, const fkm_synth* sy, void** d_bases, void** d_inv, uint64_t* n_positions) {
+    if (!ctx || !sy || !d_bases || !d_inv) return fkm_set_error(FKM_EINVAL, "null argument");
+    if (sy->genome_len < sy->read_len || sy->read_len == 0) return fkm_set_error(FKM_EINVAL, "genome shorter than a read");
+    CK(cudaSetDevice(ctx->device));
+    SynthParams P;
+    P.S = SynthSpec{sy->seed_genome, sy->seed_reads, sy->seed_errors, sy->genome_len, sy->n_reads, sy->read_len, sy->first_read};
+    P.n_pos = sy->n_reads * (sy->read_len + 1); P.n_words = (P.n_pos + 31) / 32;
+    CK(cudaMalloc((void**)&P.bases, std::max<size_t>(8, P.n_words * 8)));
+    cudaError_t e = cudaMalloc((void**)&P.inv, std::max<size_t>(4, P.n_words * 4));
+    if (e != cudaSuccess) { cudaFree(P.bases); CK(e); }
+    if (P.n_words) { k_synth<<<(unsigned)((P.n_words + 255) / 256), 256, 0, ctx->stream>>>(P); CKL(); }
+    CK(cudaStreamSynchronize(ctx->stream));
+    *d_bases = P.bases; *d_inv = P.inv; if (n_positions) *n_positions = P.n_pos;
+    return FKM_OK;
+}
+extern "C" int fkm_device_free(fkm_ctx* ctx, void* p) { if (ctx) cudaSetDevice(ctx->device); CK(cudaFree(p)); return FKM_OK; }
+
+extern "C" int fkm_debug_window_bins(fkm_ctx* ctx, const fkm_config* cfg, const uint64_t* bases, const uint32_t* inv,
+                                     uint64_t n_pos, int32_t* bins_out) {
+    int32_t B = 0; int rc = validate(cfg, &B); if (rc) return rc;
+    if (!ctx) return fkm_set_error(FKM_EINVAL, "ctx is NULL");
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t nw = (n_pos + 31) / 32;
+    void *d_b = nullptr, *d_i = nullptr; int32_t* d_o = nullptr;
+    CK(cudaMalloc(&d_b, std::max<size_t>(8, nw * 8))); CK(cudaMalloc(&d_i, std::max<size_t>(4, nw * 4))); CK(cudaMalloc((void**)&d_o, std::max<size_t>(4, n_pos * 4)));
+    CK(cudaMemcpyAsync(d_b, bases, nw * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_i, inv, nw * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ScanSetup S; S.grid = 1; S.smem = 0;
+    if (cfg->k > 32) { rc = scan_setup<true, 2>(ctx, cfg, B, d_b, d_i, n_pos, &S); if (!rc) { S.P.dbg_bins = d_o; k_scan<true, 2><<<S.grid, kScanThreads, S.smem, ctx->stream>>>(S.P); } }
+    else { rc = scan_setup<false, 2>(ctx, cfg, B, d_b, d_i, n_pos, &S); if (!rc) { S.P.dbg_bins = d_o; k_scan<false, 2><<<S.grid, kScanThreads, S.smem, ctx->stream>>>(S.P); } }
+    if (!rc) { CKL(); CK(cudaMemcpyAsync(bins_out, d_o, n_pos * 4, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream)); }
+    cudaFree(d_b); cudaFree(d_i); cudaFree(d_o);
+    return rc;
+}

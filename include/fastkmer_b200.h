@@ -1,0 +1,162 @@
+/* fastkmer_b200.h — C ABI of the B200-native exact k-mer counting path.
+ *
+ * This is the drop-in boundary for fastkmer's hot path.  The reference has no
+ * FFI; its seam is the single call
+ *     SparkBinKmerCounter.executeJob(spark, configuration)
+ *         src/main/scala/skc/SparkBinKmerCounter.scala:989   (SBKC:989)
+ * made by skc.test.LocalTestKmerCounter (LTKC:76) and skc.test.TestKmerCounter
+ * (TKC:74).  A JVM host replaces the body of executeJob by one JNI call into
+ * fkm_execute_job (see INTEGRATION.md for the Scala/JNI stub).
+ *
+ * Conventions: every function returns FKM_OK (0) or a negative FKM_E* code and
+ * never throws or aborts across the ABI; fkm_last_error() gives the message of
+ * the calling thread's last failure.  No torch / C++ types in any signature.
+ * There is no CPU fallback: without a CUDA device every compute entry point
+ * fails with FKM_ECUDA.
+ *
+ * Shorthands in the citations below:
+ *   SBKC = src/main/scala/skc/SparkBinKmerCounter.scala
+ *   UTIL = src/main/scala/skc/package.scala
+ *   TCFG = src/main/scala/skc/test/package.scala
+ *   LTKC = src/main/scala/skc/test/LocalTestKmerCounter.scala
+ */
+#ifndef FASTKMER_B200_H
+#define FASTKMER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FKM_OK        0
+#define FKM_EINVAL   -1   /* bad argument / unsupported configuration            */
+#define FKM_ECUDA    -2   /* CUDA runtime failure or no device                   */
+#define FKM_EIO      -3   /* file could not be read / written                    */
+#define FKM_ENOMEM   -4   /* host or device allocation failed                    */
+#define FKM_EOVERFLOW -5  /* a 32-bit count overflowed (reference counts are Int, SBKC:562,676) */
+
+typedef struct fkm_ctx fkm_ctx;        /* one per (process, GPU): device, stream, scratch */
+typedef struct fkm_result fkm_result;  /* per-bin (canonical k-mer, count) arrays          */
+
+/* Mirrors skc.test.testutil.TestConfiguration (TCFG:16-30); field meaning and
+ * the derived values are the reference's.  Strings are borrowed for the call. */
+typedef struct fkm_config {
+    int32_t k;                       /* k-mer length, m <= k <= 64                      */
+    int32_t m;                       /* signature length, 3 <= m <= 15 (UTIL:78 Int)    */
+    int32_t x;                       /* (k,x)-mer compression; must be >= 1 when use_ht=0 (SBKC:495 crashes on 0) */
+    int32_t max_b;                   /* requested bins; b = min(4^m, max_b) (TCFG:32)   */
+    int32_t sequence_type;           /* 0 short reads, 1 long sequence (SBKC:1010)      */
+    int32_t use_ht;                  /* 1: hash-table count (SBKC:664), 0: sort count (SBKC:428) */
+    int32_t write;                   /* 1: write <outputDir>/bin<id> files              */
+    int32_t use_kryo_serializer;     /* accepted, ignored (JVM serialisation only)      */
+    int32_t use_custom_partitioner;  /* accepted; bin->GPU ownership is always exact-histogram based */
+    int32_t num_partition_tasks;
+    const char* dataset;             /* FASTA path (fkm_execute_job only)               */
+    const char* output_directory;
+    const char* prefix;
+} fkm_config;
+
+/* Counters of one job.  n_* are exact.  *_ref are measured under the GPU's own
+ * super-k-mer chunking (the reference's cutting rule is not observable).       */
+typedef struct fkm_stats {
+    uint64_t n_positions;        /* bases + one separator per record, as laid out on device */
+    uint64_t n_bases;            /* sequence bytes of all records (invalid ones included)   */
+    uint64_t n_kmers;            /* valid k-windows                                          */
+    uint64_t n_superkmers;       /* super-k-mer records scattered into bins                  */
+    uint64_t superkmer_bytes;    /* bytes of that intermediate                               */
+    uint64_t n_distinct;         /* distinct (bin, canonical k-mer)                          */
+    uint64_t total_count;        /* sum of counts == n_kmers                                 */
+    uint64_t digest_sum;         /* order-independent digests of (bin, k-mer, count)         */
+    uint64_t digest_xor;
+    uint64_t n_nonempty_bins;
+    uint64_t h2d_bytes, d2h_bytes;
+    uint64_t gpu_launches;       /* kernels launched by this job                             */
+    uint64_t n_batches;
+    double   ms_total;           /* host wall time of the call                               */
+    double   ms_stage[8];        /* 0 parse/pack+H2D 1 histogram 2 scatter 3 count 4 compact/reduce 5 digest 6 D2H/write 7 spare (device, CUDA events) */
+} fkm_stats;
+
+const char* fkm_last_error(void);
+
+/* device < 0: current device.  stream: a cudaStream_t (as void*) to launch on,
+ * or NULL for a stream the context creates.                                    */
+int  fkm_ctx_create(int device, void* stream, fkm_ctx** out);
+void fkm_ctx_destroy(fkm_ctx* ctx);
+int  fkm_ctx_sync(fkm_ctx* ctx);
+/* tuning knobs (optional): name in {"table_budget_bytes","sort_budget_keys","load_factor"} */
+int  fkm_ctx_set(fkm_ctx* ctx, const char* name, double value);
+
+/* b = min(4^m, max_b) and outputDir = outputDirectory + prefix + "k"+k+"_m"+m+"_x"+x+"_b"+b+"_s"+sequenceType
+ * (TCFG:32-33).  out_dir may be NULL.                                          */
+int  fkm_derive(const fkm_config* cfg, int32_t* b, char* out_dir, size_t out_dir_cap);
+
+/* ---- the drop-in call: replaces the body of executeJob (SBKC:989-1046) ------
+ * Reads cfg->dataset (FASTA), counts on the GPU, writes the bin files when
+ * cfg->write (layout SBKC:550-606 sort path incl. "EOF" trailer, SBKC:715-734 HT
+ * path).  stats may be NULL.                                                   */
+int  fkm_execute_job(fkm_ctx* ctx, const fkm_config* cfg, fkm_stats* stats);
+
+/* ---- in-memory variants (same path, no file I/O) ---------------------------- */
+/* FASTA text in host memory (pinned if it came from fkm_host_alloc).           */
+int  fkm_count_fasta(fkm_ctx* ctx, const fkm_config* cfg, const uint8_t* fasta, uint64_t n_bytes,
+                     fkm_result** out, fkm_stats* stats);
+
+/* 2-bit packed input, HOST memory.  bases: 32 positions per uint64, first
+ * position in the two MSBs (A=0 C=1 G=2 T=3, UTIL:19-22); invalid: 32 positions
+ * per uint32, first position in the MSB, set for every non-ACGT byte and for the
+ * one separator position that follows each record.                             */
+int  fkm_count_packed_host(fkm_ctx* ctx, const fkm_config* cfg, const uint64_t* bases, const uint32_t* invalid,
+                           uint64_t n_positions, fkm_result** out, fkm_stats* stats);
+/* Same layout, DEVICE memory already resident (what `value` in bench.py times). */
+int  fkm_count_packed_device(fkm_ctx* ctx, const fkm_config* cfg, const void* d_bases, const void* d_invalid,
+                             uint64_t n_positions, fkm_result** out, fkm_stats* stats);
+
+/* Host-side FASTA -> packed layout (record split of SURVEY App. A.1: '\n' is
+ * stripped, every other non-ACGT byte is an invalid position).  Returns the
+ * number of positions; call with bases==NULL to size (words = (n+31)/32).      */
+int  fkm_pack_fasta(const uint8_t* fasta, uint64_t n_bytes, uint64_t* bases, uint32_t* invalid,
+                    uint64_t cap_positions, uint64_t* n_positions, uint64_t* n_bases);
+
+/* pinned host memory for inputs (so H2D runs at PCIe speed) */
+int  fkm_host_alloc(size_t bytes, void** out);
+void fkm_host_free(void* p);
+
+/* ---- results ----------------------------------------------------------------- */
+uint64_t fkm_result_size(const fkm_result* r);                   /* distinct entries            */
+int32_t  fkm_result_num_bins(const fkm_result* r);               /* b                            */
+int32_t  fkm_result_sorted(const fkm_result* r);                 /* 1 if k-mers ascend inside each bin (use_ht=0) */
+/* per-bin start offsets into the entry arrays, b+1 values */
+int  fkm_result_bin_offsets(const fkm_result* r, uint64_t* offsets);
+/* entries in bin-major order; key = 2k-bit integer, first base most significant,
+ * hi = bits 127..64 (0 when k <= 32).  Any of the pointers may be NULL.        */
+int  fkm_result_copy(const fkm_result* r, int32_t* bin, uint64_t* key_hi, uint64_t* key_lo, uint32_t* count);
+/* writes <out_dir>/bin<id> for every non-empty bin (SBKC:550-606 / 715-734)    */
+int  fkm_result_write(const fkm_result* r, const char* out_dir);
+void fkm_result_free(fkm_result* r);
+
+/* ---- synthetic inputs of SURVEY §8(d) (counter-based splitmix64) -------------- */
+typedef struct fkm_synth {
+    uint64_t seed_genome, seed_reads, seed_errors;
+    uint64_t genome_len, n_reads, read_len;
+    uint64_t first_read;          /* global index of this shard's first read (multi-GPU sharding) */
+} fkm_synth;
+/* FASTA text ('>r<i>\n<seq>\n') into host memory; out==NULL sizes. */
+int  fkm_synth_fasta_host(const fkm_synth* s, uint8_t* out, uint64_t cap, uint64_t* n_bytes);
+/* packed layout generated directly in device memory (owned by ctx until
+ * fkm_device_free).  d_bases / d_invalid receive device pointers.              */
+int  fkm_synth_packed_device(fkm_ctx* ctx, const fkm_synth* s, void** d_bases, void** d_invalid, uint64_t* n_positions);
+int  fkm_device_free(fkm_ctx* ctx, void* d_ptr);
+
+/* ---- test hooks (stage-level parity against the oracle) ----------------------- */
+/* bin of every window start (−1 where the k-window holds an invalid position);
+ * bins_out has n_positions entries.                                             */
+int  fkm_debug_window_bins(fkm_ctx* ctx, const fkm_config* cfg, const uint64_t* bases, const uint32_t* invalid,
+                           uint64_t n_positions, int32_t* bins_out);
+uint64_t fkm_total_launches(void);    /* kernels launched by this process so far */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTKMER_B200_H */

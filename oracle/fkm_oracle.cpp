@@ -484,6 +484,19 @@ int32_t fkmo_superkmers(const uint8_t* rec, int64_t len, int32_t k, int32_t m, i
     return n;
 }
 
+// bin of every k-window of one record (ASCII), -1 where the window holds a non-ACGT
+// byte: hash_to_bucket(getSignature(window)) — SBKC:99-112 applied to each window.
+void fkmo_window_bins(const uint8_t* rec, int64_t len, int32_t k, int32_t m, int32_t max_b, int32_t* out) {
+    const int B = (int)std::min<int64_t>((int64_t)1 << (2 * m), (int64_t)max_b);
+    std::vector<int32_t> norm = fill_norm(m);
+    for (int64_t i = 0; i + k <= len; i++) {
+        int64_t nf, nl; first_last_invalid(rec, i, i + k, nf, nl);
+        if (nf != -1) { out[i] = -1; continue; }
+        int32_t sig; int pos; get_signature(rec + i, k, m, norm.data(), sig, pos);
+        out[i] = hash_to_bucket(sig, B);
+    }
+}
+
 void* fkmo_count(const uint8_t* fasta, uint64_t n, int32_t k, int32_t m, int32_t x, int32_t max_b,
                  int32_t use_ht, int32_t threads, int32_t sorted) {
     if (k < m || m < 3 || m > 15 || k > 64 || max_b < 1) return nullptr;

@@ -38,6 +38,7 @@ class Oracle:
         lib.fkmo_orientation.argtypes = [C.c_char_p, C.c_int32]
         lib.fkmo_superkmers.restype = C.c_int32
         lib.fkmo_superkmers.argtypes = [C.c_char_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
+        lib.fkmo_window_bins.argtypes = [C.c_char_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
         lib.fkmo_count.restype = C.c_void_p
         lib.fkmo_count.argtypes = [C.c_void_p, C.c_uint64] + [C.c_int32] * 7
         lib.fkmo_result_size.restype = C.c_uint64
@@ -67,6 +68,12 @@ class Oracle:
         lens = np.empty(cap, dtype=np.int32)
         n = self.lib.fkmo_superkmers(rec, len(rec), k, m, max_b, bins.ctypes.data, lens.ctypes.data, cap)
         return list(zip(bins[:n].tolist(), lens[:n].tolist()))
+
+    def window_bins(self, rec: bytes, k, m, max_b):
+        out = np.full(max(len(rec) - k + 1, 0), -2, dtype=np.int32)
+        if out.size:
+            self.lib.fkmo_window_bins(rec, len(rec), k, m, max_b, out.ctypes.data)
+        return out
 
     def gen_lcg_fasta(self, seed, G, R, L) -> bytes:
         n = self.lib.fkmo_gen_lcg_fasta(seed, G, R, L, None, 0)

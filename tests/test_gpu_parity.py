@@ -1,0 +1,252 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same
+inputs — bit-exact (bin, canonical k-mer, count) sets.  Run with -m gpu on a B200."""
+import hashlib
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+import clean_spec
+import fastkmer_b200 as fk
+import oracle_lib
+from test_oracle_kat import GOLD, _rand_fasta
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = fk.Context(0)
+    yield c
+    c.close()
+
+
+def cfg(k, m, x, B, ht, **kw):
+    return fk.TestConfiguration("", "", k, m, x, max_b=B, useHT=bool(ht), write=False, **kw)
+
+
+def assert_same(got, want, what=""):
+    for key in ("bin", "hi", "lo", "cnt"):
+        assert got[key].shape == want[key].shape, "%s: %d entries vs oracle %d" % (what, got[key].size, want[key].size)
+        assert np.array_equal(got[key], want[key]), "%s: %s differs" % (what, key)
+
+
+def check(ctx, oracle, fasta: bytes, k, m, x, B, ht, what=""):
+    res, st = ctx.count_fasta(cfg(k, m, x, B, ht), fasta)
+    want = oracle.count(fasta, k, m, x, B, ht)
+    assert_same(res.sorted_arrays(), want, what)
+    ws = want["stats"]
+    assert st["n_kmers"] == ws["n_kmers"] == st["total_count"]
+    assert st["n_distinct"] == ws["n_distinct"] and st["n_bases"] == ws["n_bases"]
+    assert (st["digest_sum"], st["digest_xor"]) == (ws["digest_sum"], ws["digest_xor"])
+    if not ht:                                  # sort path: ascending inside each bin, as the reference writes them
+        a = res.arrays()
+        assert_same(a, want, what + " (unsorted order)")
+    return res, st
+
+
+# ---------------------------------------------------------------- K1: per-window bins
+@pytest.mark.parametrize("k,m,B", [(28, 10, 2048), (31, 11, 4096), (55, 13, 2048), (5, 3, 64), (10, 10, 999), (64, 15, 5000),
+                                    (33, 4, 256), (32, 3, 64), (20, 5, 2000)])
+def test_window_bins_match_oracle(ctx, oracle, k, m, B):
+    rng = random.Random(k * 100 + m)
+    seq = "".join("N" if rng.random() < 0.01 else rng.choice("ACGT") for _ in range(30000))
+    seq = seq[:5000] + "A" * 300 + "ACACACAC" * 40 + "T" * 200 + seq[5000:]
+    bases, inv, n_pos, _ = fk.pack_fasta((">s\n%s\n" % seq).encode())
+    got = ctx.window_bins(cfg(k, m, 3, B, 1), bases, inv, n_pos)
+    want = oracle.window_bins(seq.encode(), k, m, B)
+    assert np.array_equal(got[:want.size], want)
+    assert (got[want.size:] == -1).all()
+
+
+# ---------------------------------------------------------------- golden vectors
+@pytest.mark.parametrize("gid", sorted(GOLD))
+@pytest.mark.parametrize("ht", [0, 1])
+def test_golden_digests(ctx, oracle, gid, ht):
+    (seed, G, R, L), (k, m, x, B), nk, dist, nbins, maxc, _, _, sha = GOLD[gid]
+    fasta = oracle.gen_lcg_fasta(seed, G, R, L)
+    res, st = check(ctx, oracle, fasta, k, m, x, B, ht, gid)
+    assert (st["n_kmers"], st["n_distinct"], st["n_nonempty_bins"]) == (nk, dist, nbins)
+    assert oracle_lib.digest_of(res.sorted_arrays(), k) == sha
+
+
+# ---------------------------------------------------------------- edge cases of the reference's input handling
+@pytest.mark.parametrize("k,m,x,B", [(5, 3, 1, 64), (12, 4, 2, 100), (20, 5, 3, 2000), (28, 10, 3, 2048), (31, 11, 3, 4096),
+                                      (32, 7, 2, 333), (33, 8, 3, 512), (55, 13, 3, 2048), (60, 9, 4, 77), (61, 6, 3, 4096),
+                                      (64, 15, 1, 5000), (15, 15, 2, 3), (7, 7, 1, 1 << 20)])
+@pytest.mark.parametrize("ht", [0, 1])
+def test_random_reads_with_invalid_bytes(ctx, oracle, k, m, x, B, ht):
+    if not ht and k + x > 64:
+        pytest.skip("oracle's sort path holds (k+x)-mers in 128 bits")
+    rng = random.Random(k * 1000 + m + ht)
+    for alphabet, width in (("ACGT", None), ("AC", 17), ("ACGT", 70), ("A", None)):
+        fasta = _rand_fasta(rng, 40, 0, 3 * k + 60, alphabet=alphabet, width=width).encode()
+        check(ctx, oracle, fasta, k, m, x, B, ht, "%s/%s" % (alphabet, width))
+
+
+@pytest.mark.parametrize("ht", [0, 1])
+def test_degenerate_inputs(ctx, oracle, ht):
+    for text in (b"", b">empty\n", b">short\nACGT\n", b">allN\n" + b"N" * 500 + b"\n", b">lower\n" + b"acgt" * 50 + b"\n",
+                 b">one\n" + b"ACGTTGCATGCAGGCTTAACCGGTAAGC" + b"\n", b"no header\nACGTACGTACGTACGTACGTACGTACGTACGTACGT\n",
+                 b">crlf\r\n" + b"ACGGTCAGGT" * 9 + b"\r\n" + b"ACGGTCAGGT" * 9 + b"\r\n"):
+        res, st = check(ctx, oracle, text, 28, 10, 3, 2048, ht, repr(text[:12]))
+    assert len(res) == 0 or st["n_kmers"] > 0
+
+
+def test_long_homopolymer_and_repeats(ctx, oracle):          # runs far longer than one record's capacity
+    rng = random.Random(5)
+    unit = "".join(rng.choice("ACGT") for _ in range(37))
+    seq = "A" * 5000 + unit * 300 + "C" * 3000 + "AC" * 2000 + "".join(rng.choice("ACGT") for _ in range(20000))
+    fasta = (">g\n" + "\n".join(seq[i:i + 70] for i in range(0, len(seq), 70)) + "\n").encode()
+    for (k, m, x, B) in ((28, 10, 3, 2048), (31, 11, 3, 4096), (55, 13, 3, 2048), (64, 12, 1, 512)):
+        for ht in (0, 1):
+            if not ht and k + x > 64:
+                continue
+            check(ctx, oracle, fasta, k, m, x, B, ht, "k%d ht%d" % (k, ht))
+
+
+# ---------------------------------------------------------------- BASELINE configs at reduced scale
+SYNTH = {
+    "config1": (dict(seeds=(1001, 1002, 1003), genome_len=50000, n_reads=10000, read_len=100), (28, 10, 3, 2048, 0, 0)),
+    "config2": (dict(seeds=(2001, 2002, 2003), genome_len=100000, n_reads=20000, read_len=150), (28, 10, 3, 2048, 1, 0)),
+    "config4": (dict(seeds=(4001, 4002, 4003), genome_len=100000, n_reads=20000, read_len=150), (55, 13, 3, 2048, 0, 0)),
+    "config4ht": (dict(seeds=(4001, 4002, 4003), genome_len=100000, n_reads=8000, read_len=150), (55, 13, 3, 2048, 1, 0)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(SYNTH))
+def test_baseline_configs_reduced(ctx, oracle, name):
+    spec, (k, m, x, B, ht, seqtype) = SYNTH[name]
+    fasta = fk.synth_fasta(spec).tobytes()
+    res, st = check(ctx, oracle, fasta, k, m, x, B, ht, name)
+    # the device generator lays out the same reads: identical digest without any host text
+    d_b, d_i, n_pos = ctx.synth_packed_device(spec)
+    _, st2 = ctx.count_packed_device(cfg(k, m, x, B, ht), d_b, d_i, n_pos, want_result=False)
+    assert (st2["digest_sum"], st2["digest_xor"], st2["n_kmers"], st2["n_distinct"]) == \
+           (st["digest_sum"], st["digest_xor"], st["n_kmers"], st["n_distinct"])
+    ctx.free_device(d_b)
+    ctx.free_device(d_i)
+
+
+def _long_genome(n, seed):
+    rng = random.Random(seed)
+    g = [rng.choice("ACGT") for _ in range(n)]
+    for _ in range(max(1, n // 100000)):                       # 5-kb repeats
+        src = rng.randrange(0, n - 5000)
+        for c in range(10):
+            dst = rng.randrange(0, n - 5000)
+            g[dst:dst + 5000] = g[src:src + 5000]
+    for _ in range(max(1, n // 200000)):                       # N runs of 1000
+        p = rng.randrange(0, n - 1000)
+        g[p:p + 1000] = "N" * 1000
+    return "".join(g)
+
+
+def test_config3_long_sequence_reduced(ctx, oracle):          # sequenceType=1: one record, 70-column lines
+    seq = _long_genome(1_200_000, 3001)
+    fasta = (">chr1 synthetic\n" + "\n".join(seq[i:i + 70] for i in range(0, len(seq), 70)) + "\n").encode()
+    for ht in (0, 1):
+        res, st = ctx.count_fasta(cfg(31, 11, 3, 4096, ht, sequenceType=1), fasta)
+        want = oracle.count(fasta, 31, 11, 3, 4096, ht, threads=8)
+        assert_same(res.sorted_arrays(), want, "config3 ht%d" % ht)
+        assert st["n_kmers"] == want["stats"]["n_kmers"]
+
+
+# ---------------------------------------------------------------- size-independent properties at larger scale
+def test_properties_at_scale(ctx):
+    spec = dict(seeds=(2001, 2002, 2003), genome_len=2_000_000, n_reads=400_000, read_len=150)    # 60 Mbases
+    d_b, d_i, n_pos = ctx.synth_packed_device(spec)
+    _, ht = ctx.count_packed_device(cfg(28, 10, 3, 2048, 1), d_b, d_i, n_pos, want_result=False)
+    _, so = ctx.count_packed_device(cfg(28, 10, 3, 2048, 0), d_b, d_i, n_pos, want_result=False)
+    for key in ("n_kmers", "n_distinct", "total_count", "digest_sum", "digest_xor", "n_nonempty_bins"):
+        assert ht[key] == so[key], key                         # hash path == sort path (the reference's own cross-check)
+    assert ht["total_count"] == ht["n_kmers"] > 40_000_000
+    # the bin count changes where k-mers land, never which k-mers exist
+    _, b1 = ctx.count_packed_device(cfg(28, 10, 3, 1, 1), d_b, d_i, n_pos, want_result=False)
+    assert (b1["n_kmers"], b1["n_distinct"]) == (ht["n_kmers"], ht["n_distinct"])
+    ctx.free_device(d_b)
+    ctx.free_device(d_i)
+
+
+def test_strand_symmetry_and_split_invariance(ctx):
+    rng = random.Random(11)
+    seq = "".join(rng.choice("ACGT") for _ in range(200000))
+    a, sa = ctx.count_fasta(cfg(28, 10, 3, 2048, 1), (">a\n%s\n" % seq).encode())
+    b, sb = ctx.count_fasta(cfg(28, 10, 3, 2048, 1), (">a\n%s\n" % clean_spec.revcomp(seq)).encode())
+    assert (sa["digest_sum"], sa["digest_xor"]) == (sb["digest_sum"], sb["digest_xor"])
+    # overlapping chunks with a (k-1)-base halo count the same k-mers as the whole sequence
+    k = 28
+    cuts = [0, 50000, 123457, 200000]
+    text = "".join(">c%d\n%s\n" % (i, seq[cuts[i]:min(len(seq), cuts[i + 1] + k - 1)]) for i in range(3))
+    c, sc = ctx.count_fasta(cfg(28, 10, 3, 2048, 0), text.encode())
+    assert (sa["digest_sum"], sa["digest_xor"], sa["n_kmers"]) == (sc["digest_sum"], sc["digest_xor"], sc["n_kmers"])
+
+
+def test_small_table_budget_batches_and_retry(ctx, oracle):
+    spec = dict(seeds=(7, 8, 9), genome_len=30000, n_reads=30000, read_len=100)      # 100x coverage: few distinct per k-mer
+    fasta = fk.synth_fasta(spec).tobytes()
+    want = oracle.count(fasta, 28, 10, 3, 2048, 1, threads=8)
+    c2 = fk.Context(0)
+    try:
+        c2.set("table_budget_bytes", 1 << 20)
+        res, st = c2.count_fasta(cfg(28, 10, 3, 2048, 1), fasta)
+        assert st["n_batches"] > 4
+        assert_same(res.sorted_arrays(), want, "tiny budget")
+        c2.set("sort_budget_keys", 50000)
+        res, st = c2.count_fasta(cfg(28, 10, 3, 2048, 0), fasta)
+        assert st["n_batches"] > 4
+        assert_same(res.arrays(), want, "tiny sort budget")
+    finally:
+        c2.close()
+
+
+# ---------------------------------------------------------------- the drop-in call and its files
+@pytest.mark.parametrize("ht", [0, 1])
+def test_execute_job_writes_reference_layout(ctx, oracle, tmp_path, ht):
+    fasta = oracle.gen_lcg_fasta(42, 2000, 200, 100)
+    inp = tmp_path / "reads.fasta"
+    inp.write_bytes(fasta)
+    tc = fk.TestConfiguration(str(inp), str(tmp_path) + "/out/", 28, 10, 3, max_b=2048, prefix="run_", useHT=bool(ht), write=True)
+    st = fk.SparkBinKmerCounter.executeJob(ctx, tc)
+    out = tmp_path / "out" / "run_k28_m10_x3_b2048_s0"                    # test/package.scala:33
+    assert out.is_dir()
+    want = oracle.count(fasta, 28, 10, 3, 2048, ht)
+    by_bin = {}
+    for b, h, l, c in zip(want["bin"], want["hi"], want["lo"], want["cnt"]):
+        by_bin.setdefault(int(b), []).append(b"%s\t%d\n" % (oracle_lib.kmer_str(h, l, 28).encode(), int(c)))
+    assert sorted(os.listdir(out)) == sorted("bin%d" % b for b in by_bin)  # one file per non-empty bin
+    for b, lines in by_bin.items():
+        data = (out / ("bin%d" % b)).read_bytes()
+        if ht:                                                             # hash order, no trailer (SBKC:723-734)
+            assert not data.endswith(b"EOF")
+            assert sorted(data.splitlines(keepends=True)) == sorted(lines)
+        else:                                                              # ascending, then "EOF" without newline (SBKC:598-606)
+            assert data == b"".join(lines) + b"EOF"
+    assert st["n_kmers"] == 10628
+    # write=0 creates nothing (lazy writers, SBKC:552-554)
+    tc0 = fk.TestConfiguration(str(inp), str(tmp_path) + "/none/", 28, 10, 3, max_b=2048, useHT=bool(ht), write=False)
+    fk.LocalTestKmerCounter.run(tc0)
+    assert not (tmp_path / "none").exists()
+
+
+def test_cli_matches_reference_argv(oracle, tmp_path):
+    fasta = oracle.gen_lcg_fasta(45, 300, 60, 40)
+    inp = tmp_path / "g4.fasta"
+    inp.write_bytes(fasta)
+    cli = os.path.join(ROOT, "fastkmer_b200", "fastkmer_cli")
+    r = subprocess.run([cli, "5", "3", "1", "64", "0", "0", str(inp), str(tmp_path) + "/", "g4", "1", "0", "0"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = tmp_path / "g4k5_m3_x1_b64_s0"
+    first = (out / "bin0").read_bytes().splitlines()
+    assert first[:5] == [b"CTGAC\t3", b"CTGCA\t10", b"CTGGA\t13", b"CTGTC\t18", b"GGAAC\t16"]     # SURVEY App. C.4 anchor
+    lines = []
+    for name in os.listdir(out):
+        b = int(name[3:])
+        body = (out / name).read_bytes()
+        assert body.endswith(b"EOF")
+        lines += [b"%d\t%s\n" % (b, ln) for ln in body[:-3].splitlines()]
+    assert hashlib.sha256(b"".join(sorted(lines))).hexdigest() == GOLD["G4"][-1]
