@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py — exact k-mer counting throughput of the B200 path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--reads R]
+
+A "step" is one whole counting job over one synthetic read set (SURVEY §8(d) generator):
+  value : job throughput with the 2-bit packed reads already resident in HBM
+          (fkm_count_packed_device), timed with CUDA events on the launching stream
+  e2e   : the same job through the reference-facing call with HOST input
+          (fkm_count_fasta: pinned FASTA text -> H2D -> device parse -> count -> stats D2H)
+Workload at N=1 is BASELINE.json configs[1]: k=28 m=10 x=3 B=2048 useHT=1 on 50M x 150 bp reads.
+With N>1 ranks every rank scans its own shard of the reads (weak scaling: 50M reads per GPU),
+bins are owned per GPU and exchanged with one all-to-all (see fastkmer_b200/multigpu.py).
+
+--impl reference times the CPU oracle (a port of the reference's algorithm; Spark cannot run
+here) on a bounded sample of the same workload with all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K, M, X, B = 28, 10, 3, 2048
+READ_LEN = 150
+COVERAGE = 30
+SEEDS = (2001, 2002, 2003)
+FULL_READS = 50_000_000
+
+
+def workload(reads_per_gpu, n_gpus):
+    total = reads_per_gpu * n_gpus
+    return dict(seeds=SEEDS, genome_len=max(READ_LEN * 2, total * READ_LEN // COVERAGE), n_reads=reads_per_gpu, read_len=READ_LEN)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                pass
+        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 9 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) >= 9 and r[2].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_sample_spec(n_gpus):
+    # bounded sample of the same workload: 1/100 of one GPU's reads, same genome coverage model
+    reads = 500_000
+    return dict(seeds=SEEDS, genome_len=reads * READ_LEN // COVERAGE, n_reads=reads, read_len=READ_LEN)
+
+
+def run_cpu_oracle(threads, spec):
+    """Times the CPU oracle (port of the reference algorithm) on `spec`.  -> dict"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    import fastkmer_b200 as fk
+    oracle = oracle_lib.load()
+    fasta = fk.synth_fasta(spec)                      # host generator of the product lib: data only, no counting
+    t0 = time.perf_counter()
+    res = oracle.count(fasta, K, M, X, B, 1, threads=threads, sorted_=False)
+    dt = time.perf_counter() - t0
+    st = res["stats"]
+    return {"seconds": dt, "n_bases": st["n_bases"], "n_kmers": st["n_kmers"], "n_distinct": st["n_distinct"],
+            "n_superkmers_ref": st["n_superkmers"], "superkmer_bases_ref": st["superkmer_bases"]}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    spec = cpu_sample_spec(args.gpus)
+    for _ in range(args.warmup if args.warmup < 2 else 1):     # the CPU path has no warm-up effects worth more than one pass
+        run_cpu_oracle(threads, spec)
+    t = []
+    last = None
+    for _ in range(args.steps):
+        last = run_cpu_oracle(threads, spec)
+        t.append(last["seconds"])
+    sec = sum(t) / len(t)
+    value = last["n_bases"] / sec
+    sample = "%d reads x %d bp (1/%d of one GPU's reads), oracle port of the reference algorithm, useHT=1" % (
+        spec["n_reads"], READ_LEN, FULL_READS // spec["n_reads"])
+    line = {"impl": "reference", "metric": "bases_per_sec", "value": value, "unit": "bases/s", "kmers_per_sec": last["n_kmers"] / sec,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "k=28 m=10 x=3 B=2048 useHT=1, synthetic 150 bp reads (BASELINE configs[1] shape), bounded sample",
+                       "sample_reads": spec["n_reads"]},
+            "cpu_baseline": {"value": value, "unit": "bases/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--reads", type=int, default=FULL_READS, help="reads per GPU (default: the full configs[1] size)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import fastkmer_b200 as fk
+    from fastkmer_b200 import api
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("WORLD_SIZE %d != --gpus %d" % (world, args.gpus))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.Stream()                        # a real (non-NULL) stream: kernels and timing events share it
+    torch.cuda.set_stream(stream)
+    ctx = fk.Context(local_rank, stream.cuda_stream)
+    cfg = fk.TestConfiguration("", "", K, M, X, max_b=B, useHT=True, write=False)
+    spec = workload(args.reads, world)
+    spec["first_read"] = rank * args.reads
+
+    if world > 1:
+        from fastkmer_b200 import multigpu
+        job = multigpu.ShardedJob(ctx, cfg, dist, rank, world)
+    else:
+        job = None
+
+    # ---------------- device-resident input ----------------
+    d_b, d_i, n_pos = ctx.synth_packed_device(spec)
+
+    def step_resident():
+        if job is None:
+            return ctx.count_packed_device(cfg, d_b, d_i, n_pos, want_result=False)[1]
+        return job.count_packed_device(d_b, d_i, n_pos)
+
+    launches0 = None
+    st = None
+    for _ in range(args.warmup):
+        st = step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = api.load_library().fkm_total_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage = [0.0] * 8
+    e0.record(stream)
+    for _ in range(args.steps):
+        st = step_resident()
+        for i in range(8):
+            stage[i] += st["ms_stage"][i]
+    e1.record(stream)
+    barrier()
+    launches = api.load_library().fkm_total_launches() - launches0
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_step = ms / args.steps
+    stage = [s / args.steps for s in stage]
+    n_bases_total = args.reads * READ_LEN * world
+    n_kmers_total = st["n_kmers_global"] if "n_kmers_global" in st else st["n_kmers"]
+    n_distinct_total = st["n_distinct_global"] if "n_distinct_global" in st else st["n_distinct"]
+    value = n_bases_total / (ms_step * 1e-3)
+
+    # ---------------- end to end from host FASTA ----------------
+    e2e = None
+    if not args.no_e2e:
+        nbytes = api.C.c_uint64()
+        s = api._synth(spec)
+        api._check(api.load_library().fkm_synth_fasta_host(api.C.byref(s), None, 0, api.C.byref(nbytes)))
+        pinned = api.host_alloc(nbytes.value)
+        fasta = fk.synth_fasta(spec, out=pinned)
+
+        def step_e2e():
+            if job is None:
+                return ctx.count_fasta(cfg, fasta, want_result=False)[1]
+            return job.count_fasta(fasta)
+
+        for _ in range(max(1, args.warmup - 1)):
+            se = step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            se = step_e2e()
+        barrier()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        assert se["digest_sum"] == st["digest_sum"] and se["n_kmers"] == st["n_kmers"], "host path and resident path disagree"
+        e2e = {"value": n_bases_total / (dt / args.steps), "unit": "bases/s", "h2d_bytes_per_step": int(se["h2d_bytes"]),
+               "d2h_bytes_per_step": int(se["d2h_bytes"]), "ms_per_step": dt / args.steps * 1e3,
+               "ms_h2d_and_parse": se["ms_stage"][0]}
+
+    if rank != 0:
+        return
+
+    # ---------------- CPU baseline (oracle port) on a bounded sample ----------------
+    cpu = None
+    ls_per_kmer = 3.73                                   # SURVEY §8(d) planning ratio for k28/m10 (reference cutting rule)
+    if not args.no_cpu and world == 1:
+        threads = os.cpu_count() or 1
+        cs = cpu_sample_spec(world)
+        r = run_cpu_oracle(threads, cs)
+        ls_per_kmer = r["superkmer_bases_ref"] / max(1, r["n_kmers"])
+        cpu = {"value": r["n_bases"] / r["seconds"], "unit": "bases/s", "cores": threads, "kind": "port",
+               "kmers_per_sec": r["n_kmers"] / r["seconds"],
+               "sample": "%d reads x %d bp of the same generator, %.1f s" % (cs["n_reads"], READ_LEN, r["seconds"])}
+
+    # ---------------- roofline ----------------
+    peak, peak_src = measured_peaks()
+    # algorithmic bytes of the whole pipeline, SURVEY §8(d): N_b/4 + 2*L_s/4 + D*(W+4), L_s under the reference's cutting rule
+    L_s = ls_per_kmer * n_kmers_total
+    bytes_alg = n_bases_total / 4 + 2 * L_s / 4 + n_distinct_total * 12
+    # dominant kernel: k_count_ht (stage 3).  It reads the super-k-mer stream once (L_s/4 algorithmic bytes); the
+    # distinct (k-mer,count) pairs leave through k_compact_ht (stage 4).
+    n_count_launches = max(1, int(st["n_batches"]))
+    count_bytes = (L_s / 4) / world
+    count_ms = stage[3]
+    roofline = {"bound": "hbm", "kernel": "k_count_ht", "achieved": count_bytes / (count_ms * 1e-3) / 1e9 if count_ms else None,
+                "peak": peak, "unit": "GB/s", "frac": (count_bytes / (count_ms * 1e-3) / 1e9 / peak) if count_ms else None,
+                "traffic": None, "peak_source": peak_src, "launches_per_step": n_count_launches,
+                "avg_launch_ms": count_ms / n_count_launches,
+                "pipeline": {"bytes_alg": bytes_alg, "achieved": bytes_alg / (ms_step * 1e-3) / 1e9 / world,
+                             "frac": bytes_alg / (ms_step * 1e-3) / 1e9 / world / peak}}
+    line = {"metric": "bases_per_sec", "value": value, "unit": "bases/s", "kmers_per_sec": n_kmers_total / (ms_step * 1e-3),
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: k=28 m=10 x=3 B=2048 useHT=1, %d synthetic %d bp reads per GPU (30x genome, 1%% subst, 0.1%% N)"
+                                   % (args.reads, READ_LEN), "reads_per_gpu": args.reads, "n_bases": n_bases_total,
+                       "n_kmers": int(n_kmers_total), "n_distinct": int(n_distinct_total),
+                       "l2": "inputs (%.1f GB packed) larger than L2, no flush" % (n_pos * 3 / 8 / 1e9)},
+            "stage_ms": {"histogram": stage[1], "scatter": stage[2], "count": stage[3], "compact": stage[4], "digest": stage[5],
+                         "device_pipeline": stage[7]},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -82,6 +82,7 @@ def load_library():
         "fkm_synth_packed_device": (C.c_int, [vp, C.POINTER(fkm_synth), C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]),
         "fkm_device_free": (C.c_int, [vp, vp]),
         "fkm_debug_window_bins": (C.c_int, [vp, cfgp, vp, vp, u64, vp]),
+        "fkm_debug_pack_fasta_device": (C.c_int, [vp, vp, u64, vp, vp, u64, C.POINTER(u64), C.POINTER(u64)]),
         "fkm_total_launches": (u64, []),
     }
     for name, (res, args) in sig.items():
@@ -292,6 +293,18 @@ class Context:
             if p.value == ptr:
                 self._dev_bufs.remove(p)
         _check(load_library().fkm_device_free(self._h, C.c_void_p(ptr)))
+
+    def pack_fasta_device(self, fasta: bytes):
+        """Device ingest of FASTA text, copied back: (bases, inv, n_positions, n_bases) — test hook."""
+        arr = np.frombuffer(fasta, dtype=np.uint8)
+        n_pos, n_bases = C.c_uint64(), C.c_uint64()
+        nw = (arr.size + 1 + 31) // 32 + 1
+        bases = np.zeros(nw, dtype=np.uint64)
+        inv = np.zeros(nw, dtype=np.uint32)
+        _check(load_library().fkm_debug_pack_fasta_device(self._h, arr.ctypes.data, arr.size, bases.ctypes.data, inv.ctypes.data,
+                                                          nw * 32, C.byref(n_pos), C.byref(n_bases)))
+        nw = (n_pos.value + 31) // 32
+        return bases[:nw], inv[:nw], n_pos.value, n_bases.value
 
     def window_bins(self, configuration, bases, inv, n_positions):
         out = np.empty(max(n_positions, 1), dtype=np.int32)

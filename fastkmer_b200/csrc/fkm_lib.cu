@@ -7,6 +7,7 @@
 //   foreachPartition(extractKXmers)     -> k_expand + segmented radix sort + k_rle
 // There is no CPU fallback: every entry point needs a CUDA device.
 #include "fkm_kernels.cuh"
+#include "fkm_ingest.cuh"
 #include "fkm_host.h"
 #include "../../include/fastkmer_b200.h"
 
@@ -122,6 +123,21 @@ extern "C" int fkm_derive(const fkm_config* cfg, int32_t* b, char* out_dir, size
 
 extern "C" int fkm_host_alloc(size_t bytes, void** out) { CK(cudaMallocHost(out, bytes)); return FKM_OK; }
 extern "C" void fkm_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// whole file into pinned host memory (so the H2D copy runs at PCIe speed)
+static int fkm_read_file_pinned(const char* path, uint8_t** out, uint64_t* n) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return fkm_set_error(FKM_EIO, "cannot open %s", path);
+    fseek(f, 0, SEEK_END); long sz = ftell(f); fseek(f, 0, SEEK_SET);
+    if (sz < 0) { fclose(f); return fkm_set_error(FKM_EIO, "cannot size %s", path); }
+    cudaError_t e = cudaMallocHost((void**)out, std::max<long>(sz, 16));
+    if (e != cudaSuccess) { fclose(f); return fkm_set_error(FKM_ENOMEM, "pinned alloc of %ld bytes: %s", sz, cudaGetErrorString(e)); }
+    size_t got = sz ? fread(*out, 1, (size_t)sz, f) : 0;
+    fclose(f);
+    if (got != (size_t)sz) { cudaFreeHost(*out); return fkm_set_error(FKM_EIO, "short read on %s", path); }
+    *n = (uint64_t)sz;
+    return FKM_OK;
+}
 
 // ------------------------------------------------------------------ scan setup
 struct ScanSetup { ScanParams P; size_t smem; int grid; };
@@ -480,37 +496,110 @@ extern "C" int fkm_count_packed_host(fkm_ctx* ctx, const fkm_config* cfg, const 
     return rc;
 }
 
+// FASTA text already in device memory -> packed layout in device memory (fkm_ingest.cuh)
+static int ingest_device(fkm_ctx* ctx, const uint8_t* d_text, uint64_t n, void** d_bases, void** d_inv, uint64_t* n_pos, uint64_t* n_bases) {
+    cudaStream_t s = ctx->stream;
+    IngestParams P; memset(&P, 0, sizeof P);
+    P.text = d_text; P.n = n; P.n_tiles = (n + kIngTile - 1) / kIngTile;
+    const uint64_t cap_words = (n + 1 + 31) / 32 + 1;                 // every text byte keeps at most one position
+    unsigned long long* d_small = nullptr;
+    *d_bases = nullptr; *d_inv = nullptr;
+    auto fail = [&](cudaError_t e, const char* what) {
+        cudaFree(P.tile_nl); cudaFree(P.tile_pos); cudaFree(d_small); cudaFree(*d_bases); cudaFree(*d_inv); *d_bases = *d_inv = nullptr;
+        return fkm_set_error(e == cudaErrorMemoryAllocation ? FKM_ENOMEM : FKM_ECUDA, "ingest %s: %s", what, cudaGetErrorString(e));
+    };
+    cudaError_t e;
+#define CKI(call) do { e = (call); if (e != cudaSuccess) return fail(e, #call); } while (0)
+    CKI(cudaMalloc((void**)&P.tile_nl, (P.n_tiles + 1) * 8)); CKI(cudaMalloc((void**)&P.tile_pos, (P.n_tiles + 1) * 8));
+    CKI(cudaMalloc((void**)&d_small, 64));
+    CKI(cudaMalloc(d_bases, cap_words * 8)); CKI(cudaMalloc(d_inv, cap_words * 4));
+    P.bases = (unsigned long long*)*d_bases; P.inv = (unsigned int*)*d_inv;
+    P.first_hdr = d_small; P.n_hdr = d_small + 1;
+    unsigned long long init[4] = {n, 0, 0, 0};
+    CKI(cudaMemcpyAsync(d_small, init, 32, cudaMemcpyHostToDevice, s));
+    CKI(cudaMemsetAsync(*d_bases, 0, cap_words * 8, s)); CKI(cudaMemsetAsync(*d_inv, 0, cap_words * 4, s));
+    CKI(cudaMemsetAsync(P.tile_pos, 0, (P.n_tiles + 1) * 8, s));
+    if (P.n_tiles) {
+        k_ing_lines<<<(unsigned)P.n_tiles, kIngThreads, 0, s>>>(P); g_launches++; ctx->job_launches++; CKI(cudaGetLastError());
+        k_scan1<1><<<1, 1024, 0, s>>>(P.tile_nl, P.n_tiles); g_launches++; ctx->job_launches++; CKI(cudaGetLastError());
+        k_ing_emit<0><<<(unsigned)P.n_tiles, kIngThreads, 0, s>>>(P); g_launches++; ctx->job_launches++; CKI(cudaGetLastError());
+        k_scan1<0><<<1, 1024, 0, s>>>((long long*)P.tile_pos, P.n_tiles); g_launches++; ctx->job_launches++; CKI(cudaGetLastError());
+        k_ing_emit<1><<<(unsigned)P.n_tiles, kIngThreads, 0, s>>>(P); g_launches++; ctx->job_launches++; CKI(cudaGetLastError());
+    }
+    k_ing_finish<<<1, 32, 0, s>>>(P, d_small + 2, d_small + 3); g_launches++; ctx->job_launches++; CKI(cudaGetLastError());
+    unsigned long long out[2] = {0, 0};
+    CKI(cudaMemcpyAsync(out, d_small + 2, 16, cudaMemcpyDeviceToHost, s));
+    CKI(cudaStreamSynchronize(s));
+#undef CKI
+    cudaFree(P.tile_nl); cudaFree(P.tile_pos); cudaFree(d_small);
+    *n_pos = out[0]; *n_bases = out[1];
+    return FKM_OK;
+}
+
+// H2D of the raw text + device ingest.  Leaves the packed arrays on the device.
+static int upload_and_ingest(fkm_ctx* ctx, const uint8_t* fasta, uint64_t n_bytes, void** d_bases, void** d_inv,
+                             uint64_t* n_pos, uint64_t* n_bases, uint64_t* launches) {
+    CK(cudaSetDevice(ctx->device));
+    ctx->job_launches = 0;
+    uint8_t* d_text = nullptr;
+    CK(cudaMalloc((void**)&d_text, std::max<uint64_t>(n_bytes, 16)));
+    cudaError_t e = cudaMemcpyAsync(d_text, fasta, n_bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { cudaFree(d_text); CK(e); }
+    int rc = ingest_device(ctx, d_text, n_bytes, d_bases, d_inv, n_pos, n_bases);
+    cudaFree(d_text);
+    if (launches) *launches = ctx->job_launches;
+    return rc;
+}
+
 extern "C" int fkm_count_fasta(fkm_ctx* ctx, const fkm_config* cfg, const uint8_t* fasta, uint64_t n_bytes,
                                fkm_result** out, fkm_stats* stats) {
     if (!ctx) return fkm_set_error(FKM_EINVAL, "ctx is NULL");
     int32_t B = 0; int rc = validate(cfg, &B); if (rc) return rc;
     auto t0 = std::chrono::steady_clock::now();
-    uint64_t n_pos = 0, n_bases = 0;
-    rc = fkm_pack_fasta(fasta, n_bytes, nullptr, nullptr, 0, &n_pos, &n_bases); if (rc) return rc;
-    const uint64_t nw = (n_pos + 31) / 32;
-    uint64_t* hb = nullptr; uint32_t* hi = nullptr;
-    CK(cudaMallocHost((void**)&hb, std::max<size_t>(8, nw * 8)));
-    cudaError_t e = cudaMallocHost((void**)&hi, std::max<size_t>(4, nw * 4));
-    if (e != cudaSuccess) { cudaFreeHost(hb); CK(e); }
-    rc = fkm_pack_fasta(fasta, n_bytes, hb, hi, nw * 32, &n_pos, &n_bases);
+    void *d_b = nullptr, *d_i = nullptr; uint64_t n_pos = 0, n_bases = 0, launches = 0;
+    rc = upload_and_ingest(ctx, fasta, n_bytes, &d_b, &d_i, &n_pos, &n_bases, &launches); if (rc) return rc;
     fkm_stats local; fkm_stats* st = stats ? stats : &local;
-    if (!rc) {
-        double ms_pack = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        rc = fkm_count_packed_host(ctx, cfg, hb, hi, n_pos, out, st);
-        st->n_bases = n_bases; st->ms_stage[0] += ms_pack; st->ms_total += ms_pack;
+    const double ms_in = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    st->h2d_bytes = n_bytes + 32; st->n_bases = n_bases; st->ms_stage[0] = ms_in;
+    rc = count_device(ctx, cfg, d_b, d_i, n_pos, out, st);
+    st->d2h_bytes += 16; st->gpu_launches += launches; st->ms_total += ms_in;
+    cudaFree(d_b); cudaFree(d_i);
+    return rc;
+}
+
+// test hook: the device ingest's packed arrays, copied back
+extern "C" int fkm_debug_pack_fasta_device(fkm_ctx* ctx, const uint8_t* fasta, uint64_t n_bytes, uint64_t* bases, uint32_t* invalid,
+                                           uint64_t cap_positions, uint64_t* n_positions, uint64_t* n_bases) {
+    if (!ctx) return fkm_set_error(FKM_EINVAL, "ctx is NULL");
+    void *d_b = nullptr, *d_i = nullptr; uint64_t n_pos = 0, nb = 0;
+    int rc = upload_and_ingest(ctx, fasta, n_bytes, &d_b, &d_i, &n_pos, &nb, nullptr); if (rc) return rc;
+    if (n_positions) *n_positions = n_pos;
+    if (n_bases) *n_bases = nb;
+    if (bases && invalid) {
+        const uint64_t nw = (n_pos + 31) / 32;
+        if (nw * 32 > cap_positions) rc = fkm_set_error(FKM_EINVAL, "packed buffer too small");
+        else {
+            cudaMemcpy(bases, d_b, nw * 8, cudaMemcpyDeviceToHost);
+            cudaError_t e = cudaMemcpy(invalid, d_i, nw * 4, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) rc = fkm_set_error(FKM_ECUDA, "copy back: %s", cudaGetErrorString(e));
+        }
     }
-    cudaFreeHost(hb); cudaFreeHost(hi);
+    cudaFree(d_b); cudaFree(d_i);
     return rc;
 }
 
 extern "C" int fkm_execute_job(fkm_ctx* ctx, const fkm_config* cfg, fkm_stats* stats) {
     int32_t B = 0; int rc = validate(cfg, &B); if (rc) return rc;
     if (!cfg->dataset) return fkm_set_error(FKM_EINVAL, "dataset path is NULL");
-    std::vector<uint8_t> text;
-    rc = fkm_read_file(cfg->dataset, text); if (rc) return rc;
+    if (!ctx) return fkm_set_error(FKM_EINVAL, "ctx is NULL");
+    CK(cudaSetDevice(ctx->device));
+    uint8_t* text = nullptr; uint64_t n_text = 0;
+    rc = fkm_read_file_pinned(cfg->dataset, &text, &n_text); if (rc) return rc;
     fkm_result* res = nullptr;
     fkm_stats local; fkm_stats* st = stats ? stats : &local;
-    rc = fkm_count_fasta(ctx, cfg, text.data(), text.size(), &res, st); if (rc) return rc;
+    rc = fkm_count_fasta(ctx, cfg, text, n_text, &res, st);
+    cudaFreeHost(text);
+    if (rc) return rc;
     if (cfg->write) {                                        // writers are lazy in the reference: nothing is created when !write (SBKC:552-554)
         char dir[4096];
         rc = fkm_derive(cfg, nullptr, dir, sizeof dir);

@@ -99,7 +99,8 @@ int  fkm_derive(const fkm_config* cfg, int32_t* b, char* out_dir, size_t out_dir
 int  fkm_execute_job(fkm_ctx* ctx, const fkm_config* cfg, fkm_stats* stats);
 
 /* ---- in-memory variants (same path, no file I/O) ---------------------------- */
-/* FASTA text in host memory (pinned if it came from fkm_host_alloc).           */
+/* FASTA text in host memory (pinned if it came from fkm_host_alloc).  The raw
+ * text is copied to the GPU and parsed there (record split of SURVEY App. A.1). */
 int  fkm_count_fasta(fkm_ctx* ctx, const fkm_config* cfg, const uint8_t* fasta, uint64_t n_bytes,
                      fkm_result** out, fkm_stats* stats);
 
@@ -154,6 +155,9 @@ int  fkm_device_free(fkm_ctx* ctx, void* d_ptr);
  * bins_out has n_positions entries.                                             */
 int  fkm_debug_window_bins(fkm_ctx* ctx, const fkm_config* cfg, const uint64_t* bases, const uint32_t* invalid,
                            uint64_t n_positions, int32_t* bins_out);
+/* the device ingest's packed arrays (must equal fkm_pack_fasta bit for bit)     */
+int  fkm_debug_pack_fasta_device(fkm_ctx* ctx, const uint8_t* fasta, uint64_t n_bytes, uint64_t* bases, uint32_t* invalid,
+                                 uint64_t cap_positions, uint64_t* n_positions, uint64_t* n_bases);
 uint64_t fkm_total_launches(void);    /* kernels launched by this process so far */
 
 #ifdef __cplusplus

@@ -250,3 +250,43 @@ def test_cli_matches_reference_argv(oracle, tmp_path):
         assert body.endswith(b"EOF")
         lines += [b"%d\t%s\n" % (b, ln) for ln in body[:-3].splitlines()]
     assert hashlib.sha256(b"".join(sorted(lines))).hexdigest() == GOLD["G4"][-1]
+
+
+# ---------------------------------------------------------------- device FASTA ingest == host packer, bit for bit
+INGEST_TEXTS = [
+    b"", b"no header here\nACGT\n", b">only header", b">h\n", b">a\nACGTN\nAC\n>b x\nTTTT\n", b">a\r\nAC\r\nGT\r\n",
+    b"junk\n>a\nACGTacgtRYKM\n\n\nAC GT\n>b\n>c\nA", b">x\n" + b"ACGT" * 40 + b"\n>y\n" + b"TTGCA" * 13, b">a\nAC>GT\n>b\nGG\n",
+    b"\n\n>a\n\nAC\n\n", b">a\n" + b"ACGT" * 5000,                       # one line longer than a tile, no final newline
+    b">" + b"h" * 20000 + b"\nACGT\n>b\nGGCC\n",                       # header longer than two tiles
+]
+
+
+@pytest.mark.parametrize("idx", range(len(INGEST_TEXTS)))
+def test_device_ingest_equals_host_pack(ctx, idx):
+    text = INGEST_TEXTS[idx]
+    hb, hi, hn, hbases = fk.pack_fasta(text)
+    db, di, dn, dbases = ctx.pack_fasta_device(text)
+    assert (dn, dbases) == (hn, hbases)
+    assert np.array_equal(db, hb) and np.array_equal(di, hi)
+
+
+def test_device_ingest_random_texts(ctx):
+    rng = random.Random(99)
+    for trial in range(6):
+        parts = []
+        if trial % 2:
+            parts.append("leading junk\nmore junk\n")
+        for r in range(rng.randint(1, 400)):
+            L = rng.choice([0, 1, 31, 32, 33, 100, 150, 1000, 9000])
+            s = "".join(rng.choice("ACGTNacgt>\r ") if rng.random() < 0.03 else rng.choice("ACGT") for _ in range(L))
+            width = rng.choice([None, 60, 70, 7])
+            if width:
+                s = "\n".join(s[i:i + width] for i in range(0, len(s), width))
+            parts.append(">r%d %s\n%s%s" % (r, "x" * rng.randint(0, 80), s, "\n" if rng.random() < 0.95 else ""))
+            if not parts[-1].endswith("\n"):
+                parts[-1] += "\n"
+        text = "".join(parts).encode()
+        hb, hi, hn, hbases = fk.pack_fasta(text)
+        db, di, dn, dbases = ctx.pack_fasta_device(text)
+        assert (dn, dbases) == (hn, hbases)
+        assert np.array_equal(db, hb) and np.array_equal(di, hi)
