@@ -165,12 +165,16 @@ def synth_fasta(spec, out=None) -> np.ndarray:
 
 
 class CountResult:
-    """Per-bin (canonical k-mer, count) arrays held on the device; numpy views on demand."""
+    """Per-bin (canonical k-mer, count) arrays held on the device; numpy copies on demand.
 
-    def __init__(self, handle, k):
+    The device arrays belong to the context's job arena and stay valid until the next job on
+    that context: call arrays()/write() before counting again (arrays() caches host copies)."""
+
+    def __init__(self, handle, k, ctx=None):
         self._h = handle
         self.k = k
         self._cache = None
+        self._ctx = ctx            # the arrays live in the context's arena: keep it alive
 
     def __len__(self):
         return int(load_library().fkm_result_size(self._h))
@@ -265,20 +269,20 @@ class Context:
         st, cfg, h = fkm_stats(), _cfg(configuration), C.c_void_p()
         _check(load_library().fkm_count_fasta(self._h, C.byref(cfg), arr.ctypes.data, arr.size,
                                               C.byref(h) if want_result else None, C.byref(st)))
-        return (CountResult(h, configuration.k) if want_result else None), _stats(st)
+        return (CountResult(h, configuration.k, self) if want_result else None), _stats(st)
 
     def count_packed_host(self, configuration, bases, inv, n_positions, want_result=True):
         st, cfg, h = fkm_stats(), _cfg(configuration), C.c_void_p()
         _check(load_library().fkm_count_packed_host(self._h, C.byref(cfg), bases.ctypes.data, inv.ctypes.data, n_positions,
                                                     C.byref(h) if want_result else None, C.byref(st)))
-        return (CountResult(h, configuration.k) if want_result else None), _stats(st)
+        return (CountResult(h, configuration.k, self) if want_result else None), _stats(st)
 
     def count_packed_device(self, configuration, d_bases, d_inv, n_positions, want_result=True):
         """d_bases / d_inv: raw device pointers (ints) in the library's packed layout."""
         st, cfg, h = fkm_stats(), _cfg(configuration), C.c_void_p()
         _check(load_library().fkm_count_packed_device(self._h, C.byref(cfg), C.c_void_p(d_bases), C.c_void_p(d_inv), n_positions,
                                                       C.byref(h) if want_result else None, C.byref(st)))
-        return (CountResult(h, configuration.k) if want_result else None), _stats(st)
+        return (CountResult(h, configuration.k, self) if want_result else None), _stats(st)
 
     def synth_packed_device(self, spec):
         """-> (d_bases, d_inv, n_positions): synthetic reads generated in device memory (freed with the context)."""

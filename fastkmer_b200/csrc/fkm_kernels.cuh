@@ -100,11 +100,10 @@ struct ScanParams {
     const uint64_t* bases; const uint32_t* inv;
     uint64_t n_pos;                 // positions in the input
     uint64_t n_words;               // u64 words in bases (= u32 words in inv)
+    uint64_t e_total;               // window-end positions to visit
+    uint64_t n_seg; uint32_t seg_len;   // segments of seg_len window ends (multiple of 32), one warp each
     int k, m, w;                    // w = k-m+1 m-mers per window
-    int nb;                         // blocks of w positions per thread
-    int wpad;                       // w rounded up to odd (bank-conflict-free stride)
-    uint32_t T;                     // window starts per tile = 256*nb*w
-    uint64_t n_tiles;
+    int L, d;                       // w = 2^L + d, 0 <= d < 2^L
     uint32_t B;
     int cap;                        // max k-mers per record
     int smem_hist;                  // 1: per-CTA histogram in shared memory (B <= 4096)
@@ -116,180 +115,211 @@ struct ScanParams {
     int32_t* dbg_bins;              // [n_pos]                        (MODE 2)
 };
 
-// Iterator over consecutive window starts of a tile; yields the window's
-// signature value (minimum norm over its w m-mers) or kInvalidMin.
-struct WinIter {
-    const uint32_t* s_h; const uint32_t* s_g; const uint32_t* s_inv;
-    int k, w, wpad;
-    int i, blk, off, bad_end; uint32_t invw;
-    __device__ __forceinline__ void init(int i0) {
-        i = i0; blk = i0 / w; off = i0 - blk * w;
-        bad_end = 0;
-        if (k > 1) {
-            uint64_t bits = bits64_at(s_inv, (uint32_t)i0) >> (64 - (k - 1));   // positions i0 .. i0+k-2
-            if (bits) bad_end = i0 + (k - 2 - (__ffsll((long long)bits) - 1)) + 1;
-        }
-        invw = s_inv[(i0 + k - 1) >> 5];
-    }
-    __device__ __forceinline__ uint32_t value() {
-        int p = i + k - 1;
-        if ((invw >> (31 - (p & 31))) & 1u) bad_end = p + 1;
-        if (i < bad_end) return kInvalidMin;
-        uint32_t h = s_h[blk * wpad + off];
-        uint32_t g = off ? s_g[(blk + 1) * wpad + off - 1] : s_g[blk * wpad + w - 1];
-        return min(h, g);
-    }
-    __device__ __forceinline__ void advance() {
-        i++; off++;
-        if (off == w) { off = 0; blk++; }
-        int p = i + k - 1;
-        if ((p & 31) == 0) invw = s_inv[p >> 5];
-    }
-};
+__device__ __forceinline__ uint32_t revcomp32(uint32_t v, int len) {       // len <= 15
+    uint32_t x = __brev(~v);
+    x = ((x & 0xAAAAAAAAu) >> 1) | ((x & 0x55555555u) << 1);
+    return x >> (32 - 2 * len);
+}
 
 // MODE 0: histogram (records and k-mers per bin).  MODE 1: scatter the records.
 // MODE 2: per-window bin ids (test hook).
 //
-// One CTA per tile of T window starts (persistent, grid-strided).  Phase 1: each
-// thread rolls the forward and reverse-complement m-mer over blocks of w
-// positions, stores norm values and their in-block prefix minima; phase 2 turns
-// the norm values into in-block suffix minima (van Herk / Gil-Werman: the minimum
-// over any w consecutive positions is min(suffix[i], prefix[i+w-1])).  Phase 3:
-// each thread walks its chunk of windows, starts a run wherever the signature
-// value changes, extends it (possibly past its chunk) and emits <= cap k-mers per
-// record.  Runs are cut at tile boundaries; the reference's own cutting rule
-// (SBKC:102-136) is not observable.
+// Warp-striped sliding window.  A warp owns a segment of consecutive window-END
+// positions and walks it 32 at a time, lane l <-> position e = 32 g + l:
+//   * the m-mer ending at e is cut out of two broadcast 64-bit words (funnel shift),
+//     its reverse complement comes from brev, norm() is the closed form of UTIL:46-100;
+//   * the minimum over the window's w = 2^L + d m-mers is built by doubling with warp
+//     shuffles: x_{j+1}[e] = min(x_j[e], x_j[e - 2^j]); values that fall before lane 0
+//     come from the previous group's registers (prev[j]);
+//   * a window is valid iff the last invalid position at or before e is >= k behind;
+//   * run boundaries (signature value changes / validity changes) are found with one
+//     shuffle and two ballots; every lane that sees a run END pushes (start, length,
+//     value) into a per-warp queue in shared memory, and the queue is drained 32 events
+//     at a time so that hashing, atomics and record extraction run with full lanes.
+// Two warm-up groups before each segment rebuild the register state, so segments are
+// independent; runs are cut at segment boundaries (the reference's own cutting rule,
+// SBKC:102-136, is not observable: SURVEY §7).
 template <bool WIDE, int MODE>
 __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x;
-    const int k = P.k, m = P.m, w = P.w, wpad = P.wpad, nb = P.nb;
-    const uint32_t T = P.T;
-    const int nblk = kScanThreads * nb + 1;
-    const uint32_t nwords = (T + (uint32_t)k + 31u) / 32u + 6u;
-    uint64_t* s_bases = reinterpret_cast<uint64_t*>(smem_raw);
-    uint32_t* s_inv = reinterpret_cast<uint32_t*>(s_bases + nwords);
-    uint32_t* s_h = s_inv + nwords + (nwords & 1u);
-    uint32_t* s_g = s_h + (size_t)nblk * wpad;
-    uint32_t* s_hist_rec = s_g + (size_t)nblk * wpad;
+    __shared__ unsigned long long q_rs[kScanThreads / 32][64];
+    __shared__ uint32_t q_n[kScanThreads / 32][64];
+    __shared__ uint32_t q_v[kScanThreads / 32][64];
+    uint32_t* s_hist_rec = reinterpret_cast<uint32_t*>(smem_raw);
     uint32_t* s_hist_kmer = s_hist_rec + P.B;
-    const uint32_t mmask = (m == 16) ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1u);
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int k = P.k, m = P.m, L = P.L, d = P.d;
+    const uint32_t mmask = (1u << (2 * m)) - 1u;
 
     if (MODE == 0 && P.smem_hist) {
-        for (uint32_t b = tid; b < P.B; b += kScanThreads) { s_hist_rec[b] = 0; s_hist_kmer[b] = 0; }
+        for (uint32_t b = threadIdx.x; b < P.B; b += kScanThreads) { s_hist_rec[b] = 0; s_hist_kmer[b] = 0; }
+        __syncthreads();
     }
 
-    for (uint64_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-        const uint64_t t0 = tile * (uint64_t)T;
-        const uint64_t word0 = t0 >> 5;
-        __syncthreads();                       // previous tile fully consumed
-        for (uint32_t j = tid; j < nwords; j += kScanThreads) {
-            uint64_t gw = word0 + j;
-            bool in = gw < P.n_words;
-            s_bases[j] = in ? P.bases[gw] : 0ull;
-            uint32_t iv = in ? P.inv[gw] : 0xFFFFFFFFu;
-            // positions >= n_pos are invalid
-            uint64_t p0 = gw << 5;
-            if (p0 + 32 > P.n_pos) iv |= (p0 >= P.n_pos) ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (uint32_t)(P.n_pos - p0));
-            s_inv[j] = iv;
-        }
-        __syncthreads();
-
-        // ---- phase 1+2: norm values, in-block prefix (g) and suffix (h) minima
-        const int nmine = nb + (tid == kScanThreads - 1 ? 1 : 0);
-        for (int jb = 0; jb < nmine; jb++) {
-            const int blk = tid * nb + jb;
-            const uint32_t q0 = (uint32_t)blk * (uint32_t)w;
-            uint32_t v = (uint32_t)(bases64_at(s_bases, q0) >> (64 - 2 * m));
-            uint32_t r = (uint32_t)revcomp64(v, m);
-            uint32_t q = q0 + (uint32_t)m;                      // next base to enter
-            uint64_t bw = s_bases[q >> 5];
-            uint32_t* hrow = s_h + blk * wpad;
-            uint32_t* grow = s_g + blk * wpad;
-            uint32_t g = kInvalidMin;
-            for (int off = 0; off < w; off++) {
-                uint32_t nv = mmer_norm(v, r, m, mmask);
-                g = min(g, nv);
-                hrow[off] = nv; grow[off] = g;
-                uint32_t b = (uint32_t)(bw >> (62 - 2 * (q & 31))) & 3u;
-                v = ((v << 2) | b) & mmask;
-                r = (r >> 2) | ((3u - b) << (2 * m - 2));
-                q++;
-                if ((q & 31) == 0) bw = s_bases[q >> 5];
+    auto load_bases = [&](unsigned long long gw) -> uint64_t { return gw < P.n_words ? P.bases[gw] : 0ull; };
+    auto load_inv = [&](unsigned long long gw) -> uint32_t {
+        if (gw >= P.n_words) return 0xFFFFFFFFu;
+        uint32_t iv = P.inv[gw];
+        const unsigned long long p0 = gw << 5;
+        if (p0 + 32 > P.n_pos) iv |= (p0 >= P.n_pos) ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (uint32_t)(P.n_pos - p0));
+        return iv;
+    };
+    // one event = one run of `n` windows whose first window ENDS at position rs, signature value v
+    auto emit_event = [&](unsigned long long rs, uint32_t n, uint32_t v) {
+        const uint32_t bin = hash_to_bucket(v, P.B);
+        for (uint32_t off = 0; off < n; off += (uint32_t)P.cap) {
+            const uint32_t nn = min((uint32_t)P.cap, n - off);
+            if (MODE == 0) {
+                if (P.smem_hist) { atomicAdd(&s_hist_rec[bin], 1u); atomicAdd(&s_hist_kmer[bin], nn); }
+                else { atomicAdd(&P.hist_rec[bin], 1ull); atomicAdd(&P.hist_kmer[bin], (unsigned long long)nn); }
+            } else if (MODE == 1) {
+                const unsigned long long slot = P.bin_base[bin] + atomicAdd(&P.cursor[bin], 1ull);
+                const unsigned long long a = rs + off - (unsigned long long)(k - 1);     // first base of the piece
+                const unsigned long long j = a >> 5; const uint32_t sh = 2u * (uint32_t)(a & 31ull);
+                if constexpr (!WIDE) {
+                    uint64_t w0 = load_bases(j), w1 = load_bases(j + 1), w2 = load_bases(j + 2);
+                    uint64_t r0 = sh ? ((w0 << sh) | (w1 >> (64 - sh))) : w0;
+                    uint64_t r1 = sh ? ((w1 << sh) | (w2 >> (64 - sh))) : w1;
+                    r1 = (r1 & ~0xFFull) | (uint64_t)nn;
+                    reinterpret_cast<ulonglong2*>(P.records)[slot] = make_ulonglong2(r0, r1);
+                } else {
+                    uint64_t x0 = load_bases(j), x1 = load_bases(j + 1), x2 = load_bases(j + 2), x3 = load_bases(j + 3), x4 = load_bases(j + 4);
+                    uint64_t r0 = sh ? ((x0 << sh) | (x1 >> (64 - sh))) : x0;
+                    uint64_t r1 = sh ? ((x1 << sh) | (x2 >> (64 - sh))) : x1;
+                    uint64_t r2 = sh ? ((x2 << sh) | (x3 >> (64 - sh))) : x2;
+                    uint64_t r3 = sh ? ((x3 << sh) | (x4 >> (64 - sh))) : x3;
+                    r3 = (r3 & ~0xFFull) | (uint64_t)nn;
+                    ulonglong2* dst = reinterpret_cast<ulonglong2*>(P.records) + 2 * slot;
+                    dst[0] = make_ulonglong2(r0, r1);
+                    dst[1] = make_ulonglong2(r2, r3);
+                }
             }
-            uint32_t h = hrow[w - 1];
-            for (int off = w - 2; off >= 0; off--) { h = min(h, hrow[off]); hrow[off] = h; }
         }
-        __syncthreads();
+    };
 
-        // ---- phase 3: runs of equal signature value -> records
-        const int Ct = nb * w;
-        const int c0 = tid * Ct, c1 = c0 + Ct;
-        WinIter it; it.s_h = s_h; it.s_g = s_g; it.s_inv = s_inv; it.k = k; it.w = w; it.wpad = wpad;
-        if (MODE == 2) {
-            it.init(c0);
-            for (int i = c0; i < c1; i++) {
-                uint32_t v = it.value();
-                uint64_t gp = t0 + (uint64_t)i;
-                if (gp < P.n_pos) P.dbg_bins[gp] = (v == kInvalidMin) ? -1 : (int32_t)hash_to_bucket(v, P.B);
-                it.advance();
-            }
-            continue;
-        }
-        uint32_t prev = kInvalidMin;
-        if (c0 > 0) { it.init(c0 - 1); prev = it.value(); it.advance(); }
-        else it.init(0);
-        uint32_t cur = it.value();
-        while (it.i < c1) {
-            if (cur != kInvalidMin && cur != prev) {
-                const int a = it.i;
-                uint32_t nxt;
-                do {
-                    it.advance();
-                    nxt = (it.i < (int)T) ? it.value() : kInvalidMin;
-                } while (nxt == cur);
-                const int e = it.i;                            // run = windows [a, e)
-                const uint32_t bin = hash_to_bucket(cur, P.B);
-                for (int s = a; s < e; s += P.cap) {
-                    const int n = min(P.cap, e - s);
-                    if (MODE == 0) {
-                        if (P.smem_hist) { atomicAdd(&s_hist_rec[bin], 1u); atomicAdd(&s_hist_kmer[bin], (uint32_t)n); }
-                        else { atomicAdd(&P.hist_rec[bin], 1ull); atomicAdd(&P.hist_kmer[bin], (unsigned long long)n); }
-                    } else {
-                        const unsigned long long slot = P.bin_base[bin] + atomicAdd(&P.cursor[bin], 1ull);
-                        const uint32_t j = (uint32_t)s >> 5, sh = 2u * ((uint32_t)s & 31u);
-                        if constexpr (!WIDE) {
-                            uint64_t w0 = s_bases[j], w1 = s_bases[j + 1], w2 = s_bases[j + 2];
-                            uint64_t r0 = sh ? ((w0 << sh) | (w1 >> (64 - sh))) : w0;
-                            uint64_t r1 = sh ? ((w1 << sh) | (w2 >> (64 - sh))) : w1;
-                            r1 = (r1 & ~0xFFull) | (uint64_t)n;
-                            reinterpret_cast<ulonglong2*>(P.records)[slot] = make_ulonglong2(r0, r1);
-                        } else {
-                            uint64_t x0 = s_bases[j], x1 = s_bases[j + 1], x2 = s_bases[j + 2], x3 = s_bases[j + 3], x4 = s_bases[j + 4];
-                            uint64_t r0 = sh ? ((x0 << sh) | (x1 >> (64 - sh))) : x0;
-                            uint64_t r1 = sh ? ((x1 << sh) | (x2 >> (64 - sh))) : x1;
-                            uint64_t r2 = sh ? ((x2 << sh) | (x3 >> (64 - sh))) : x2;
-                            uint64_t r3 = sh ? ((x3 << sh) | (x4 >> (64 - sh))) : x3;
-                            r3 = (r3 & ~0xFFull) | (uint64_t)n;
-                            ulonglong2* dst = reinterpret_cast<ulonglong2*>(P.records) + 2 * slot;
-                            dst[0] = make_ulonglong2(r0, r1);
-                            dst[1] = make_ulonglong2(r2, r3);
+    int qn = 0;                                              // events waiting in this warp's queue (warp-uniform)
+    const unsigned long long n_warps = (unsigned long long)gridDim.x * (kScanThreads / 32);
+    for (unsigned long long seg = (unsigned long long)blockIdx.x * (kScanThreads / 32) + warp; seg < P.n_seg; seg += n_warps) {
+        const unsigned long long e0 = seg * P.seg_len;
+        const unsigned long long e1 = min(e0 + (unsigned long long)P.seg_len, (unsigned long long)P.e_total);
+        const unsigned long long g0 = e0 >> 5, g1 = (e1 + 31) >> 5;
+        const unsigned long long gs = g0 >= 2 ? g0 - 2 : 0;   // two warm-up groups (>= k-1 positions)
+        long long carry_bad = (long long)(gs << 5) - 1;       // last invalid position seen so far
+        uint32_t prev[7];
+#pragma unroll
+        for (int j = 0; j < 7; j++) prev[j] = kInvalidMin;
+        uint32_t prev_last = kInvalidMin;                     // value of the window ending just before this group
+        unsigned long long run_start = 0;                     // END position of the first window of the open run
+        uint64_t Wprev = gs > 0 ? load_bases(gs - 1) : 0ull;
+
+        for (unsigned long long gb = gs; gb < g1; gb += 32) {
+            const uint64_t Wb = load_bases(gb + lane);
+            const uint32_t Ib = load_inv(gb + lane);
+            const int ng = (int)min(32ull, g1 - gb);
+            for (int gi = 0; gi < ng; gi++) {
+                const uint64_t W = __shfl_sync(FULL, Wb, gi);
+                const uint32_t IW = __shfl_sync(FULL, Ib, gi);
+                const unsigned long long g = gb + gi;
+                const unsigned long long e = (g << 5) + lane;
+                const bool real = g >= g0;
+                // ---- m-mer ending at e: low 2m bits of (Wprev:W) >> 2*(31-lane)
+                const uint32_t sh = 2u * (31u - (uint32_t)lane);
+                const uint32_t lo = sh < 32 ? (uint32_t)W : (uint32_t)(W >> 32);
+                const uint32_t hi = sh < 32 ? (uint32_t)(W >> 32) : (uint32_t)Wprev;
+                const uint32_t v = __funnelshift_r(lo, hi, sh & 31u) & mmask;
+                uint32_t x = mmer_norm(v, revcomp32(v, m), m, mmask);
+                // ---- minimum over the last w m-mers (doubling)
+#pragma unroll
+                for (int j = 0; j < 6; j++) {
+                    if (j < L) {
+                        const int s = 1 << j;
+                        const uint32_t cur = x;
+                        uint32_t partner;
+                        if (s == 32) partner = prev[j];
+                        else {
+                            const uint32_t t = __shfl_up_sync(FULL, cur, s);
+                            const uint32_t u = __shfl_sync(FULL, prev[j], (lane - s) & 31);
+                            partner = lane >= s ? t : u;
                         }
+                        x = min(cur, partner);
+                        prev[j] = cur;
                     }
                 }
-                prev = cur; cur = nxt;
-                // the window at it.i (value nxt) is evaluated by the next loop turn
-            } else {
-                prev = cur;
-                it.advance();
-                cur = (it.i < c1) ? it.value() : kInvalidMin;
+                if (d > 0) {
+                    const uint32_t cur = x;
+                    const uint32_t t = __shfl_up_sync(FULL, cur, d);
+                    const uint32_t u = __shfl_sync(FULL, prev[6], (lane - d) & 31);
+                    x = min(cur, lane >= d ? t : u);
+                    prev[6] = cur;
+                }
+                // ---- validity: last invalid position <= e must be at least k behind
+                const uint32_t tb = IW >> (31 - lane);
+                const long long last_bad = tb ? (long long)e - (long long)(__ffs((int)tb) - 1) : carry_bad;
+                const bool valid = ((long long)e - last_bad) >= (long long)k;
+                if (IW) carry_bad = (long long)(g << 5) + 31 - (long long)(__ffs((int)IW) - 1);
+                const uint32_t Ev = valid ? x : kInvalidMin;
+                Wprev = W;
+                if (!real) continue;                                           // warm-up group (warp-uniform)
+                if (MODE == 2) {
+                    if (e + 1 >= (unsigned long long)k) {
+                        const unsigned long long i = e + 1 - (unsigned long long)k;
+                        if (i < P.n_pos) P.dbg_bins[i] = valid ? (int32_t)hash_to_bucket(x, P.B) : -1;
+                    }
+                    continue;
+                }
+                // ---- run boundaries
+                uint32_t Ep = __shfl_up_sync(FULL, Ev, 1);
+                if (lane == 0) Ep = prev_last;
+                const bool is_start = (Ev != kInvalidMin) && (Ev != Ep);
+                const bool is_end = (Ep != kInvalidMin) && (Ev != Ep);        // the run ending at e-1
+                const uint32_t Sm = __ballot_sync(FULL, is_start), Em = __ballot_sync(FULL, is_end);
+                if (Em) {
+                    if (is_end) {
+                        const uint32_t below = Sm & lt_mask;
+                        const unsigned long long rs = below ? (g << 5) + (unsigned long long)(31 - __clz((int)below)) : run_start;
+                        const int idx = qn + __popc(Em & lt_mask);
+                        q_rs[warp][idx] = rs; q_n[warp][idx] = (uint32_t)(e - rs); q_v[warp][idx] = Ep;
+                    }
+                    qn += __popc(Em);
+                    __syncwarp();
+                    if (qn >= 32) {
+                        emit_event(q_rs[warp][lane], q_n[warp][lane], q_v[warp][lane]);
+                        __syncwarp();
+                        const bool mv = lane < qn - 32;
+                        unsigned long long t0 = 0; uint32_t t1 = 0, t2 = 0;
+                        if (mv) { t0 = q_rs[warp][32 + lane]; t1 = q_n[warp][32 + lane]; t2 = q_v[warp][32 + lane]; }
+                        __syncwarp();
+                        if (mv) { q_rs[warp][lane] = t0; q_n[warp][lane] = t1; q_v[warp][lane] = t2; }
+                        qn -= 32;
+                        __syncwarp();
+                    }
+                }
+                if (Sm) run_start = (g << 5) + (unsigned long long)(31 - __clz((int)Sm));
+                prev_last = __shfl_sync(FULL, Ev, 31);
             }
         }
+        // the run still open at the end of the segment is cut here
+        if (MODE != 2 && prev_last != kInvalidMin) {
+            if (lane == 0) { q_rs[warp][qn] = run_start; q_n[warp][qn] = (uint32_t)((g1 << 5) - run_start); q_v[warp][qn] = prev_last; }
+            qn += 1;
+            __syncwarp();
+            if (qn >= 32) {                 // qn == 32 exactly
+                emit_event(q_rs[warp][lane], q_n[warp][lane], q_v[warp][lane]);
+                qn = 0;
+                __syncwarp();
+            }
+        }
+    }
+    if (MODE != 2) {
+        __syncwarp();
+        if (lane < qn) emit_event(q_rs[warp][lane], q_n[warp][lane], q_v[warp][lane]);
     }
 
     if (MODE == 0 && P.smem_hist) {
         __syncthreads();
-        for (uint32_t b = tid; b < P.B; b += kScanThreads) {
+        for (uint32_t b = threadIdx.x; b < P.B; b += kScanThreads) {
             uint32_t r = s_hist_rec[b];
             if (r) { atomicAdd(&P.hist_rec[b], (unsigned long long)r); atomicAdd(&P.hist_kmer[b], (unsigned long long)s_hist_kmer[b]); }
         }

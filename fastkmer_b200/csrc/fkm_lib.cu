@@ -36,6 +36,50 @@ int fkm_set_error(int code, const char* fmt, ...) {
     return fkm_set_error(e_ == cudaErrorMemoryAllocation ? FKM_ENOMEM : FKM_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
 #define CKL() do { g_launches++; ctx->job_launches++; CK(cudaGetLastError()); } while (0)
 
+// Bump arena for everything a job allocates on the device.  Slabs are only ever added
+// inside a job; when the next job begins, several slabs are merged into one of the
+// peak size, so a steady stream of similar jobs does no cudaMalloc / cudaFree at all.
+struct Arena {
+    struct Slab { char* p; size_t cap, used; };
+    std::vector<Slab> slabs;
+    struct Mark { size_t slab, used; };
+    static size_t up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+    cudaError_t alloc(void** out, size_t n) {
+        n = up(n ? n : 16, 512);
+        if (!slabs.empty() && slabs.back().used + n <= slabs.back().cap) {
+            *out = slabs.back().p + slabs.back().used; slabs.back().used += n; return cudaSuccess;
+        }
+        Slab sl; sl.cap = std::max<size_t>(n, (size_t)64 << 20); sl.used = n;
+        cudaError_t e = cudaMalloc((void**)&sl.p, sl.cap);
+        if (e != cudaSuccess) return e;
+        slabs.push_back(sl); *out = sl.p;
+        return cudaSuccess;
+    }
+    Mark mark() const { return slabs.empty() ? Mark{0, 0} : Mark{slabs.size() - 1, slabs.back().used}; }
+    void release(Mark m) {                       // stack discipline: drop everything allocated after mark()
+        if (slabs.empty()) return;
+        for (size_t i = m.slab + 1; i < slabs.size(); i++) slabs[i].used = 0;
+        // a slab that did not exist at mark() time is simply emptied
+        if (m.slab < slabs.size()) slabs[m.slab].used = std::min(slabs[m.slab].used, m.used);
+    }
+    size_t peak = 0;
+    void note_peak() { size_t t = 0; for (auto& sl : slabs) t += sl.cap == 0 ? 0 : std::max(sl.used, (size_t)0); peak = std::max(peak, t); }
+    cudaError_t reset() {                        // caller guarantees the device is idle
+        size_t total = 0; for (auto& sl : slabs) total += sl.cap;
+        if (slabs.size() > 1) {
+            for (auto& sl : slabs) cudaFree(sl.p);
+            slabs.clear();
+            Slab sl; sl.cap = up(total + total / 50, (size_t)64 << 20); sl.used = 0;
+            cudaError_t e = cudaMalloc((void**)&sl.p, sl.cap);
+            if (e != cudaSuccess) return e;
+            slabs.push_back(sl);
+        }
+        for (auto& sl : slabs) sl.used = 0;
+        return cudaSuccess;
+    }
+    void destroy() { for (auto& sl : slabs) cudaFree(sl.p); slabs.clear(); }
+};
+
 struct fkm_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -46,11 +90,19 @@ struct fkm_ctx {
     double sort_budget_keys = 256.0 * (1 << 20);
     double load_factor = 0.6;
     uint64_t job_launches = 0;
+    uint64_t gen = 0;                 // job generation: results of older jobs are invalid
+    Arena arena;
     cudaEvent_t ev[10];
 };
 
+// job-lifetime device memory (see Arena); "free" is a no-op, the arena is reset by the next job
+static inline cudaError_t dmalloc(fkm_ctx* ctx, void** p, size_t n) { return ctx->arena.alloc(p, n); }
+template <typename T> static inline cudaError_t dmalloc(fkm_ctx* ctx, T** p, size_t n) { return dmalloc(ctx, (void**)p, n); }
+static inline void dfree(fkm_ctx*, void*) {}
+
 struct Chunk { void* keys = nullptr; uint32_t* cnt = nullptr; uint64_t n = 0; };
 struct fkm_result {
+    fkm_ctx* ctx = nullptr; uint64_t gen = 0;     // arrays live in ctx's arena until its next job
     int device = 0;
     int32_t B = 0, k = 0; bool wide = false; bool sorted = false;
     std::vector<Chunk> chunks;
@@ -84,6 +136,8 @@ extern "C" void fkm_ctx_destroy(fkm_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     for (auto& ev : c->ev) cudaEventDestroy(ev);
+    cudaStreamSynchronize(c->stream);
+    c->arena.destroy();
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -94,6 +148,16 @@ extern "C" int fkm_ctx_set(fkm_ctx* c, const char* name, double v) {
     else if (!strcmp(name, "sort_budget_keys")) c->sort_budget_keys = v;
     else if (!strcmp(name, "load_factor")) c->load_factor = v;
     else return fkm_set_error(FKM_EINVAL, "unknown knob %s", name);
+    return FKM_OK;
+}
+
+// start of a job on this context: device idle, arena rewound, older results invalidated
+static int job_begin(fkm_ctx* ctx) {
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(ctx->arena.reset());
+    ctx->gen++;
+    ctx->job_launches = 0;
     return FKM_OK;
 }
 
@@ -148,25 +212,37 @@ static int scan_setup(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const void
     P.bases = (const uint64_t*)d_bases; P.inv = (const uint32_t*)d_inv;
     P.n_pos = n_pos; P.n_words = (n_pos + 31) / 32;
     P.k = cfg->k; P.m = cfg->m; P.w = cfg->k - cfg->m + 1;
-    P.nb = std::max(1, (40 + P.w / 2) / P.w);
-    P.wpad = P.w | 1;
-    P.T = (uint32_t)(kScanThreads * P.nb * P.w);
-    P.n_tiles = (n_pos + P.T - 1) / P.T;
+    P.L = 0; while ((2 << P.L) <= P.w) P.L++;
+    P.d = P.w - (1 << P.L);
+    P.seg_len = 4096;
+    P.e_total = (MODE == 2) ? n_pos + (uint64_t)cfg->k - 1 : n_pos;
+    P.n_seg = (P.e_total + P.seg_len - 1) / P.seg_len;
     P.B = (uint32_t)B;
     P.cap = (cfg->k > 32) ? (125 - cfg->k) : (61 - cfg->k);
     P.smem_hist = (MODE == 0 && B <= kSmemHistMaxB) ? 1 : 0;
-    const uint32_t nwords = (P.T + (uint32_t)P.k + 31u) / 32u + 6u;
-    const int nblk = kScanThreads * P.nb + 1;
-    S->smem = (size_t)nwords * 8 + (size_t)(nwords + (nwords & 1u)) * 4 + (size_t)nblk * P.wpad * 8 + (P.smem_hist ? (size_t)B * 8 : 0);
-    if (S->smem > ctx->smem_optin) return fkm_set_error(FKM_EINVAL, "scan tile needs %zu B shared memory > %zu", S->smem, ctx->smem_optin);
+    S->smem = P.smem_hist ? (size_t)B * 8 : 0;
     CK(cudaFuncSetAttribute(k_scan<WIDE, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan<WIDE, MODE>, kScanThreads, S->smem));
     if (occ < 1) occ = 1;
-    S->grid = (int)std::min<uint64_t>(P.n_tiles, (uint64_t)ctx->n_sm * occ);
+    const uint64_t ctas = (P.n_seg + kScanThreads / 32 - 1) / (kScanThreads / 32);
+    S->grid = (int)std::min<uint64_t>(ctas, (uint64_t)ctx->n_sm * occ);
     if (S->grid < 1) S->grid = 1;
     return FKM_OK;
 }
+
+// FKM_TRACE=1: host-side timeline of one job on stderr (where the host blocks between launches)
+struct Trace {
+    bool on; std::chrono::steady_clock::time_point t0, last;
+    Trace() : on(getenv("FKM_TRACE") != nullptr) { t0 = last = std::chrono::steady_clock::now(); }
+    void mark(const char* what, long long a = -1) {
+        if (!on) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[fkm trace] %9.3f ms (+%8.3f) %s %lld\n", std::chrono::duration<double, std::milli>(now - t0).count(),
+                std::chrono::duration<double, std::milli>(now - last).count(), what, a);
+        last = now;
+    }
+};
 
 static inline uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
@@ -178,6 +254,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
     typedef typename Traits<WIDE>::Slot Slot;
     cudaStream_t s = ctx->stream;
     const int rec_bytes = Traits<WIDE>::kRecWords * 8;
+    res->ctx = ctx; res->gen = ctx->gen;
     res->B = B; res->k = cfg->k; res->wide = WIDE; res->sorted = !cfg->use_ht; res->device = ctx->device;
     res->out_base.assign((size_t)B + 1, 0);
 
@@ -189,18 +266,19 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
     int rc = FKM_OK;
     // everything below frees through this lambda
     auto cleanup = [&]() {
-        cudaFree(d_hist_rec); cudaFree(d_hist_kmer); cudaFree(d_bin_base); cudaFree(d_cursor); cudaFree(d_distinct);
-        cudaFree(d_out_base); cudaFree(d_small); cudaFree(d_tbl_base); cudaFree(d_records); cudaFree(d_table); cudaFree(d_ovf);
-        cudaFree(d_keysA); cudaFree(d_keysB); cudaFree(d_tile_seg); cudaFree(d_seg_tile0); cudaFree(d_tile_hist); cudaFree(d_tile_heads); cudaFree(d_first);
+        dfree(ctx, d_hist_rec); dfree(ctx, d_hist_kmer); dfree(ctx, d_bin_base); dfree(ctx, d_cursor); dfree(ctx, d_distinct);
+        dfree(ctx, d_out_base); dfree(ctx, d_small); dfree(ctx, d_tbl_base); dfree(ctx, d_records); dfree(ctx, d_table); dfree(ctx, d_ovf);
+        dfree(ctx, d_keysA); dfree(ctx, d_keysB); dfree(ctx, d_tile_seg); dfree(ctx, d_seg_tile0); dfree(ctx, d_tile_hist); dfree(ctx, d_tile_heads); dfree(ctx, d_first);
     };
 #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); \
     return fkm_set_error(e_ == cudaErrorMemoryAllocation ? FKM_ENOMEM : FKM_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } } while (0)
 #define CKLC() do { g_launches++; ctx->job_launches++; CKC(cudaGetLastError()); } while (0)
 
+    Trace tr;
     const size_t bB = (size_t)B * 8;
-    CKC(cudaMalloc(&d_hist_rec, bB)); CKC(cudaMalloc(&d_hist_kmer, bB)); CKC(cudaMalloc(&d_bin_base, bB + 8));
-    CKC(cudaMalloc(&d_cursor, bB)); CKC(cudaMalloc(&d_distinct, bB)); CKC(cudaMalloc(&d_out_base, bB + 8));
-    CKC(cudaMalloc(&d_small, 64)); CKC(cudaMalloc(&d_ovf, 4)); CKC(cudaMalloc(&d_tbl_base, bB + 8));
+    CKC(dmalloc(ctx, &d_hist_rec, bB)); CKC(dmalloc(ctx, &d_hist_kmer, bB)); CKC(dmalloc(ctx, &d_bin_base, bB + 8));
+    CKC(dmalloc(ctx, &d_cursor, bB)); CKC(dmalloc(ctx, &d_distinct, bB)); CKC(dmalloc(ctx, &d_out_base, bB + 8));
+    CKC(dmalloc(ctx, &d_small, 64)); CKC(dmalloc(ctx, &d_ovf, 4)); CKC(dmalloc(ctx, &d_tbl_base, bB + 8));
     CKC(cudaMemsetAsync(d_hist_rec, 0, bB, s)); CKC(cudaMemsetAsync(d_hist_kmer, 0, bB, s));
     CKC(cudaMemsetAsync(d_cursor, 0, bB, s)); CKC(cudaMemsetAsync(d_distinct, 0, bB, s));
     CKC(cudaMemsetAsync(d_out_base, 0, bB + 8, s)); CKC(cudaMemsetAsync(d_small, 0, 64, s));
@@ -217,6 +295,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
     CKC(cudaMemcpyAsync(h_rec.data(), d_hist_rec, bB, cudaMemcpyDeviceToHost, s));
     CKC(cudaMemcpyAsync(h_kmer.data(), d_hist_kmer, bB, cudaMemcpyDeviceToHost, s));
     CKC(cudaStreamSynchronize(s));
+    tr.mark("histogram done");
     st->d2h_bytes += 2 * bB;
     uint64_t n_rec = 0, n_kmers = 0, nonempty = 0;
     for (int b = 0; b < B; b++) { h_base[(size_t)b] = n_rec; n_rec += h_rec[(size_t)b]; n_kmers += h_kmer[(size_t)b]; nonempty += h_rec[(size_t)b] ? 1 : 0; }
@@ -224,7 +303,8 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
     st->n_kmers = n_kmers; st->n_superkmers = n_rec; st->superkmer_bytes = n_rec * rec_bytes; st->n_nonempty_bins = nonempty;
 
     // ---- stage 2: scatter super-k-mer records, bin-major (the "shuffle")
-    CKC(cudaMalloc(&d_records, std::max<size_t>(16, (size_t)n_rec * rec_bytes)));
+    CKC(dmalloc(ctx, &d_records, std::max<size_t>(16, (size_t)n_rec * rec_bytes)));
+    tr.mark("records allocated", (long long)n_rec);
     CKC(cudaMemcpyAsync(d_bin_base, h_base.data(), bB + 8, cudaMemcpyHostToDevice, s));
     st->h2d_bytes += bB + 8;
     {
@@ -259,10 +339,11 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
                     if (lo == 0 && rho == 1.0 && hi - lo >= std::max(1, B / 64) && slots * sizeof(Slot) > (64ull << 20)) break;   // small first batch to learn rho
                 }
                 if (slots > table_cap) {
-                    cudaFree(d_table); d_table = nullptr;
-                    CKC(cudaMalloc(&d_table, (size_t)slots * sizeof(Slot)));
+                    dfree(ctx, d_table); d_table = nullptr;
+                    CKC(dmalloc(ctx, &d_table, (size_t)slots * sizeof(Slot)));
                     table_cap = slots;
                 }
+                tr.mark("batch planned+table alloc", (long long)slots);
                 CKC(cudaEventRecord(ctx->ev[6], s));
                 CKC(cudaMemsetAsync(d_table, 0xFF, (size_t)slots * sizeof(Slot), s));
                 CKC(cudaMemsetAsync(d_ovf, 0, 4, s));
@@ -280,6 +361,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
                 CKC(cudaMemcpyAsync(&batch_total, d_small, 8, cudaMemcpyDeviceToHost, s));
                 CKC(cudaMemcpyAsync(&ovf, d_ovf, 4, cudaMemcpyDeviceToHost, s));
                 CKC(cudaStreamSynchronize(s));
+                tr.mark("count synced", hi - lo);
                 st->d2h_bytes += 12;
                 { float ms; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); ms_count += ms; }
                 if (ovf) {
@@ -293,10 +375,11 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
                 if (nk > 100000) rho = std::min(1.0, (double)batch_total / (double)nk * 1.25 + 0.02);
                 Chunk ch; ch.n = batch_total;
                 if (batch_total) {
-                    CKC(cudaMalloc(&ch.keys, (size_t)batch_total * sizeof(Key)));
-                    cudaError_t e2 = cudaMalloc(&ch.cnt, (size_t)batch_total * 4);
-                    if (e2 != cudaSuccess) { cudaFree(ch.keys); CKC(e2); }
+                    CKC(dmalloc(ctx, &ch.keys, (size_t)batch_total * sizeof(Key)));
+                    cudaError_t e2 = dmalloc(ctx, &ch.cnt, (size_t)batch_total * 4);
+                    if (e2 != cudaSuccess) { dfree(ctx, ch.keys); CKC(e2); }
                     res->chunks.push_back(ch);
+                    tr.mark("chunk allocated", (long long)batch_total);
                     CompactParams Q;
                     Q.table = d_table; Q.n_slots = slots; Q.tbl_base = d_tbl_base; Q.n_bins = hi - lo; Q.bin_lo = lo;
                     Q.out_base = d_out_base; Q.out_cursor = d_cursor; Q.out_origin = out_total;
@@ -307,6 +390,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
                     CKC(cudaEventRecord(ctx->ev[7], s));
                     CKC(cudaStreamSynchronize(s));
                     { float ms; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); ms_compact += ms; }
+                    tr.mark("compact synced");
                 }
                 out_total += batch_total;
                 st->n_batches++;
@@ -340,17 +424,17 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
                 continue;
             }
             if (nk > key_cap) {
-                cudaFree(d_keysA); cudaFree(d_keysB); d_keysA = d_keysB = nullptr;
-                CKC(cudaMalloc(&d_keysA, (size_t)nk * sizeof(Key))); CKC(cudaMalloc(&d_keysB, (size_t)nk * sizeof(Key)));
+                dfree(ctx, d_keysA); dfree(ctx, d_keysB); d_keysA = d_keysB = nullptr;
+                CKC(dmalloc(ctx, &d_keysA, (size_t)nk * sizeof(Key))); CKC(dmalloc(ctx, &d_keysB, (size_t)nk * sizeof(Key)));
                 key_cap = nk;
             }
             if (n_tiles > tile_cap) {
-                cudaFree(d_tile_seg); cudaFree(d_tile_hist); cudaFree(d_tile_heads); d_tile_seg = d_tile_hist = d_tile_heads = nullptr;
-                CKC(cudaMalloc(&d_tile_seg, (size_t)n_tiles * 4)); CKC(cudaMalloc(&d_tile_hist, (size_t)n_tiles * 256 * 4));
-                CKC(cudaMalloc(&d_tile_heads, (size_t)(n_tiles + 1) * 4));
+                dfree(ctx, d_tile_seg); dfree(ctx, d_tile_hist); dfree(ctx, d_tile_heads); d_tile_seg = d_tile_hist = d_tile_heads = nullptr;
+                CKC(dmalloc(ctx, &d_tile_seg, (size_t)n_tiles * 4)); CKC(dmalloc(ctx, &d_tile_hist, (size_t)n_tiles * 256 * 4));
+                CKC(dmalloc(ctx, &d_tile_heads, (size_t)(n_tiles + 1) * 4));
                 tile_cap = n_tiles;
             }
-            if (!d_seg_tile0) CKC(cudaMalloc(&d_seg_tile0, ((size_t)B + 1) * 4));
+            if (!d_seg_tile0) CKC(dmalloc(ctx, &d_seg_tile0, ((size_t)B + 1) * 4));
             CKC(cudaMemcpyAsync(d_tbl_base, kb.data(), kb.size() * 8, cudaMemcpyHostToDevice, s));
             CKC(cudaMemcpyAsync(d_tile_seg, tseg.data(), (size_t)n_tiles * 4, cudaMemcpyHostToDevice, s));
             CKC(cudaMemcpyAsync(d_seg_tile0, st0.data(), st0.size() * 4, cudaMemcpyHostToDevice, s));
@@ -386,13 +470,13 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
             CKC(cudaStreamSynchronize(s));
             st->d2h_bytes += 8;
             Chunk ch; ch.n = batch_total;
-            CKC(cudaMalloc(&ch.keys, (size_t)batch_total * sizeof(Key)));
-            cudaError_t e2 = cudaMalloc(&ch.cnt, (size_t)batch_total * 4);
-            if (e2 != cudaSuccess) { cudaFree(ch.keys); CKC(e2); }
+            CKC(dmalloc(ctx, &ch.keys, (size_t)batch_total * sizeof(Key)));
+            cudaError_t e2 = dmalloc(ctx, &ch.cnt, (size_t)batch_total * 4);
+            if (e2 != cudaSuccess) { dfree(ctx, ch.keys); CKC(e2); }
             res->chunks.push_back(ch);
             if (batch_total + 1 > first_cap) {
-                cudaFree(d_first); d_first = nullptr;
-                CKC(cudaMalloc(&d_first, (size_t)(batch_total + 1) * 8));
+                dfree(ctx, d_first); d_first = nullptr;
+                CKC(dmalloc(ctx, &d_first, (size_t)(batch_total + 1) * 8));
                 first_cap = batch_total + 1;
             }
             R.out_keys = ch.keys; R.out_cnt = ch.cnt; R.first_idx = d_first;
@@ -427,6 +511,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
     CKC(cudaEventRecord(ctx->ev[4], s));
     CKC(cudaStreamSynchronize(s));
     st->d2h_bytes += bB + 8 + 24;
+    tr.mark("digest synced");
     res->total = out_total;
     // empty trailing bins keep the running offset
     for (int b = 0; b < B; b++) if (res->out_base[(size_t)b + 1] < res->out_base[(size_t)b]) res->out_base[(size_t)b + 1] = res->out_base[(size_t)b];
@@ -456,12 +541,11 @@ static int count_device(fkm_ctx* ctx, const fkm_config* cfg, const void* d_bases
     memset(st, 0, sizeof *st);
     st->h2d_bytes = keep_h2d; st->n_bases = keep_bases; st->ms_stage[0] = keep_ms0;
     st->n_positions = n_pos;
-    ctx->job_launches = 0;
     auto t0 = std::chrono::steady_clock::now();
     fkm_result* res = new fkm_result();
     rc = (cfg->k > 32) ? run_pipeline<true>(ctx, cfg, B, d_bases, d_inv, n_pos, res, st)
                        : run_pipeline<false>(ctx, cfg, B, d_bases, d_inv, n_pos, res, st);
-    st->gpu_launches = ctx->job_launches;
+    st->gpu_launches = ctx->job_launches;       // everything since job_begin (ingest included)
     st->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (rc) { fkm_result_free(res); return rc; }
     if (out) *out = res; else fkm_result_free(res);
@@ -470,84 +554,78 @@ static int count_device(fkm_ctx* ctx, const fkm_config* cfg, const void* d_bases
 
 extern "C" int fkm_count_packed_device(fkm_ctx* ctx, const fkm_config* cfg, const void* d_bases, const void* d_inv,
                                        uint64_t n_pos, fkm_result** out, fkm_stats* stats) {
+    if (!ctx) return fkm_set_error(FKM_EINVAL, "ctx is NULL");
     if (stats) { stats->h2d_bytes = 0; stats->n_bases = 0; stats->ms_stage[0] = 0; }
+    int rc = job_begin(ctx); if (rc) return rc;
     return count_device(ctx, cfg, d_bases, d_inv, n_pos, out, stats);
 }
 
 extern "C" int fkm_count_packed_host(fkm_ctx* ctx, const fkm_config* cfg, const uint64_t* bases, const uint32_t* inv,
                                      uint64_t n_pos, fkm_result** out, fkm_stats* stats) {
     if (!ctx) return fkm_set_error(FKM_EINVAL, "ctx is NULL");
-    CK(cudaSetDevice(ctx->device));
+    { int rc0 = job_begin(ctx); if (rc0) return rc0; }
     const uint64_t nw = (n_pos + 31) / 32;
     void *d_b = nullptr, *d_i = nullptr;
-    CK(cudaMalloc(&d_b, std::max<size_t>(8, nw * 8)));
-    cudaError_t e = cudaMalloc(&d_i, std::max<size_t>(4, nw * 4));
-    if (e != cudaSuccess) { cudaFree(d_b); CK(e); }
+    CK(dmalloc(ctx, &d_b, std::max<size_t>(8, nw * 8)));
+    cudaError_t e = dmalloc(ctx, &d_i, std::max<size_t>(4, nw * 4));
+    if (e != cudaSuccess) { dfree(ctx, d_b); CK(e); }
     auto t0 = std::chrono::steady_clock::now();
     cudaMemcpyAsync(d_b, bases, nw * 8, cudaMemcpyHostToDevice, ctx->stream);
     cudaMemcpyAsync(d_i, inv, nw * 4, cudaMemcpyHostToDevice, ctx->stream);
     e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) { cudaFree(d_b); cudaFree(d_i); CK(e); }
+    if (e != cudaSuccess) { dfree(ctx, d_b); dfree(ctx, d_i); CK(e); }
     fkm_stats local; fkm_stats* st = stats ? stats : &local;
     st->h2d_bytes = nw * 12; st->n_bases = 0;
     st->ms_stage[0] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     int rc = count_device(ctx, cfg, d_b, d_i, n_pos, out, st);
-    cudaFree(d_b); cudaFree(d_i);
+    dfree(ctx, d_b); dfree(ctx, d_i);
     return rc;
 }
 
-// FASTA text already in device memory -> packed layout in device memory (fkm_ingest.cuh)
-static int ingest_device(fkm_ctx* ctx, const uint8_t* d_text, uint64_t n, void** d_bases, void** d_inv, uint64_t* n_pos, uint64_t* n_bases) {
+// FASTA text already in device memory -> packed layout in device memory (fkm_ingest.cuh).
+// d_bases / d_inv are preallocated with ingest_cap_words(n) words.
+static inline uint64_t ingest_cap_words(uint64_t n_bytes) { return (n_bytes + 1 + 31) / 32 + 1; }   // every text byte keeps at most one position
+static int ingest_device(fkm_ctx* ctx, const uint8_t* d_text, uint64_t n, void* d_bases, void* d_inv, uint64_t* n_pos, uint64_t* n_bases) {
     cudaStream_t s = ctx->stream;
     IngestParams P; memset(&P, 0, sizeof P);
     P.text = d_text; P.n = n; P.n_tiles = (n + kIngTile - 1) / kIngTile;
-    const uint64_t cap_words = (n + 1 + 31) / 32 + 1;                 // every text byte keeps at most one position
+    const uint64_t cap_words = ingest_cap_words(n);
     unsigned long long* d_small = nullptr;
-    *d_bases = nullptr; *d_inv = nullptr;
-    auto fail = [&](cudaError_t e, const char* what) {
-        cudaFree(P.tile_nl); cudaFree(P.tile_pos); cudaFree(d_small); cudaFree(*d_bases); cudaFree(*d_inv); *d_bases = *d_inv = nullptr;
-        return fkm_set_error(e == cudaErrorMemoryAllocation ? FKM_ENOMEM : FKM_ECUDA, "ingest %s: %s", what, cudaGetErrorString(e));
-    };
-    cudaError_t e;
-#define CKI(call) do { e = (call); if (e != cudaSuccess) return fail(e, #call); } while (0)
-    CKI(cudaMalloc((void**)&P.tile_nl, (P.n_tiles + 1) * 8)); CKI(cudaMalloc((void**)&P.tile_pos, (P.n_tiles + 1) * 8));
-    CKI(cudaMalloc((void**)&d_small, 64));
-    CKI(cudaMalloc(d_bases, cap_words * 8)); CKI(cudaMalloc(d_inv, cap_words * 4));
-    P.bases = (unsigned long long*)*d_bases; P.inv = (unsigned int*)*d_inv;
+    CK(dmalloc(ctx, (void**)&P.tile_nl, (P.n_tiles + 1) * 8)); CK(dmalloc(ctx, (void**)&P.tile_pos, (P.n_tiles + 1) * 8));
+    CK(dmalloc(ctx, (void**)&d_small, 64));
+    P.bases = (unsigned long long*)d_bases; P.inv = (unsigned int*)d_inv;
     P.first_hdr = d_small; P.n_hdr = d_small + 1;
     unsigned long long init[4] = {n, 0, 0, 0};
-    CKI(cudaMemcpyAsync(d_small, init, 32, cudaMemcpyHostToDevice, s));
-    CKI(cudaMemsetAsync(*d_bases, 0, cap_words * 8, s)); CKI(cudaMemsetAsync(*d_inv, 0, cap_words * 4, s));
-    CKI(cudaMemsetAsync(P.tile_pos, 0, (P.n_tiles + 1) * 8, s));
+    CK(cudaMemcpyAsync(d_small, init, 32, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(d_bases, 0, cap_words * 8, s)); CK(cudaMemsetAsync(d_inv, 0, cap_words * 4, s));
+    CK(cudaMemsetAsync(P.tile_pos, 0, (P.n_tiles + 1) * 8, s));
     if (P.n_tiles) {
-        k_ing_lines<<<(unsigned)P.n_tiles, kIngThreads, 0, s>>>(P); g_launches++; ctx->job_launches++; CKI(cudaGetLastError());
-        k_scan1<1><<<1, 1024, 0, s>>>(P.tile_nl, P.n_tiles); g_launches++; ctx->job_launches++; CKI(cudaGetLastError());
-        k_ing_emit<0><<<(unsigned)P.n_tiles, kIngThreads, 0, s>>>(P); g_launches++; ctx->job_launches++; CKI(cudaGetLastError());
-        k_scan1<0><<<1, 1024, 0, s>>>((long long*)P.tile_pos, P.n_tiles); g_launches++; ctx->job_launches++; CKI(cudaGetLastError());
-        k_ing_emit<1><<<(unsigned)P.n_tiles, kIngThreads, 0, s>>>(P); g_launches++; ctx->job_launches++; CKI(cudaGetLastError());
+        k_ing_lines<<<(unsigned)P.n_tiles, kIngThreads, 0, s>>>(P); CKL();
+        k_scan1<1><<<1, 1024, 0, s>>>(P.tile_nl, P.n_tiles); CKL();
+        k_ing_emit<0><<<(unsigned)P.n_tiles, kIngThreads, 0, s>>>(P); CKL();
+        k_scan1<0><<<1, 1024, 0, s>>>((long long*)P.tile_pos, P.n_tiles); CKL();
+        k_ing_emit<1><<<(unsigned)P.n_tiles, kIngThreads, 0, s>>>(P); CKL();
     }
-    k_ing_finish<<<1, 32, 0, s>>>(P, d_small + 2, d_small + 3); g_launches++; ctx->job_launches++; CKI(cudaGetLastError());
+    k_ing_finish<<<1, 32, 0, s>>>(P, d_small + 2, d_small + 3); CKL();
     unsigned long long out[2] = {0, 0};
-    CKI(cudaMemcpyAsync(out, d_small + 2, 16, cudaMemcpyDeviceToHost, s));
-    CKI(cudaStreamSynchronize(s));
-#undef CKI
-    cudaFree(P.tile_nl); cudaFree(P.tile_pos); cudaFree(d_small);
+    CK(cudaMemcpyAsync(out, d_small + 2, 16, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
     *n_pos = out[0]; *n_bases = out[1];
     return FKM_OK;
 }
 
-// H2D of the raw text + device ingest.  Leaves the packed arrays on the device.
+// H2D of the raw text + device ingest.  The packed arrays stay in the job's arena; the
+// text and the ingest temporaries are released again before counting starts.
 static int upload_and_ingest(fkm_ctx* ctx, const uint8_t* fasta, uint64_t n_bytes, void** d_bases, void** d_inv,
-                             uint64_t* n_pos, uint64_t* n_bases, uint64_t* launches) {
-    CK(cudaSetDevice(ctx->device));
-    ctx->job_launches = 0;
+                             uint64_t* n_pos, uint64_t* n_bases) {
+    const uint64_t cap_words = ingest_cap_words(n_bytes);
+    CK(dmalloc(ctx, d_bases, cap_words * 8)); CK(dmalloc(ctx, d_inv, cap_words * 4));
+    const Arena::Mark mk = ctx->arena.mark();
     uint8_t* d_text = nullptr;
-    CK(cudaMalloc((void**)&d_text, std::max<uint64_t>(n_bytes, 16)));
-    cudaError_t e = cudaMemcpyAsync(d_text, fasta, n_bytes, cudaMemcpyHostToDevice, ctx->stream);
-    if (e != cudaSuccess) { cudaFree(d_text); CK(e); }
-    int rc = ingest_device(ctx, d_text, n_bytes, d_bases, d_inv, n_pos, n_bases);
-    cudaFree(d_text);
-    if (launches) *launches = ctx->job_launches;
+    CK(dmalloc(ctx, (void**)&d_text, std::max<uint64_t>(n_bytes, 16)));
+    CK(cudaMemcpyAsync(d_text, fasta, n_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = ingest_device(ctx, d_text, n_bytes, *d_bases, *d_inv, n_pos, n_bases);
+    ctx->arena.release(mk);
     return rc;
 }
 
@@ -555,15 +633,15 @@ extern "C" int fkm_count_fasta(fkm_ctx* ctx, const fkm_config* cfg, const uint8_
                                fkm_result** out, fkm_stats* stats) {
     if (!ctx) return fkm_set_error(FKM_EINVAL, "ctx is NULL");
     int32_t B = 0; int rc = validate(cfg, &B); if (rc) return rc;
+    rc = job_begin(ctx); if (rc) return rc;
     auto t0 = std::chrono::steady_clock::now();
-    void *d_b = nullptr, *d_i = nullptr; uint64_t n_pos = 0, n_bases = 0, launches = 0;
-    rc = upload_and_ingest(ctx, fasta, n_bytes, &d_b, &d_i, &n_pos, &n_bases, &launches); if (rc) return rc;
+    void *d_b = nullptr, *d_i = nullptr; uint64_t n_pos = 0, n_bases = 0;
+    rc = upload_and_ingest(ctx, fasta, n_bytes, &d_b, &d_i, &n_pos, &n_bases); if (rc) return rc;
     fkm_stats local; fkm_stats* st = stats ? stats : &local;
     const double ms_in = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     st->h2d_bytes = n_bytes + 32; st->n_bases = n_bases; st->ms_stage[0] = ms_in;
     rc = count_device(ctx, cfg, d_b, d_i, n_pos, out, st);
-    st->d2h_bytes += 16; st->gpu_launches += launches; st->ms_total += ms_in;
-    cudaFree(d_b); cudaFree(d_i);
+    st->d2h_bytes += 16; st->ms_total += ms_in;
     return rc;
 }
 
@@ -571,21 +649,18 @@ extern "C" int fkm_count_fasta(fkm_ctx* ctx, const fkm_config* cfg, const uint8_
 extern "C" int fkm_debug_pack_fasta_device(fkm_ctx* ctx, const uint8_t* fasta, uint64_t n_bytes, uint64_t* bases, uint32_t* invalid,
                                            uint64_t cap_positions, uint64_t* n_positions, uint64_t* n_bases) {
     if (!ctx) return fkm_set_error(FKM_EINVAL, "ctx is NULL");
+    int rc = job_begin(ctx); if (rc) return rc;
     void *d_b = nullptr, *d_i = nullptr; uint64_t n_pos = 0, nb = 0;
-    int rc = upload_and_ingest(ctx, fasta, n_bytes, &d_b, &d_i, &n_pos, &nb, nullptr); if (rc) return rc;
+    rc = upload_and_ingest(ctx, fasta, n_bytes, &d_b, &d_i, &n_pos, &nb); if (rc) return rc;
     if (n_positions) *n_positions = n_pos;
     if (n_bases) *n_bases = nb;
     if (bases && invalid) {
         const uint64_t nw = (n_pos + 31) / 32;
-        if (nw * 32 > cap_positions) rc = fkm_set_error(FKM_EINVAL, "packed buffer too small");
-        else {
-            cudaMemcpy(bases, d_b, nw * 8, cudaMemcpyDeviceToHost);
-            cudaError_t e = cudaMemcpy(invalid, d_i, nw * 4, cudaMemcpyDeviceToHost);
-            if (e != cudaSuccess) rc = fkm_set_error(FKM_ECUDA, "copy back: %s", cudaGetErrorString(e));
-        }
+        if (nw * 32 > cap_positions) return fkm_set_error(FKM_EINVAL, "packed buffer too small");
+        CK(cudaMemcpy(bases, d_b, nw * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(invalid, d_i, nw * 4, cudaMemcpyDeviceToHost));
     }
-    cudaFree(d_b); cudaFree(d_i);
-    return rc;
+    return FKM_OK;
 }
 
 extern "C" int fkm_execute_job(fkm_ctx* ctx, const fkm_config* cfg, fkm_stats* stats) {
@@ -623,6 +698,8 @@ extern "C" int fkm_result_bin_offsets(const fkm_result* r, uint64_t* offsets) {
 }
 extern "C" int fkm_result_copy(const fkm_result* r, int32_t* bin, uint64_t* key_hi, uint64_t* key_lo, uint32_t* count) {
     if (!r) return fkm_set_error(FKM_EINVAL, "null result");
+    if (r->total && r->gen != r->ctx->gen)
+        return fkm_set_error(FKM_EINVAL, "result was invalidated by a later job on the same context (copy it out first)");
     CK(cudaSetDevice(r->device));
     uint64_t o = 0;
     std::vector<uint64_t> tmp;
@@ -652,12 +729,7 @@ extern "C" int fkm_result_write(const fkm_result* r, const char* out_dir) {
     int rc = fkm_result_copy(r, nullptr, hi.data(), lo.data(), cnt.data()); if (rc) return rc;
     return fkm_write_bins(out_dir, r->B, r->k, r->sorted, r->out_base.data(), hi.data(), lo.data(), cnt.data());
 }
-extern "C" void fkm_result_free(fkm_result* r) {
-    if (!r) return;
-    cudaSetDevice(r->device);
-    for (Chunk& ch : r->chunks) { cudaFree(ch.keys); cudaFree(ch.cnt); }
-    delete r;
-}
+extern "C" void fkm_result_free(fkm_result* r) { delete r; }   // device arrays belong to the context arena
 
 // ------------------------------------------------------------------ synthetic data, test hooks
 extern "C" int fkm_synth_packed_device(fkm_ctx* ctx, const fkm_synth* sy, void** d_bases, void** d_inv, uint64_t* n_positions) {
@@ -667,6 +739,7 @@ extern "C" int fkm_synth_packed_device(fkm_ctx* ctx, const fkm_synth* sy, void**
     SynthParams P;
     P.S = SynthSpec{sy->seed_genome, sy->seed_reads, sy->seed_errors, sy->genome_len, sy->n_reads, sy->read_len, sy->first_read};
     P.n_pos = sy->n_reads * (sy->read_len + 1); P.n_words = (P.n_pos + 31) / 32;
+    // caller-owned (outlives jobs): plain cudaMalloc, not the job arena
     CK(cudaMalloc((void**)&P.bases, std::max<size_t>(8, P.n_words * 8)));
     cudaError_t e = cudaMalloc((void**)&P.inv, std::max<size_t>(4, P.n_words * 4));
     if (e != cudaSuccess) { cudaFree(P.bases); CK(e); }
@@ -675,22 +748,26 @@ extern "C" int fkm_synth_packed_device(fkm_ctx* ctx, const fkm_synth* sy, void**
     *d_bases = P.bases; *d_inv = P.inv; if (n_positions) *n_positions = P.n_pos;
     return FKM_OK;
 }
-extern "C" int fkm_device_free(fkm_ctx* ctx, void* p) { if (ctx) cudaSetDevice(ctx->device); CK(cudaFree(p)); return FKM_OK; }
+extern "C" int fkm_device_free(fkm_ctx* ctx, void* p) {
+    if (!ctx) return fkm_set_error(FKM_EINVAL, "ctx is NULL");
+    CK(cudaSetDevice(ctx->device)); CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFree(p));
+    return FKM_OK;
+}
 
 extern "C" int fkm_debug_window_bins(fkm_ctx* ctx, const fkm_config* cfg, const uint64_t* bases, const uint32_t* inv,
                                      uint64_t n_pos, int32_t* bins_out) {
     int32_t B = 0; int rc = validate(cfg, &B); if (rc) return rc;
     if (!ctx) return fkm_set_error(FKM_EINVAL, "ctx is NULL");
-    CK(cudaSetDevice(ctx->device));
+    rc = job_begin(ctx); if (rc) return rc;
     const uint64_t nw = (n_pos + 31) / 32;
     void *d_b = nullptr, *d_i = nullptr; int32_t* d_o = nullptr;
-    CK(cudaMalloc(&d_b, std::max<size_t>(8, nw * 8))); CK(cudaMalloc(&d_i, std::max<size_t>(4, nw * 4))); CK(cudaMalloc((void**)&d_o, std::max<size_t>(4, n_pos * 4)));
+    CK(dmalloc(ctx, &d_b, std::max<size_t>(8, nw * 8))); CK(dmalloc(ctx, &d_i, std::max<size_t>(4, nw * 4))); CK(dmalloc(ctx, (void**)&d_o, std::max<size_t>(4, n_pos * 4)));
     CK(cudaMemcpyAsync(d_b, bases, nw * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_i, inv, nw * 4, cudaMemcpyHostToDevice, ctx->stream));
     ScanSetup S; S.grid = 1; S.smem = 0;
     if (cfg->k > 32) { rc = scan_setup<true, 2>(ctx, cfg, B, d_b, d_i, n_pos, &S); if (!rc) { S.P.dbg_bins = d_o; k_scan<true, 2><<<S.grid, kScanThreads, S.smem, ctx->stream>>>(S.P); } }
     else { rc = scan_setup<false, 2>(ctx, cfg, B, d_b, d_i, n_pos, &S); if (!rc) { S.P.dbg_bins = d_o; k_scan<false, 2><<<S.grid, kScanThreads, S.smem, ctx->stream>>>(S.P); } }
     if (!rc) { CKL(); CK(cudaMemcpyAsync(bins_out, d_o, n_pos * 4, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream)); }
-    cudaFree(d_b); cudaFree(d_i); cudaFree(d_o);
+    dfree(ctx, d_b); dfree(ctx, d_i); dfree(ctx, d_o);
     return rc;
 }

@@ -124,7 +124,10 @@ int  fkm_pack_fasta(const uint8_t* fasta, uint64_t n_bytes, uint64_t* bases, uin
 int  fkm_host_alloc(size_t bytes, void** out);
 void fkm_host_free(void* p);
 
-/* ---- results ----------------------------------------------------------------- */
+/* ---- results -----------------------------------------------------------------
+ * The device arrays of a result live in the context's job arena: they stay valid
+ * until the NEXT job on the same context (or fkm_ctx_destroy).  Copy or write a
+ * result before counting again; a stale result fails with FKM_EINVAL.           */
 uint64_t fkm_result_size(const fkm_result* r);                   /* distinct entries            */
 int32_t  fkm_result_num_bins(const fkm_result* r);               /* b                            */
 int32_t  fkm_result_sorted(const fkm_result* r);                 /* 1 if k-mers ascend inside each bin (use_ht=0) */
