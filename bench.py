@@ -144,6 +144,7 @@ def main():
     ap.add_argument("--reads", type=int, default=FULL_READS, help="reads per GPU (default: the full configs[1] size)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--set", action="append", default=[], help="context knob name=value (tuning experiments)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -171,6 +172,9 @@ def main():
     stream = torch.cuda.Stream()                        # a real (non-NULL) stream: kernels and timing events share it
     torch.cuda.set_stream(stream)
     ctx = fk.Context(local_rank, stream.cuda_stream)
+    for kv in args.set:
+        name, val = kv.split("=")
+        ctx.set(name, float(val))
     cfg = fk.TestConfiguration("", "", K, M, X, max_b=B, useHT=True, write=False)
     spec = workload(args.reads, world)
     spec["first_read"] = rank * args.reads

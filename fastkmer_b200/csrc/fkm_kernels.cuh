@@ -106,9 +106,12 @@ struct ScanParams {
     int L, d;                       // w = 2^L + d, 0 <= d < 2^L
     uint32_t B;
     int cap;                        // max k-mers per record
+    int wide;                       // record format (MODE 1 only)
     int smem_hist;                  // 1: per-CTA histogram in shared memory (B <= 4096)
     unsigned long long* hist_rec;   // [B] records per bin            (MODE 0)
     unsigned long long* hist_kmer;  // [B] k-mers per bin             (MODE 0)
+    ulonglong2* events;             // run events {first window end, n | value<<32}   (MODE 0)
+    unsigned long long ev_cap; unsigned long long* ev_count; int* ev_overflow;
     const unsigned long long* bin_base;   // [B+1] record offsets     (MODE 1)
     unsigned long long* cursor;     // [B]                            (MODE 1)
     void* records;                  //                                (MODE 1)
@@ -121,7 +124,33 @@ __device__ __forceinline__ uint32_t revcomp32(uint32_t v, int len) {       // le
     return x >> (32 - 2 * len);
 }
 
-// MODE 0: histogram (records and k-mers per bin).  MODE 1: scatter the records.
+// bases [a, a+n+k-1) -> one super-k-mer record at `slot`
+template <bool WIDE>
+__device__ __forceinline__ void write_record(void* records, unsigned long long slot, const uint64_t* bases, uint64_t n_words,
+                                             unsigned long long a, uint32_t nn) {
+    auto ld = [&](unsigned long long gw) -> uint64_t { return gw < n_words ? bases[gw] : 0ull; };
+    const unsigned long long j = a >> 5; const uint32_t sh = 2u * (uint32_t)(a & 31ull);
+    if constexpr (!WIDE) {
+        uint64_t w0 = ld(j), w1 = ld(j + 1), w2 = ld(j + 2);
+        uint64_t r0 = sh ? ((w0 << sh) | (w1 >> (64 - sh))) : w0;
+        uint64_t r1 = sh ? ((w1 << sh) | (w2 >> (64 - sh))) : w1;
+        r1 = (r1 & ~0xFFull) | (uint64_t)nn;
+        reinterpret_cast<ulonglong2*>(records)[slot] = make_ulonglong2(r0, r1);
+    } else {
+        uint64_t x0 = ld(j), x1 = ld(j + 1), x2 = ld(j + 2), x3 = ld(j + 3), x4 = ld(j + 4);
+        uint64_t r0 = sh ? ((x0 << sh) | (x1 >> (64 - sh))) : x0;
+        uint64_t r1 = sh ? ((x1 << sh) | (x2 >> (64 - sh))) : x1;
+        uint64_t r2 = sh ? ((x2 << sh) | (x3 >> (64 - sh))) : x2;
+        uint64_t r3 = sh ? ((x3 << sh) | (x4 >> (64 - sh))) : x3;
+        r3 = (r3 & ~0xFFull) | (uint64_t)nn;
+        ulonglong2* dst = reinterpret_cast<ulonglong2*>(records) + 2 * slot;
+        dst[0] = make_ulonglong2(r0, r1);
+        dst[1] = make_ulonglong2(r2, r3);
+    }
+}
+
+// MODE 0: bin histogram (records and k-mers per bin) + the list of run events.
+// MODE 1: scatter records directly (recomputes the scan; fallback when the event list overflowed).
 // MODE 2: per-window bin ids (test hook).
 //
 // Warp-striped sliding window.  A warp owns a segment of consecutive window-END
@@ -130,16 +159,18 @@ __device__ __forceinline__ uint32_t revcomp32(uint32_t v, int len) {       // le
 //     its reverse complement comes from brev, norm() is the closed form of UTIL:46-100;
 //   * the minimum over the window's w = 2^L + d m-mers is built by doubling with warp
 //     shuffles: x_{j+1}[e] = min(x_j[e], x_j[e - 2^j]); values that fall before lane 0
-//     come from the previous group's registers (prev[j]);
+//     come from the previous group's registers (prev[j]); L is a template parameter so
+//     the level loop is straight-line code;
 //   * a window is valid iff the last invalid position at or before e is >= k behind;
 //   * run boundaries (signature value changes / validity changes) are found with one
 //     shuffle and two ballots; every lane that sees a run END pushes (start, length,
 //     value) into a per-warp queue in shared memory, and the queue is drained 32 events
-//     at a time so that hashing, atomics and record extraction run with full lanes.
-// Two warm-up groups before each segment rebuild the register state, so segments are
-// independent; runs are cut at segment boundaries (the reference's own cutting rule,
-// SBKC:102-136, is not observable: SURVEY §7).
-template <bool WIDE, int MODE>
+//     at a time so that hashing, atomics and stores run with full lanes.
+// Positions inside a segment are 32-bit offsets from its warm-up start.  Two warm-up
+// groups before each segment rebuild the register state, so segments are independent;
+// runs are cut at segment boundaries (the reference's own cutting rule, SBKC:102-136,
+// is not observable: SURVEY §7).
+template <int MODE, int L>
 __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long q_rs[kScanThreads / 32][64];
@@ -150,8 +181,10 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams P) {
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const int k = P.k, m = P.m, L = P.L, d = P.d;
+    const int k = P.k, m = P.m, d = P.d;
     const uint32_t mmask = (1u << (2 * m)) - 1u;
+    const bool upper = lane >= 16;                          // m-mer lies inside W (else it reaches into Wprev)
+    const uint32_t fsh = (2u * (31u - (uint32_t)lane)) & 31u;
 
     if (MODE == 0 && P.smem_hist) {
         for (uint32_t b = threadIdx.x; b < P.B; b += kScanThreads) { s_hist_rec[b] = 0; s_hist_kmer[b] = 0; }
@@ -166,34 +199,32 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams P) {
         if (p0 + 32 > P.n_pos) iv |= (p0 >= P.n_pos) ? 0xFFFFFFFFu : (0xFFFFFFFFu >> (uint32_t)(P.n_pos - p0));
         return iv;
     };
-    // one event = one run of `n` windows whose first window ENDS at position rs, signature value v
-    auto emit_event = [&](unsigned long long rs, uint32_t n, uint32_t v) {
-        const uint32_t bin = hash_to_bucket(v, P.B);
-        for (uint32_t off = 0; off < n; off += (uint32_t)P.cap) {
-            const uint32_t nn = min((uint32_t)P.cap, n - off);
+    // drain `cnt` (<= 32) queued events: lane i takes event i
+    auto drain = [&](int cnt) {
+        const bool have = lane < cnt;
+        unsigned long long rs = 0; uint32_t n = 0, v = 0;
+        if (have) { rs = q_rs[warp][lane]; n = q_n[warp][lane]; v = q_v[warp][lane]; }
+        if (MODE == 0) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(P.ev_count, (unsigned long long)cnt);
+            base = __shfl_sync(FULL, base, 0);
+            if (base + (unsigned long long)cnt <= P.ev_cap) {
+                if (have) P.events[base + lane] = make_ulonglong2(rs, (unsigned long long)n | ((unsigned long long)v << 32));
+            } else if (lane == 0) *P.ev_overflow = 1;
+        }
+        if (have) {
+            const uint32_t bin = hash_to_bucket(v, P.B);
             if (MODE == 0) {
-                if (P.smem_hist) { atomicAdd(&s_hist_rec[bin], 1u); atomicAdd(&s_hist_kmer[bin], nn); }
-                else { atomicAdd(&P.hist_rec[bin], 1ull); atomicAdd(&P.hist_kmer[bin], (unsigned long long)nn); }
+                const uint32_t pieces = (n + (uint32_t)P.cap - 1) / (uint32_t)P.cap;
+                if (P.smem_hist) { atomicAdd(&s_hist_rec[bin], pieces); atomicAdd(&s_hist_kmer[bin], n); }
+                else { atomicAdd(&P.hist_rec[bin], (unsigned long long)pieces); atomicAdd(&P.hist_kmer[bin], (unsigned long long)n); }
             } else if (MODE == 1) {
-                const unsigned long long slot = P.bin_base[bin] + atomicAdd(&P.cursor[bin], 1ull);
-                const unsigned long long a = rs + off - (unsigned long long)(k - 1);     // first base of the piece
-                const unsigned long long j = a >> 5; const uint32_t sh = 2u * (uint32_t)(a & 31ull);
-                if constexpr (!WIDE) {
-                    uint64_t w0 = load_bases(j), w1 = load_bases(j + 1), w2 = load_bases(j + 2);
-                    uint64_t r0 = sh ? ((w0 << sh) | (w1 >> (64 - sh))) : w0;
-                    uint64_t r1 = sh ? ((w1 << sh) | (w2 >> (64 - sh))) : w1;
-                    r1 = (r1 & ~0xFFull) | (uint64_t)nn;
-                    reinterpret_cast<ulonglong2*>(P.records)[slot] = make_ulonglong2(r0, r1);
-                } else {
-                    uint64_t x0 = load_bases(j), x1 = load_bases(j + 1), x2 = load_bases(j + 2), x3 = load_bases(j + 3), x4 = load_bases(j + 4);
-                    uint64_t r0 = sh ? ((x0 << sh) | (x1 >> (64 - sh))) : x0;
-                    uint64_t r1 = sh ? ((x1 << sh) | (x2 >> (64 - sh))) : x1;
-                    uint64_t r2 = sh ? ((x2 << sh) | (x3 >> (64 - sh))) : x2;
-                    uint64_t r3 = sh ? ((x3 << sh) | (x4 >> (64 - sh))) : x3;
-                    r3 = (r3 & ~0xFFull) | (uint64_t)nn;
-                    ulonglong2* dst = reinterpret_cast<ulonglong2*>(P.records) + 2 * slot;
-                    dst[0] = make_ulonglong2(r0, r1);
-                    dst[1] = make_ulonglong2(r2, r3);
+                for (uint32_t off = 0; off < n; off += (uint32_t)P.cap) {
+                    const uint32_t nn = min((uint32_t)P.cap, n - off);
+                    const unsigned long long slot = P.bin_base[bin] + atomicAdd(&P.cursor[bin], 1ull);
+                    const unsigned long long a = rs + off - (unsigned long long)(k - 1);
+                    if (P.wide) write_record<true>(P.records, slot, P.bases, P.n_words, a, nn);
+                    else write_record<false>(P.records, slot, P.bases, P.n_words, a, nn);
                 }
             }
         }
@@ -206,86 +237,86 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams P) {
         const unsigned long long e1 = min(e0 + (unsigned long long)P.seg_len, (unsigned long long)P.e_total);
         const unsigned long long g0 = e0 >> 5, g1 = (e1 + 31) >> 5;
         const unsigned long long gs = g0 >= 2 ? g0 - 2 : 0;   // two warm-up groups (>= k-1 positions)
-        long long carry_bad = (long long)(gs << 5) - 1;       // last invalid position seen so far
-        uint32_t prev[7];
+        const unsigned long long ws = gs << 5;                // absolute position of relative position 0
+        const int n_groups = (int)(g1 - gs), n_warm = (int)(g0 - gs);
+        int carry_bad = -1;                                   // last invalid relative position seen so far
+        uint32_t prev[L + 1];
 #pragma unroll
-        for (int j = 0; j < 7; j++) prev[j] = kInvalidMin;
+        for (int j = 0; j <= L; j++) prev[j] = kInvalidMin;
         uint32_t prev_last = kInvalidMin;                     // value of the window ending just before this group
-        unsigned long long run_start = 0;                     // END position of the first window of the open run
+        uint32_t run_start = 0;                               // relative END position of the first window of the open run
         uint64_t Wprev = gs > 0 ? load_bases(gs - 1) : 0ull;
 
-        for (unsigned long long gb = gs; gb < g1; gb += 32) {
-            const uint64_t Wb = load_bases(gb + lane);
-            const uint32_t Ib = load_inv(gb + lane);
-            const int ng = (int)min(32ull, g1 - gb);
+        for (int gb = 0; gb < n_groups; gb += 32) {
+            const uint64_t Wb = load_bases(gs + gb + lane);
+            const uint32_t Ib = load_inv(gs + gb + lane);
+            const int ng = min(32, n_groups - gb);
             for (int gi = 0; gi < ng; gi++) {
                 const uint64_t W = __shfl_sync(FULL, Wb, gi);
                 const uint32_t IW = __shfl_sync(FULL, Ib, gi);
-                const unsigned long long g = gb + gi;
-                const unsigned long long e = (g << 5) + lane;
-                const bool real = g >= g0;
+                const int gr = gb + gi;                       // group index inside the segment
+                const uint32_t e = ((uint32_t)gr << 5) + (uint32_t)lane;
+                const bool real = gr >= n_warm;
                 // ---- m-mer ending at e: low 2m bits of (Wprev:W) >> 2*(31-lane)
-                const uint32_t sh = 2u * (31u - (uint32_t)lane);
-                const uint32_t lo = sh < 32 ? (uint32_t)W : (uint32_t)(W >> 32);
-                const uint32_t hi = sh < 32 ? (uint32_t)(W >> 32) : (uint32_t)Wprev;
-                const uint32_t v = __funnelshift_r(lo, hi, sh & 31u) & mmask;
+                const uint32_t lo = upper ? (uint32_t)W : (uint32_t)(W >> 32);
+                const uint32_t hi = upper ? (uint32_t)(W >> 32) : (uint32_t)Wprev;
+                const uint32_t v = __funnelshift_r(lo, hi, fsh) & mmask;
                 uint32_t x = mmer_norm(v, revcomp32(v, m), m, mmask);
-                // ---- minimum over the last w m-mers (doubling)
+                Wprev = W;
+                // ---- minimum over the last w m-mers (doubling, straight-line)
 #pragma unroll
-                for (int j = 0; j < 6; j++) {
-                    if (j < L) {
-                        const int s = 1 << j;
-                        const uint32_t cur = x;
-                        uint32_t partner;
-                        if (s == 32) partner = prev[j];
-                        else {
-                            const uint32_t t = __shfl_up_sync(FULL, cur, s);
-                            const uint32_t u = __shfl_sync(FULL, prev[j], (lane - s) & 31);
-                            partner = lane >= s ? t : u;
-                        }
-                        x = min(cur, partner);
-                        prev[j] = cur;
+                for (int j = 0; j < L; j++) {
+                    const int s = 1 << j;
+                    const uint32_t cur = x;
+                    uint32_t partner;
+                    if (s == 32) partner = prev[j];
+                    else {
+                        const uint32_t t = __shfl_up_sync(FULL, cur, s);
+                        const uint32_t u = __shfl_sync(FULL, prev[j], (lane - s) & 31);
+                        partner = lane >= s ? t : u;
                     }
+                    x = min(cur, partner);
+                    prev[j] = cur;
                 }
-                if (d > 0) {
+                {   // w = 2^L + d: one more step with offset d (d == 0 degenerates to min(x, x))
                     const uint32_t cur = x;
                     const uint32_t t = __shfl_up_sync(FULL, cur, d);
-                    const uint32_t u = __shfl_sync(FULL, prev[6], (lane - d) & 31);
+                    const uint32_t u = __shfl_sync(FULL, prev[L], (lane - d) & 31);
                     x = min(cur, lane >= d ? t : u);
-                    prev[6] = cur;
+                    prev[L] = cur;
                 }
                 // ---- validity: last invalid position <= e must be at least k behind
                 const uint32_t tb = IW >> (31 - lane);
-                const long long last_bad = tb ? (long long)e - (long long)(__ffs((int)tb) - 1) : carry_bad;
-                const bool valid = ((long long)e - last_bad) >= (long long)k;
-                if (IW) carry_bad = (long long)(g << 5) + 31 - (long long)(__ffs((int)IW) - 1);
+                const int last_bad = tb ? (int)e - (__ffs((int)tb) - 1) : carry_bad;
+                const bool valid = ((int)e - last_bad) >= k;
+                carry_bad = IW ? (gr << 5) + 31 - (__ffs((int)IW) - 1) : carry_bad;
                 const uint32_t Ev = valid ? x : kInvalidMin;
-                Wprev = W;
-                if (!real) continue;                                           // warm-up group (warp-uniform)
                 if (MODE == 2) {
-                    if (e + 1 >= (unsigned long long)k) {
-                        const unsigned long long i = e + 1 - (unsigned long long)k;
+                    const unsigned long long ea = ws + e;
+                    if (real && ea + 1 >= (unsigned long long)k) {
+                        const unsigned long long i = ea + 1 - (unsigned long long)k;
                         if (i < P.n_pos) P.dbg_bins[i] = valid ? (int32_t)hash_to_bucket(x, P.B) : -1;
                     }
                     continue;
                 }
-                // ---- run boundaries
+                // ---- run boundaries (shuffles and votes stay outside any branch)
                 uint32_t Ep = __shfl_up_sync(FULL, Ev, 1);
                 if (lane == 0) Ep = prev_last;
-                const bool is_start = (Ev != kInvalidMin) && (Ev != Ep);
-                const bool is_end = (Ep != kInvalidMin) && (Ev != Ep);        // the run ending at e-1
+                const bool is_start = real && (Ev != kInvalidMin) && (Ev != Ep);
+                const bool is_end = real && (Ep != kInvalidMin) && (Ev != Ep);        // the run ending at e-1
                 const uint32_t Sm = __ballot_sync(FULL, is_start), Em = __ballot_sync(FULL, is_end);
+                const uint32_t last = __shfl_sync(FULL, Ev, 31);
                 if (Em) {
                     if (is_end) {
                         const uint32_t below = Sm & lt_mask;
-                        const unsigned long long rs = below ? (g << 5) + (unsigned long long)(31 - __clz((int)below)) : run_start;
+                        const uint32_t rs = below ? ((uint32_t)gr << 5) + (uint32_t)(31 - __clz((int)below)) : run_start;
                         const int idx = qn + __popc(Em & lt_mask);
-                        q_rs[warp][idx] = rs; q_n[warp][idx] = (uint32_t)(e - rs); q_v[warp][idx] = Ep;
+                        q_rs[warp][idx] = ws + rs; q_n[warp][idx] = e - rs; q_v[warp][idx] = Ep;
                     }
                     qn += __popc(Em);
                     __syncwarp();
                     if (qn >= 32) {
-                        emit_event(q_rs[warp][lane], q_n[warp][lane], q_v[warp][lane]);
+                        drain(32);
                         __syncwarp();
                         const bool mv = lane < qn - 32;
                         unsigned long long t0 = 0; uint32_t t1 = 0, t2 = 0;
@@ -296,25 +327,21 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams P) {
                         __syncwarp();
                     }
                 }
-                if (Sm) run_start = (g << 5) + (unsigned long long)(31 - __clz((int)Sm));
-                prev_last = __shfl_sync(FULL, Ev, 31);
+                if (Sm) run_start = ((uint32_t)gr << 5) + (uint32_t)(31 - __clz((int)Sm));
+                if (real) prev_last = last;
             }
         }
         // the run still open at the end of the segment is cut here
         if (MODE != 2 && prev_last != kInvalidMin) {
-            if (lane == 0) { q_rs[warp][qn] = run_start; q_n[warp][qn] = (uint32_t)((g1 << 5) - run_start); q_v[warp][qn] = prev_last; }
+            if (lane == 0) { q_rs[warp][qn] = ws + run_start; q_n[warp][qn] = ((uint32_t)n_groups << 5) - run_start; q_v[warp][qn] = prev_last; }
             qn += 1;
             __syncwarp();
-            if (qn >= 32) {                 // qn == 32 exactly
-                emit_event(q_rs[warp][lane], q_n[warp][lane], q_v[warp][lane]);
-                qn = 0;
-                __syncwarp();
-            }
+            if (qn >= 32) { drain(32); qn = 0; __syncwarp(); }     // qn == 32 exactly
         }
     }
     if (MODE != 2) {
         __syncwarp();
-        if (lane < qn) emit_event(q_rs[warp][lane], q_n[warp][lane], q_v[warp][lane]);
+        if (qn > 0) drain(qn);
     }
 
     if (MODE == 0 && P.smem_hist) {
@@ -323,6 +350,29 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams P) {
             uint32_t r = s_hist_rec[b];
             if (r) { atomicAdd(&P.hist_rec[b], (unsigned long long)r); atomicAdd(&P.hist_kmer[b], (unsigned long long)s_hist_kmer[b]); }
         }
+    }
+}
+
+// K4: run events -> super-k-mer records, bin-major (the "shuffle").  One thread per event.
+struct ScatterParams {
+    const ulonglong2* events; unsigned long long n_events;
+    const uint64_t* bases; uint64_t n_words;
+    uint32_t B; int cap; int k;
+    const unsigned long long* bin_base; unsigned long long* cursor; void* records;
+};
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_scatter_events(const ScatterParams P) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_events) return;
+    const ulonglong2 ev = __ldcs(P.events + i);
+    const unsigned long long rs = ev.x;
+    const uint32_t n = (uint32_t)ev.y, v = (uint32_t)(ev.y >> 32);
+    const uint32_t bin = hash_to_bucket(v, P.B);
+    const uint32_t pieces = (n + (uint32_t)P.cap - 1) / (uint32_t)P.cap;
+    const unsigned long long slot0 = P.bin_base[bin] + atomicAdd(&P.cursor[bin], (unsigned long long)pieces);
+    for (uint32_t pc = 0, off = 0; off < n; off += (uint32_t)P.cap, pc++) {
+        const uint32_t nn = min((uint32_t)P.cap, n - off);
+        write_record<WIDE>(P.records, slot0 + pc, P.bases, P.n_words, rs + off - (unsigned long long)(P.k - 1), nn);
     }
 }
 
@@ -396,9 +446,26 @@ struct CountParams {
     int k; int max_probe;
 };
 
+// 32-bit table hash (murmur3 finaliser over the folded key); the slot is mulhi(hash, size)
+__device__ __forceinline__ uint32_t fmix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint32_t key_hash(uint64_t key) {
+    return fmix32((uint32_t)key * 0x9E3779B1u ^ (uint32_t)(key >> 32) * 0x85EBCA77u);
+}
+__device__ __forceinline__ uint32_t key_hash(key128 key) {
+    return fmix32(((uint32_t)key.lo * 0x9E3779B1u ^ (uint32_t)(key.lo >> 32) * 0x85EBCA77u) +
+                  ((uint32_t)key.hi * 0xC2B2AE3Du ^ (uint32_t)(key.hi >> 32) * 0x27D4EB2Fu));
+}
+__device__ __forceinline__ unsigned long long slot_of(uint32_t h, unsigned long long size) {
+    return (size <= 0xFFFFFFFFull) ? (unsigned long long)__umulhi(h, (uint32_t)size)
+                                   : __umul64hi(((unsigned long long)h << 32) | fmix32(h), size);
+}
+
 // returns 1 if this call claimed a new slot, 0 if the key was present, -1 on overflow
 __device__ __forceinline__ int ht_insert(SlotN* tbl, unsigned long long size, uint64_t key, int max_probe) {
-    unsigned long long slot = __umul64hi(mix64(key), size);
+    unsigned long long slot = slot_of(key_hash(key), size);
     for (int probe = 0; probe < max_probe; probe++) {
         SlotN* s = tbl + slot;
         uint64_t cur = __ldcg(&s->key);
@@ -413,7 +480,7 @@ __device__ __forceinline__ int ht_insert(SlotN* tbl, unsigned long long size, ui
     return -1;
 }
 __device__ __forceinline__ int ht_insert(SlotW* tbl, unsigned long long size, key128 key, int max_probe) {
-    unsigned long long slot = __umul64hi(mix64(key.lo ^ mix64(key.hi)), size);
+    unsigned long long slot = slot_of(key_hash(key), size);
     const key128 empty = {~0ull, ~0ull};
     for (int probe = 0; probe < max_probe; probe++) {
         SlotW* s = tbl + slot;
@@ -431,107 +498,197 @@ __device__ __forceinline__ int ht_insert(SlotW* tbl, unsigned long long size, ke
     return -1;
 }
 
-// One thread per super-k-mer record: roll the forward / reverse-complement
-// k-mer, take the canonical one, insert into the bin's table (counts start at
-// 0xFFFFFFFF because the table is cleared with an all-ones memset: real = cnt+1).
+// canonical k-mer number j of a record whose words sit in shared memory (n byte already cleared)
+__device__ __forceinline__ uint64_t kmer_at_narrow(const uint64_t* rec, int j, int k) {
+    const int q = j >> 5, sh = 2 * (j & 31);
+    const uint64_t a0 = rec[q], a1 = q ? 0ull : rec[1];
+    const uint64_t hi = sh ? ((a0 << sh) | (a1 >> (64 - sh))) : a0;
+    const uint64_t fwd = hi >> (64 - 2 * k);
+    const uint64_t rc = revcomp64(fwd, k);
+    return min(fwd, rc);
+}
+__device__ __forceinline__ key128 kmer_at_wide(const uint64_t* rec, int j, int k) {
+    const int q = j >> 5, sh = 2 * (j & 31);
+    const uint64_t a0 = rec[q], a1 = (q + 1 < 4) ? rec[q + 1] : 0ull, a2 = (q + 2 < 4) ? rec[q + 2] : 0ull;
+    const uint64_t h0 = sh ? ((a0 << sh) | (a1 >> (64 - sh))) : a0;
+    const uint64_t h1 = sh ? ((a1 << sh) | (a2 >> (64 - sh))) : a1;
+    const int s = 128 - 2 * k;
+    key128 fwd;
+    fwd.hi = h0 >> s; fwd.lo = s ? ((h0 << (64 - s)) | (h1 >> s)) : h1;
+    const key128 rc = revcomp128(fwd, k);
+    return key_less(rc, fwd) ? rc : fwd;
+}
+
+// One warp per 32 super-k-mer records.  The records go to shared memory, an exclusive
+// prefix sum of their k-mer counts maps k-mer slot t to (record, offset): with M the
+// bitmask of record starts inside the current block of 32 slots (one redux.or),
+// record(t) = #starts before the block + popc(M & lanes<=t) - 1.  Every lane then cuts
+// its own k-mer out of the record, canonicalises it and inserts it — no lane idles
+// because its record is shorter than its neighbour's.  Table counts start at
+// 0xFFFFFFFF (the table is cleared with an all-ones memset): real = cnt + 1.
 template <bool WIDE>
 __global__ void __launch_bounds__(256) k_count_ht(const CountParams P) {
     typedef typename Traits<WIDE>::Slot Slot;
-    const unsigned long long r = P.rec_lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int bin = -1; unsigned int claims = 0; bool ovf = false;
-    if (r < P.rec_hi) {
+    constexpr int RW = Traits<WIDE>::kRecWords;
+    __shared__ uint64_t s_rec[8][32 * RW];
+    __shared__ uint32_t s_off[8][32];
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long r = P.rec_lo + ((unsigned long long)blockIdx.x * 8 + warp) * 32 + lane;
+    const bool in = r < P.rec_hi;
+    uint64_t w[RW];
+    uint32_t n = 0; int bin = -1;
+    if (in) {
+        const ulonglong2* src = reinterpret_cast<const ulonglong2*>(P.records) + (RW / 2) * r;
+#pragma unroll
+        for (int i = 0; i < RW / 2; i++) { ulonglong2 v = __ldcs(src + i); w[2 * i] = v.x; w[2 * i + 1] = v.y; }   // read once: keep L2 for the tables
+        n = (uint32_t)(w[RW - 1] & 0xFFull);
+        w[RW - 1] &= ~0xFFull;
         bin = find_bin(P.bin_base, P.bin_lo, P.bin_hi, r);
-        const unsigned long long tb = P.tbl_base[bin - P.bin_lo];
-        const unsigned long long size = P.tbl_base[bin - P.bin_lo + 1] - tb;
-        Slot* tbl = reinterpret_cast<Slot*>(P.table) + tb;
-        if constexpr (!WIDE) {
-            ulonglong2 rec = reinterpret_cast<const ulonglong2*>(P.records)[r];
-            for_each_kmer_narrow(rec.x, rec.y, P.k, [&](uint64_t key) {
-                int c = ht_insert(reinterpret_cast<SlotN*>(tbl), size, key, P.max_probe);
+#pragma unroll
+        for (int i = 0; i < RW; i++) s_rec[warp][lane * RW + i] = w[i];
+    }
+    uint32_t incl = n;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) { uint32_t t = __shfl_up_sync(FULL, incl, dd); if (lane >= dd) incl += t; }
+    const uint32_t excl = incl - n;
+    const uint32_t T = __shfl_sync(FULL, incl, 31);
+    if (T == 0) return;
+    s_off[warp][lane] = excl;
+    __syncwarp();
+    const int bin0 = __shfl_sync(FULL, bin, 0);
+    const bool uniform = __all_sync(FULL, bin == bin0 || bin < 0);
+    unsigned int claims = 0; bool ovf = false;
+    if (uniform) {
+        const unsigned long long tb0 = P.tbl_base[bin0 - P.bin_lo];
+        const unsigned long long size = P.tbl_base[bin0 - P.bin_lo + 1] - tb0;
+        Slot* tbl = reinterpret_cast<Slot*>(P.table) + tb0;
+        const uint32_t le_mask = (2u << lane) - 1u;
+        uint32_t cb = 0;
+        for (uint32_t tb = 0; tb < T; tb += 32) {
+            const uint32_t p = excl - tb;
+            const uint32_t M = __reduce_or_sync(FULL, (n > 0 && p < 32u) ? (1u << p) : 0u);
+            const uint32_t t = tb + lane;
+            if (t < T) {
+                const int ri = (int)(cb + __popc(M & le_mask)) - 1;
+                const int j = (int)(t - s_off[warp][ri]);
+                int c;
+                if constexpr (!WIDE) c = ht_insert(reinterpret_cast<SlotN*>(tbl), size, kmer_at_narrow(&s_rec[warp][ri * RW], j, P.k), P.max_probe);
+                else c = ht_insert(reinterpret_cast<SlotW*>(tbl), size, kmer_at_wide(&s_rec[warp][ri * RW], j, P.k), P.max_probe);
                 if (c < 0) ovf = true; else claims += (unsigned)c;
-            });
-        } else {
-            const ulonglong2* src = reinterpret_cast<const ulonglong2*>(P.records) + 2 * r;
-            ulonglong2 a = src[0], b = src[1];
-            for_each_kmer_wide(a.x, a.y, b.x, b.y, P.k, [&](key128 key) {
-                int c = ht_insert(reinterpret_cast<SlotW*>(tbl), size, key, P.max_probe);
-                if (c < 0) ovf = true; else claims += (unsigned)c;
-            });
+            }
+            cb += __popc(M);
         }
+        const unsigned int tot = __reduce_add_sync(FULL, claims);
+        if (lane == 0 && tot) atomicAdd(&P.bin_distinct[bin0], (unsigned long long)tot);
+    } else if (in) {
+        // the 32 records straddle a bin boundary (rare): one lane per record
+        const unsigned long long tb0 = P.tbl_base[bin - P.bin_lo];
+        const unsigned long long size = P.tbl_base[bin - P.bin_lo + 1] - tb0;
+        Slot* tbl = reinterpret_cast<Slot*>(P.table) + tb0;
+        for (int j = 0; j < (int)n; j++) {
+            int c;
+            if constexpr (!WIDE) c = ht_insert(reinterpret_cast<SlotN*>(tbl), size, kmer_at_narrow(&s_rec[warp][lane * RW], j, P.k), P.max_probe);
+            else c = ht_insert(reinterpret_cast<SlotW*>(tbl), size, kmer_at_wide(&s_rec[warp][lane * RW], j, P.k), P.max_probe);
+            if (c < 0) ovf = true; else claims += (unsigned)c;
+        }
+        if (claims) atomicAdd(&P.bin_distinct[bin], (unsigned long long)claims);
     }
     if (ovf) *P.overflow = 1;
-    // warp-aggregated claim counts (records are bin-major, so a warp is almost always one bin)
-    int uniform;
-    __match_all_sync(0xFFFFFFFFu, bin, &uniform);
-    if (uniform) {
-        unsigned int tot = __reduce_add_sync(0xFFFFFFFFu, claims);
-        if ((threadIdx.x & 31) == 0 && bin >= 0 && tot) atomicAdd(&P.bin_distinct[bin], (unsigned long long)tot);
-    } else if (bin >= 0 && claims) {
-        atomicAdd(&P.bin_distinct[bin], (unsigned long long)claims);
-    }
 }
 
 struct CompactParams {
-    const void* table; unsigned long long n_slots;        // batch table space; every 1024-slot tile lies in one bin
+    void* table; unsigned long long n_slots;               // batch table space; every 1024-slot tile lies in one bin
     const unsigned long long* tbl_base; int n_bins; int bin_lo;
     const unsigned long long* out_base;                    // [B+1] global output offsets (entries)
-    unsigned long long out_origin;                         // global offset of the first entry of this batch's arrays
+    unsigned long long out_origin;                         // global offset of the first entry of the output arrays
+    unsigned long long out_cap;                            // entries the output arrays can hold
     unsigned long long* out_cursor;                        // [B]
-    void* out_keys; uint32_t* out_cnt;                     // global output arrays
+    void* out_keys; uint32_t* out_cnt;
+    int clear;                                             // 1: write EMPTY back into every occupied slot (table reusable without a memset)
+    int* cap_overflow;                                     // set when the output arrays are too small
+    unsigned long long* acc;                               // [3][64] digest accumulators (sum, xor, count), or NULL
 };
-// table -> dense output.  Order inside a bin is slot order up to tile permutation
-// (the reference's HT order is fastutil's iteration order: unspecified, SBKC:723).
+// table -> dense output, persistent grid-stride over 1024-slot tiles.  Order inside a bin
+// is slot order up to tile permutation (the reference's HT order is fastutil's iteration
+// order: unspecified, SBKC:723).  Also folds the entries into the result digest.
 template <bool WIDE>
 __global__ void __launch_bounds__(256) k_compact_ht(const CompactParams P) {
     typedef typename Traits<WIDE>::Slot Slot;
     typedef typename Traits<WIDE>::Key Key;
     __shared__ unsigned int s_warp[8];
     __shared__ unsigned long long s_base;
-    const unsigned long long tile0 = (unsigned long long)blockIdx.x * 1024ull;
+    __shared__ int s_bin;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const Slot* tbl = reinterpret_cast<const Slot*>(P.table);
-    Key keys[4]; uint32_t cnts[4]; unsigned int have = 0;
+    Slot* tbl = reinterpret_cast<Slot*>(P.table);
+    const unsigned long long n_tiles = (P.n_slots + 1023) / 1024;
+    unsigned long long dsum = 0, dxor = 0, dcnt = 0;
+    for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const unsigned long long tile0 = tile * 1024ull;
+        Key keys[4]; uint32_t cnts[4]; unsigned int have = 0;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        unsigned long long s = tile0 + (unsigned long long)j * 256ull + threadIdx.x;
-        cnts[j] = 0xFFFFFFFFu;
-        if (s < P.n_slots) {
-            if constexpr (!WIDE) {
-                ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&tbl[s]);
-                *reinterpret_cast<uint64_t*>(&keys[j]) = v.x; cnts[j] = (uint32_t)v.y;
-                if (v.x != ~0ull) have |= 1u << j;
-            } else {
-                const ulonglong2* p = reinterpret_cast<const ulonglong2*>(&tbl[s]);
-                ulonglong2 kv = p[0]; ulonglong2 cv = p[1];
-                key128 kk; kk.lo = kv.x; kk.hi = kv.y;
-                *reinterpret_cast<key128*>(&keys[j]) = kk; cnts[j] = (uint32_t)cv.x;
-                if (!(kv.x == ~0ull && kv.y == ~0ull)) have |= 1u << j;
+        for (int j = 0; j < 4; j++) {
+            const unsigned long long sl = tile0 + (unsigned long long)j * 256ull + threadIdx.x;
+            cnts[j] = 0xFFFFFFFFu;
+            if (sl < P.n_slots) {
+                if constexpr (!WIDE) {
+                    ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&tbl[sl]);
+                    keys[j] = v.x; cnts[j] = (uint32_t)v.y;
+                    if (v.x != ~0ull) { have |= 1u << j; if (P.clear) *reinterpret_cast<ulonglong2*>(&tbl[sl]) = make_ulonglong2(~0ull, ~0ull); }
+                } else {
+                    ulonglong2* p = reinterpret_cast<ulonglong2*>(&tbl[sl]);
+                    ulonglong2 kv = p[0]; ulonglong2 cv = p[1];
+                    key128 kk; kk.lo = kv.x; kk.hi = kv.y;
+                    keys[j] = kk; cnts[j] = (uint32_t)cv.x;
+                    if (!(kv.x == ~0ull && kv.y == ~0ull)) {
+                        have |= 1u << j;
+                        if (P.clear) { p[0] = make_ulonglong2(~0ull, ~0ull); p[1] = make_ulonglong2(~0ull, ~0ull); }
+                    }
+                }
+            }
+        }
+        const unsigned int c = __popc(have);
+        unsigned int incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { unsigned int t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
+        __syncthreads();                                   // previous tile's s_warp / s_base fully consumed
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        unsigned int wbase = 0, total = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { unsigned int t = s_warp[i]; if (i < warp) wbase += t; total += t; }
+        if (total == 0) continue;                          // block-uniform
+        if (threadIdx.x == 0) {
+            const int bin = P.bin_lo + find_bin(P.tbl_base, 0, P.n_bins, tile0);
+            s_bin = bin;
+            s_base = P.out_base[bin] - P.out_origin + atomicAdd(&P.out_cursor[bin], (unsigned long long)total);
+        }
+        __syncthreads();
+        const unsigned long long base = s_base; const uint32_t bin = (uint32_t)s_bin;
+        if (base + total > P.out_cap) { if (threadIdx.x == 0) *P.cap_overflow = 1; continue; }
+        unsigned long long o = base + wbase + (incl - c);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (have & (1u << j)) {
+                const uint32_t n = cnts[j] + 1u;
+                reinterpret_cast<Key*>(P.out_keys)[o] = keys[j];
+                P.out_cnt[o] = n;
+                o++;
+                uint64_t hi, lo;
+                if constexpr (!WIDE) { hi = 0; lo = keys[j]; } else { hi = keys[j].hi; lo = keys[j].lo; }
+                const uint64_t h = entry_hash(bin, hi, lo);
+                dsum += h * (uint64_t)n; dxor ^= mix64(h + n); dcnt += n;
             }
         }
     }
-    unsigned int c = __popc(have);
-    unsigned int incl = c;
+    if (P.acc) {
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { unsigned int t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    unsigned int wbase = 0, total = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) { unsigned int t = s_warp[i]; if (i < warp) wbase += t; total += t; }
-    if (total == 0) return;
-    if (threadIdx.x == 0) {
-        int bin_local = find_bin(P.tbl_base, 0, P.n_bins, tile0);
-        int bin = P.bin_lo + bin_local;
-        s_base = P.out_base[bin] - P.out_origin + atomicAdd(&P.out_cursor[bin], (unsigned long long)total);
-    }
-    __syncthreads();
-    unsigned long long o = s_base + wbase + (incl - c);
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        if (have & (1u << j)) {
-            reinterpret_cast<Key*>(P.out_keys)[o] = keys[j];
-            P.out_cnt[o] = cnts[j] + 1u;
-            o++;
+        for (int d = 16; d; d >>= 1) {
+            dsum += __shfl_xor_sync(0xFFFFFFFFu, dsum, d); dxor ^= __shfl_xor_sync(0xFFFFFFFFu, dxor, d); dcnt += __shfl_xor_sync(0xFFFFFFFFu, dcnt, d);
+        }
+        if (lane == 0 && dcnt) {
+            const int a = (blockIdx.x * 8 + warp) & 63;
+            atomicAdd(&P.acc[a], dsum); atomicXor(&P.acc[64 + a], dxor); atomicAdd(&P.acc[128 + a], dcnt);
         }
     }
 }
@@ -801,7 +958,7 @@ __global__ void __launch_bounds__(256) k_bin_offsets(const unsigned long long* b
 struct DigestParams {
     const void* keys; const uint32_t* cnt; const unsigned long long* out_base; int B;
     unsigned long long n; unsigned long long origin;  // entries in this chunk, global offset of its first entry
-    unsigned long long* acc;                          // acc[0]=sum(h*cnt) acc[1]=xor(mix(h+cnt)) acc[2]=sum(cnt)
+    unsigned long long* acc;                          // [3][64]: sum(h*cnt), xor(mix(h+cnt)), sum(cnt), spread over 64 slots
 };
 template <bool WIDE>
 __global__ void __launch_bounds__(256) k_digest(const DigestParams P) {
@@ -821,7 +978,10 @@ __global__ void __launch_bounds__(256) k_digest(const DigestParams P) {
     for (int d = 16; d; d >>= 1) {
         s += __shfl_xor_sync(0xFFFFFFFFu, s, d); x ^= __shfl_xor_sync(0xFFFFFFFFu, x, d); c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
     }
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&P.acc[0], s); atomicXor(&P.acc[1], x); atomicAdd(&P.acc[2], c); }
+    if ((threadIdx.x & 31) == 0) {
+        const int a = (blockIdx.x * 8 + (threadIdx.x >> 5)) & 63;
+        atomicAdd(&P.acc[a], s); atomicXor(&P.acc[64 + a], x); atomicAdd(&P.acc[128 + a], c);
+    }
 }
 
 // ------------------------------------------------------------------ synthetic reads

@@ -89,10 +89,14 @@ struct fkm_ctx {
     double table_budget_bytes = 4.0 * (1ull << 30);
     double sort_budget_keys = 256.0 * (1 << 20);
     double load_factor = 0.6;
+    double debug_event_scale = 1.0;   // test hook: scales the run-event list capacity (forces the second-scan fallback)
+    double debug_rho_scale = 1.0;     // test hook: scales the learnt distinct/k-mer ratio (forces the overflow fallback)
+    double l2_table_bytes = 1024.0 * (1 << 20); // tables of one asynchronous batch; 0 disables the asynchronous phase (measured: 0.25-16 GB all within 8%, profiles/r1_table_sweep.txt)
     uint64_t job_launches = 0;
     uint64_t gen = 0;                 // job generation: results of older jobs are invalid
     Arena arena;
     cudaEvent_t ev[10];
+    cudaEvent_t evs[24];              // sampled per-kernel timings inside the asynchronous phase
 };
 
 // job-lifetime device memory (see Arena); "free" is a no-op, the arena is reset by the next job
@@ -129,6 +133,7 @@ extern "C" int fkm_ctx_create(int device, void* stream, fkm_ctx** out) {
     cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, device));
     c->n_sm = p.multiProcessorCount; c->smem_optin = p.sharedMemPerBlockOptin;
     for (auto& ev : c->ev) CK(cudaEventCreate(&ev));
+    for (auto& ev : c->evs) CK(cudaEventCreate(&ev));
     *out = c;
     return FKM_OK;
 }
@@ -136,6 +141,7 @@ extern "C" void fkm_ctx_destroy(fkm_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     for (auto& ev : c->ev) cudaEventDestroy(ev);
+    for (auto& ev : c->evs) cudaEventDestroy(ev);
     cudaStreamSynchronize(c->stream);
     c->arena.destroy();
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -147,6 +153,9 @@ extern "C" int fkm_ctx_set(fkm_ctx* c, const char* name, double v) {
     if (!strcmp(name, "table_budget_bytes")) c->table_budget_bytes = v;
     else if (!strcmp(name, "sort_budget_keys")) c->sort_budget_keys = v;
     else if (!strcmp(name, "load_factor")) c->load_factor = v;
+    else if (!strcmp(name, "l2_table_bytes")) c->l2_table_bytes = v;
+    else if (!strcmp(name, "debug_rho_scale")) c->debug_rho_scale = v;
+    else if (!strcmp(name, "debug_event_scale")) c->debug_event_scale = v;
     else return fkm_set_error(FKM_EINVAL, "unknown knob %s", name);
     return FKM_OK;
 }
@@ -204,8 +213,15 @@ static int fkm_read_file_pinned(const char* path, uint8_t** out, uint64_t* n) {
 }
 
 // ------------------------------------------------------------------ scan setup
-struct ScanSetup { ScanParams P; size_t smem; int grid; };
-template <bool WIDE, int MODE>
+typedef void (*ScanKernel)(const ScanParams);
+template <int MODE> static ScanKernel scan_kernel(int L) {
+    switch (L) {
+        case 0: return k_scan<MODE, 0>; case 1: return k_scan<MODE, 1>; case 2: return k_scan<MODE, 2>;
+        case 3: return k_scan<MODE, 3>; case 4: return k_scan<MODE, 4>; default: return k_scan<MODE, 5>;
+    }
+}
+struct ScanSetup { ScanParams P; size_t smem; int grid; ScanKernel fn; };
+template <int MODE>
 static int scan_setup(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const void* d_bases, const void* d_inv, uint64_t n_pos, ScanSetup* S) {
     ScanParams& P = S->P;
     memset(&P, 0, sizeof P);
@@ -218,12 +234,14 @@ static int scan_setup(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const void
     P.e_total = (MODE == 2) ? n_pos + (uint64_t)cfg->k - 1 : n_pos;
     P.n_seg = (P.e_total + P.seg_len - 1) / P.seg_len;
     P.B = (uint32_t)B;
+    P.wide = cfg->k > 32;
     P.cap = (cfg->k > 32) ? (125 - cfg->k) : (61 - cfg->k);
     P.smem_hist = (MODE == 0 && B <= kSmemHistMaxB) ? 1 : 0;
     S->smem = P.smem_hist ? (size_t)B * 8 : 0;
-    CK(cudaFuncSetAttribute(k_scan<WIDE, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->smem));
+    S->fn = scan_kernel<MODE>(P.L);
+    CK(cudaFuncSetAttribute(S->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->smem));
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan<WIDE, MODE>, kScanThreads, S->smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, S->fn, kScanThreads, S->smem));
     if (occ < 1) occ = 1;
     const uint64_t ctas = (P.n_seg + kScanThreads / 32 - 1) / (kScanThreads / 32);
     S->grid = (int)std::min<uint64_t>(ctas, (uint64_t)ctx->n_sm * occ);
@@ -260,7 +278,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
 
     unsigned long long *d_hist_rec = nullptr, *d_hist_kmer = nullptr, *d_bin_base = nullptr, *d_cursor = nullptr,
                        *d_distinct = nullptr, *d_out_base = nullptr, *d_small = nullptr, *d_tbl_base = nullptr;
-    void* d_records = nullptr; void* d_table = nullptr; int* d_ovf = nullptr;
+    void* d_records = nullptr; void* d_table = nullptr; int* d_ovf = nullptr; unsigned long long* d_acc = nullptr;
     void *d_keysA = nullptr, *d_keysB = nullptr; unsigned int *d_tile_seg = nullptr, *d_seg_tile0 = nullptr, *d_tile_hist = nullptr, *d_tile_heads = nullptr;
     unsigned long long* d_first = nullptr;
     int rc = FKM_OK;
@@ -278,25 +296,38 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
     const size_t bB = (size_t)B * 8;
     CKC(dmalloc(ctx, &d_hist_rec, bB)); CKC(dmalloc(ctx, &d_hist_kmer, bB)); CKC(dmalloc(ctx, &d_bin_base, bB + 8));
     CKC(dmalloc(ctx, &d_cursor, bB)); CKC(dmalloc(ctx, &d_distinct, bB)); CKC(dmalloc(ctx, &d_out_base, bB + 8));
-    CKC(dmalloc(ctx, &d_small, 64)); CKC(dmalloc(ctx, &d_ovf, 4)); CKC(dmalloc(ctx, &d_tbl_base, bB + 8));
+    // d_small: [0] batch total, [4] event count
+    CKC(dmalloc(ctx, &d_small, 64)); CKC(dmalloc(ctx, &d_ovf, 8)); CKC(dmalloc(ctx, &d_tbl_base, bB + 8));
+    CKC(dmalloc(ctx, &d_acc, 192 * 8));
+    CKC(cudaMemsetAsync(d_acc, 0, 192 * 8, s));
     CKC(cudaMemsetAsync(d_hist_rec, 0, bB, s)); CKC(cudaMemsetAsync(d_hist_kmer, 0, bB, s));
     CKC(cudaMemsetAsync(d_cursor, 0, bB, s)); CKC(cudaMemsetAsync(d_distinct, 0, bB, s));
     CKC(cudaMemsetAsync(d_out_base, 0, bB + 8, s)); CKC(cudaMemsetAsync(d_small, 0, 64, s));
 
-    // ---- stage 1: exact histogram (records and k-mers per bin)
+    // ---- stage 1: one scan of the input: exact bin histogram + the list of run events
     CKC(cudaEventRecord(ctx->ev[0], s));
     std::vector<unsigned long long> h_rec((size_t)B), h_kmer((size_t)B), h_base((size_t)B + 1);
+    const int w_mm = cfg->k - cfg->m + 1;
+    // runs average ~(w+1)/2 windows on random sequence; leave generous head-room, an overflow falls back to a second scan
+    const uint64_t ev_cap = (uint64_t)(((double)n_pos * std::min(0.5, 2.4 / (double)(w_mm + 1)) + (double)(1u << 20)) * ctx->debug_event_scale) + 64;
+    ulonglong2* d_events = nullptr;
+    CKC(dmalloc(ctx, &d_events, (size_t)ev_cap * 16));
     {
-        ScanSetup S; rc = scan_setup<WIDE, 0>(ctx, cfg, B, d_bases, d_inv, n_pos, &S); if (rc) { cleanup(); return rc; }
+        ScanSetup S; rc = scan_setup<0>(ctx, cfg, B, d_bases, d_inv, n_pos, &S); if (rc) { cleanup(); return rc; }
         S.P.hist_rec = d_hist_rec; S.P.hist_kmer = d_hist_kmer;
-        if (n_pos) { k_scan<WIDE, 0><<<S.grid, kScanThreads, S.smem, s>>>(S.P); CKLC(); }
+        S.P.events = d_events; S.P.ev_cap = ev_cap; S.P.ev_count = d_small + 4; S.P.ev_overflow = d_ovf;
+        CKC(cudaMemsetAsync(d_ovf, 0, 8, s));
+        if (n_pos) { S.fn<<<S.grid, kScanThreads, S.smem, s>>>(S.P); CKLC(); }
     }
     CKC(cudaEventRecord(ctx->ev[1], s));
+    unsigned long long n_events = 0; int ev_ovf = 0;
     CKC(cudaMemcpyAsync(h_rec.data(), d_hist_rec, bB, cudaMemcpyDeviceToHost, s));
     CKC(cudaMemcpyAsync(h_kmer.data(), d_hist_kmer, bB, cudaMemcpyDeviceToHost, s));
+    CKC(cudaMemcpyAsync(&n_events, d_small + 4, 8, cudaMemcpyDeviceToHost, s));
+    CKC(cudaMemcpyAsync(&ev_ovf, d_ovf, 4, cudaMemcpyDeviceToHost, s));
     CKC(cudaStreamSynchronize(s));
     tr.mark("histogram done");
-    st->d2h_bytes += 2 * bB;
+    st->d2h_bytes += 2 * bB + 12;
     uint64_t n_rec = 0, n_kmers = 0, nonempty = 0;
     for (int b = 0; b < B; b++) { h_base[(size_t)b] = n_rec; n_rec += h_rec[(size_t)b]; n_kmers += h_kmer[(size_t)b]; nonempty += h_rec[(size_t)b] ? 1 : 0; }
     h_base[(size_t)B] = n_rec;
@@ -307,10 +338,18 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
     tr.mark("records allocated", (long long)n_rec);
     CKC(cudaMemcpyAsync(d_bin_base, h_base.data(), bB + 8, cudaMemcpyHostToDevice, s));
     st->h2d_bytes += bB + 8;
-    {
-        ScanSetup S; rc = scan_setup<WIDE, 1>(ctx, cfg, B, d_bases, d_inv, n_pos, &S); if (rc) { cleanup(); return rc; }
+    if (!ev_ovf) {
+        ScatterParams Q;
+        Q.events = d_events; Q.n_events = n_events; Q.bases = (const uint64_t*)d_bases; Q.n_words = (n_pos + 31) / 32;
+        Q.B = (uint32_t)B; Q.cap = (cfg->k > 32) ? (125 - cfg->k) : (61 - cfg->k); Q.k = cfg->k;
+        Q.bin_base = d_bin_base; Q.cursor = d_cursor; Q.records = d_records;
+        if (n_events) { k_scatter_events<WIDE><<<(unsigned)((n_events + 255) / 256), 256, 0, s>>>(Q); CKLC(); }
+    } else {
+        // the event list was too small for this input: scan again, writing the records directly
+        st->n_fallbacks++;
+        ScanSetup S; rc = scan_setup<1>(ctx, cfg, B, d_bases, d_inv, n_pos, &S); if (rc) { cleanup(); return rc; }
         S.P.bin_base = d_bin_base; S.P.cursor = d_cursor; S.P.records = d_records;
-        if (n_rec) { k_scan<WIDE, 1><<<S.grid, kScanThreads, S.smem, s>>>(S.P); CKLC(); }
+        if (n_rec) { S.fn<<<S.grid, kScanThreads, S.smem, s>>>(S.P); CKLC(); }
     }
     CKC(cudaEventRecord(ctx->ev[2], s));
 
@@ -318,86 +357,190 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
     uint64_t out_total = 0;
     float ms_count = 0, ms_compact = 0;
     if (cfg->use_ht) {
-        const uint64_t budget_slots = std::max<uint64_t>(1024, (uint64_t)(ctx->table_budget_bytes / sizeof(Slot)));
-        double rho = 1.0;                         // estimate of distinct / k-mers, learnt from the first batch
+        double rho = 1.0;                         // sizing estimate of distinct / k-mers (with margin), learnt from the first batch
+        double rho_obs = 1.0;                     // the ratio actually observed
         uint64_t table_cap = 0;
         std::vector<unsigned long long> tb;
-        int lo = 0;
-        while (lo < B) {
-            bool retried = false;
-            double use_rho = rho;
-            int hi;
-            for (;;) {
-                // plan [lo, hi)
-                tb.clear(); tb.push_back(0);
-                hi = lo; uint64_t slots = 0;
+
+        // ---- synchronous batches (DRAM-sized tables, exact output allocation, retry on overflow).
+        // Used for the first batch (which measures rho) and as the fallback of the fast path.
+        auto safe_batches = [&](int lo, const int hi_end, const bool one_batch, int* next_lo) -> int {
+            const uint64_t budget_slots = std::max<uint64_t>(1024, (uint64_t)(ctx->table_budget_bytes / sizeof(Slot)));
+            while (lo < hi_end) {
+                bool retried = false;
+                double use_rho = rho;
+                int hi;
+                for (;;) {
+                    tb.clear(); tb.push_back(0);
+                    hi = lo; uint64_t slots = 0;
+                    while (hi < hi_end) {
+                        uint64_t want = (uint64_t)((double)h_kmer[(size_t)hi] * use_rho / ctx->load_factor) + 1;
+                        uint64_t sz = h_kmer[(size_t)hi] ? round_up(std::max<uint64_t>(want, 1024), 1024) : 0;
+                        if (hi > lo && slots + sz > budget_slots) break;
+                        slots += sz; tb.push_back(slots); hi++;
+                        if (one_batch && hi - lo >= std::max(1, B / 64) && slots * sizeof(Slot) > (64ull << 20)) break;   // small first batch to learn rho
+                    }
+                    if (slots > table_cap) { CKC(dmalloc(ctx, &d_table, (size_t)slots * sizeof(Slot))); table_cap = slots; }
+                    CKC(cudaEventRecord(ctx->ev[6], s));
+                    CKC(cudaMemsetAsync(d_table, 0xFF, (size_t)slots * sizeof(Slot), s));
+                    CKC(cudaMemsetAsync(d_ovf, 0, 8, s));
+                    CKC(cudaMemcpyAsync(d_tbl_base, tb.data(), tb.size() * 8, cudaMemcpyHostToDevice, s));
+                    st->h2d_bytes += tb.size() * 8;
+                    CountParams C;
+                    C.records = d_records; C.rec_lo = h_base[(size_t)lo]; C.rec_hi = h_base[(size_t)hi];
+                    C.bin_base = d_bin_base; C.bin_lo = lo; C.bin_hi = hi; C.table = d_table; C.tbl_base = d_tbl_base;
+                    C.bin_distinct = d_distinct; C.overflow = d_ovf; C.k = cfg->k; C.max_probe = 512;
+                    const uint64_t nr = C.rec_hi - C.rec_lo;
+                    if (nr) { k_count_ht<WIDE><<<(unsigned)((nr + 255) / 256), 256, 0, s>>>(C); CKLC(); }
+                    k_bin_offsets<<<1, 256, 0, s>>>(d_distinct, d_out_base, lo, hi, d_small); CKLC();
+                    CKC(cudaEventRecord(ctx->ev[7], s));
+                    unsigned long long batch_total = 0; int ovf = 0;
+                    CKC(cudaMemcpyAsync(&batch_total, d_small, 8, cudaMemcpyDeviceToHost, s));
+                    CKC(cudaMemcpyAsync(&ovf, d_ovf, 4, cudaMemcpyDeviceToHost, s));
+                    CKC(cudaStreamSynchronize(s));
+                    st->d2h_bytes += 12;
+                    { float ms; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); ms_count += ms; }
+                    if (ovf) {
+                        if (retried && use_rho >= 1.0) return fkm_set_error(FKM_ECUDA, "hash table overflow at full size (bins %d..%d)", lo, hi);
+                        CKC(cudaMemsetAsync(d_distinct + lo, 0, (size_t)(hi - lo) * 8, s));
+                        use_rho = retried ? 1.0 : std::min(1.0, use_rho * 2.0); retried = true;
+                        continue;
+                    }
+                    uint64_t nk = 0; for (int b = lo; b < hi; b++) nk += h_kmer[(size_t)b];
+                    if (nk > 100000) { rho_obs = (double)batch_total / (double)nk; rho = std::min(1.0, rho_obs * 1.25 + 0.02); }
+                    Chunk ch; ch.n = batch_total;
+                    if (batch_total) {
+                        CKC(dmalloc(ctx, &ch.keys, (size_t)batch_total * sizeof(Key)));
+                        CKC(dmalloc(ctx, &ch.cnt, (size_t)batch_total * 4));
+                        res->chunks.push_back(ch);
+                        CompactParams Q;
+                        Q.table = d_table; Q.n_slots = slots; Q.tbl_base = d_tbl_base; Q.n_bins = hi - lo; Q.bin_lo = lo;
+                        Q.out_base = d_out_base; Q.out_cursor = d_cursor; Q.out_origin = out_total; Q.out_cap = batch_total;
+                        Q.out_keys = ch.keys; Q.out_cnt = ch.cnt; Q.clear = 0; Q.cap_overflow = d_ovf + 1; Q.acc = d_acc;
+                        CKC(cudaMemsetAsync(d_cursor + lo, 0, (size_t)(hi - lo) * 8, s));
+                        CKC(cudaEventRecord(ctx->ev[6], s));
+                        const unsigned grid = (unsigned)std::min<uint64_t>((slots + 1023) / 1024, (uint64_t)ctx->n_sm * 8);
+                        k_compact_ht<WIDE><<<grid, 256, 0, s>>>(Q); CKLC();
+                        CKC(cudaEventRecord(ctx->ev[7], s));
+                        CKC(cudaStreamSynchronize(s));
+                        { float ms; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); ms_compact += ms; }
+                    }
+                    out_total += batch_total;
+                    st->n_batches++;
+                    break;
+                }
+                lo = hi;
+                if (one_batch) break;
+            }
+            *next_lo = lo;
+            return FKM_OK;
+        };
+
+        // ---- asynchronous batches with L2-resident tables: all launches are queued without a
+        // host sync; tables are sized from rho, the output arrays from rho_obs; the compaction
+        // kernel clears the slots it reads, so one memset serves every batch.  Any overflow
+        // (table or output) is caught by flags read once at the end; the caller then redoes
+        // the bins with safe_batches.
+        auto fast_batches = [&](const int lo0, bool* ok) -> int {
+            *ok = false;
+            const uint64_t budget_slots = std::max<uint64_t>(1024, (uint64_t)(ctx->l2_table_bytes / sizeof(Slot)));
+            struct Batch { int lo, hi; size_t tb_idx; uint64_t slots; };
+            std::vector<Batch> batches; std::vector<unsigned long long> tb_all;
+            uint64_t max_slots = 0, nk_rest = 0;
+            for (int lo = lo0; lo < B;) {
+                Batch bt; bt.lo = lo; bt.tb_idx = tb_all.size(); tb_all.push_back(0);
+                int hi = lo; uint64_t slots = 0;
                 while (hi < B) {
-                    uint64_t want = (uint64_t)((double)h_kmer[(size_t)hi] * use_rho / ctx->load_factor) + 1;
+                    uint64_t want = (uint64_t)((double)h_kmer[(size_t)hi] * rho / ctx->load_factor) + 1;
                     uint64_t sz = h_kmer[(size_t)hi] ? round_up(std::max<uint64_t>(want, 1024), 1024) : 0;
                     if (hi > lo && slots + sz > budget_slots) break;
-                    slots += sz; tb.push_back(slots); hi++;
-                    if (lo == 0 && rho == 1.0 && hi - lo >= std::max(1, B / 64) && slots * sizeof(Slot) > (64ull << 20)) break;   // small first batch to learn rho
+                    slots += sz; tb_all.push_back(slots); nk_rest += h_kmer[(size_t)hi]; hi++;
                 }
-                if (slots > table_cap) {
-                    dfree(ctx, d_table); d_table = nullptr;
-                    CKC(dmalloc(ctx, &d_table, (size_t)slots * sizeof(Slot)));
-                    table_cap = slots;
-                }
-                tr.mark("batch planned+table alloc", (long long)slots);
-                CKC(cudaEventRecord(ctx->ev[6], s));
-                CKC(cudaMemsetAsync(d_table, 0xFF, (size_t)slots * sizeof(Slot), s));
-                CKC(cudaMemsetAsync(d_ovf, 0, 4, s));
-                CKC(cudaMemcpyAsync(d_tbl_base, tb.data(), tb.size() * 8, cudaMemcpyHostToDevice, s));
-                st->h2d_bytes += tb.size() * 8;
+                bt.hi = hi; bt.slots = slots; batches.push_back(bt);
+                max_slots = std::max(max_slots, slots);
+                lo = hi;
+            }
+            const uint64_t out_cap = std::min<uint64_t>(nk_rest, (uint64_t)((double)nk_rest * rho_obs * 1.3) + (1u << 20));
+            unsigned long long* d_tb_all = nullptr; void* d_tab = nullptr;
+            Chunk ch;
+            CKC(dmalloc(ctx, &d_tb_all, tb_all.size() * 8));
+            CKC(dmalloc(ctx, &d_tab, (size_t)std::max<uint64_t>(max_slots, 1024) * sizeof(Slot)));
+            CKC(dmalloc(ctx, &ch.keys, (size_t)std::max<uint64_t>(out_cap, 1) * sizeof(Key)));
+            CKC(dmalloc(ctx, &ch.cnt, (size_t)std::max<uint64_t>(out_cap, 1) * 4));
+            CKC(cudaMemcpyAsync(d_tb_all, tb_all.data(), tb_all.size() * 8, cudaMemcpyHostToDevice, s));
+            st->h2d_bytes += tb_all.size() * 8;
+            CKC(cudaMemsetAsync(d_tab, 0xFF, (size_t)std::max<uint64_t>(max_slots, 1024) * sizeof(Slot), s));
+            CKC(cudaMemsetAsync(d_ovf, 0, 8, s));
+            CKC(cudaMemsetAsync(d_cursor + lo0, 0, (size_t)(B - lo0) * 8, s));
+            CKC(cudaEventRecord(ctx->ev[6], s));
+            const int n_samples = 8; int sampled = 0;
+            const size_t stride = std::max<size_t>(1, batches.size() / n_samples);
+            for (size_t bi = 0; bi < batches.size(); bi++) {
+                const Batch& bt = batches[bi];
+                const bool sample = (bi % stride == stride / 2) && sampled < n_samples;
                 CountParams C;
-                C.records = d_records; C.rec_lo = h_base[(size_t)lo]; C.rec_hi = h_base[(size_t)hi];
-                C.bin_base = d_bin_base; C.bin_lo = lo; C.bin_hi = hi; C.table = d_table; C.tbl_base = d_tbl_base;
+                C.records = d_records; C.rec_lo = h_base[(size_t)bt.lo]; C.rec_hi = h_base[(size_t)bt.hi];
+                C.bin_base = d_bin_base; C.bin_lo = bt.lo; C.bin_hi = bt.hi; C.table = d_tab; C.tbl_base = d_tb_all + bt.tb_idx;
                 C.bin_distinct = d_distinct; C.overflow = d_ovf; C.k = cfg->k; C.max_probe = 512;
                 const uint64_t nr = C.rec_hi - C.rec_lo;
+                if (sample) CKC(cudaEventRecord(ctx->evs[3 * sampled], s));
                 if (nr) { k_count_ht<WIDE><<<(unsigned)((nr + 255) / 256), 256, 0, s>>>(C); CKLC(); }
-                k_bin_offsets<<<1, 256, 0, s>>>(d_distinct, d_out_base, lo, hi, d_small); CKLC();
-                CKC(cudaEventRecord(ctx->ev[7], s));
-                unsigned long long batch_total = 0; int ovf = 0;
-                CKC(cudaMemcpyAsync(&batch_total, d_small, 8, cudaMemcpyDeviceToHost, s));
-                CKC(cudaMemcpyAsync(&ovf, d_ovf, 4, cudaMemcpyDeviceToHost, s));
-                CKC(cudaStreamSynchronize(s));
-                tr.mark("count synced", hi - lo);
-                st->d2h_bytes += 12;
-                { float ms; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); ms_count += ms; }
-                if (ovf) {
-                    if (retried && use_rho >= 1.0) { cleanup(); return fkm_set_error(FKM_ECUDA, "hash table overflow at full size (bins %d..%d)", lo, hi); }
-                    CKC(cudaMemsetAsync(d_distinct + lo, 0, (size_t)(hi - lo) * 8, s));
-                    use_rho = retried ? 1.0 : std::min(1.0, use_rho * 2.0); retried = true;
-                    continue;
-                }
-                // learn rho from what we saw
-                uint64_t nk = 0; for (int b = lo; b < hi; b++) nk += h_kmer[(size_t)b];
-                if (nk > 100000) rho = std::min(1.0, (double)batch_total / (double)nk * 1.25 + 0.02);
-                Chunk ch; ch.n = batch_total;
-                if (batch_total) {
-                    CKC(dmalloc(ctx, &ch.keys, (size_t)batch_total * sizeof(Key)));
-                    cudaError_t e2 = dmalloc(ctx, &ch.cnt, (size_t)batch_total * 4);
-                    if (e2 != cudaSuccess) { dfree(ctx, ch.keys); CKC(e2); }
-                    res->chunks.push_back(ch);
-                    tr.mark("chunk allocated", (long long)batch_total);
+                if (sample) CKC(cudaEventRecord(ctx->evs[3 * sampled + 1], s));
+                k_bin_offsets<<<1, 256, 0, s>>>(d_distinct, d_out_base, bt.lo, bt.hi, d_small); CKLC();
+                if (bt.slots) {
                     CompactParams Q;
-                    Q.table = d_table; Q.n_slots = slots; Q.tbl_base = d_tbl_base; Q.n_bins = hi - lo; Q.bin_lo = lo;
-                    Q.out_base = d_out_base; Q.out_cursor = d_cursor; Q.out_origin = out_total;
-                    Q.out_keys = ch.keys; Q.out_cnt = ch.cnt;
-                    CKC(cudaMemsetAsync(d_cursor + lo, 0, (size_t)(hi - lo) * 8, s));
-                    CKC(cudaEventRecord(ctx->ev[6], s));
-                    k_compact_ht<WIDE><<<(unsigned)((slots + 1023) / 1024), 256, 0, s>>>(Q); CKLC();
-                    CKC(cudaEventRecord(ctx->ev[7], s));
-                    CKC(cudaStreamSynchronize(s));
-                    { float ms; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); ms_compact += ms; }
-                    tr.mark("compact synced");
+                    Q.table = d_tab; Q.n_slots = bt.slots; Q.tbl_base = d_tb_all + bt.tb_idx; Q.n_bins = bt.hi - bt.lo; Q.bin_lo = bt.lo;
+                    Q.out_base = d_out_base; Q.out_cursor = d_cursor; Q.out_origin = out_total; Q.out_cap = out_cap;
+                    Q.out_keys = ch.keys; Q.out_cnt = ch.cnt; Q.clear = 1; Q.cap_overflow = d_ovf + 1; Q.acc = d_acc;
+                    const unsigned grid = (unsigned)std::min<uint64_t>((bt.slots + 1023) / 1024, (uint64_t)ctx->n_sm * 8);
+                    k_compact_ht<WIDE><<<grid, 256, 0, s>>>(Q); CKLC();
                 }
-                out_total += batch_total;
-                st->n_batches++;
-                break;
+                if (sample) { CKC(cudaEventRecord(ctx->evs[3 * sampled + 2], s)); sampled++; }
             }
-            lo = hi;
+            CKC(cudaEventRecord(ctx->ev[7], s));
+            int flags[2] = {0, 0}; unsigned long long end_off = 0;
+            CKC(cudaMemcpyAsync(flags, d_ovf, 8, cudaMemcpyDeviceToHost, s));
+            CKC(cudaMemcpyAsync(&end_off, d_out_base + B, 8, cudaMemcpyDeviceToHost, s));
+            CKC(cudaStreamSynchronize(s));
+            st->d2h_bytes += 16;
+            float ms_all = 0; cudaEventElapsedTime(&ms_all, ctx->ev[6], ctx->ev[7]);
+            float sc = 0, sp = 0;
+            for (int i = 0; i < sampled; i++) {
+                float a1 = 0, a2 = 0;
+                cudaEventElapsedTime(&a1, ctx->evs[3 * i], ctx->evs[3 * i + 1]); cudaEventElapsedTime(&a2, ctx->evs[3 * i + 1], ctx->evs[3 * i + 2]);
+                sc += a1; sp += a2;
+            }
+            const float share = (sc + sp) > 0 ? sc / (sc + sp) : 1.0f;      // split of the phase between count and offsets+compact, from the sampled batches
+            ms_count += ms_all * share; ms_compact += ms_all * (1.0f - share);
+            if (flags[0] || flags[1]) {            // undo: the caller redoes [lo0, B) synchronously
+                CKC(cudaMemsetAsync(d_distinct + lo0, 0, (size_t)(B - lo0) * 8, s));
+                CKC(cudaMemsetAsync(d_cursor + lo0, 0, (size_t)(B - lo0) * 8, s));
+                st->n_fallbacks++;
+                return FKM_OK;
+            }
+            ch.n = end_off - out_total;
+            res->chunks.push_back(ch);
+            out_total = end_off;
+            st->n_batches += batches.size();
+            *ok = true;
+            return FKM_OK;
+        };
+
+        int lo = 0;
+        rc = safe_batches(0, B, true, &lo); if (rc) { cleanup(); return rc; }
+        bool fast_ok = false;
+        const double rho_keep = rho, rho_obs_keep = rho_obs;
+        rho *= ctx->debug_rho_scale; rho_obs *= ctx->debug_rho_scale;
+        if (lo < B && ctx->l2_table_bytes >= 1.0) {
+            // the fast path folds its digest into the accumulators: keep a copy to roll back on fallback
+            unsigned long long* d_acc_keep = nullptr;
+            CKC(dmalloc(ctx, &d_acc_keep, 192 * 8));
+            CKC(cudaMemcpyAsync(d_acc_keep, d_acc, 192 * 8, cudaMemcpyDeviceToDevice, s));
+            rc = fast_batches(lo, &fast_ok); if (rc) { cleanup(); return rc; }
+            if (!fast_ok) CKC(cudaMemcpyAsync(d_acc, d_acc_keep, 192 * 8, cudaMemcpyDeviceToDevice, s));
         }
+        rho = rho_keep; rho_obs = rho_obs_keep;
+        if (!fast_ok && lo < B) { rc = safe_batches(lo, B, false, &lo); if (rc) { cleanup(); return rc; } }
     } else {
         const uint64_t budget_keys = std::max<uint64_t>(kSortTile, (uint64_t)ctx->sort_budget_keys);
         const int n_pass = (2 * cfg->k + 7) / 8;
@@ -494,23 +637,24 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
 
     // ---- stage 5: digest + bookkeeping
     CKC(cudaMemcpyAsync(res->out_base.data(), d_out_base, bB + 8, cudaMemcpyDeviceToHost, s));
-    CKC(cudaMemsetAsync(d_small, 0, 64, s));
-    {
+    if (!cfg->use_ht) {                         // the HT path folds its digest into k_compact_ht
         uint64_t origin = 0;
         for (const Chunk& ch : res->chunks) {
             if (!ch.n) continue;
             DigestParams D;
-            D.keys = ch.keys; D.cnt = ch.cnt; D.out_base = d_out_base; D.B = B; D.n = ch.n; D.origin = origin; D.acc = d_small;
+            D.keys = ch.keys; D.cnt = ch.cnt; D.out_base = d_out_base; D.B = B; D.n = ch.n; D.origin = origin; D.acc = d_acc;
             int grid = (int)std::min<uint64_t>((ch.n + 255) / 256, (uint64_t)ctx->n_sm * 8);
             k_digest<WIDE><<<grid, 256, 0, s>>>(D); CKLC();
             origin += ch.n;
         }
     }
-    unsigned long long acc[3] = {0, 0, 0};
-    CKC(cudaMemcpyAsync(acc, d_small, 24, cudaMemcpyDeviceToHost, s));
+    unsigned long long h_acc[192];
+    CKC(cudaMemcpyAsync(h_acc, d_acc, 192 * 8, cudaMemcpyDeviceToHost, s));
     CKC(cudaEventRecord(ctx->ev[4], s));
     CKC(cudaStreamSynchronize(s));
-    st->d2h_bytes += bB + 8 + 24;
+    st->d2h_bytes += bB + 8 + 192 * 8;
+    unsigned long long acc[3] = {0, 0, 0};
+    for (int i = 0; i < 64; i++) { acc[0] += h_acc[i]; acc[1] ^= h_acc[64 + i]; acc[2] += h_acc[128 + i]; }
     tr.mark("digest synced");
     res->total = out_total;
     // empty trailing bins keep the running offset
@@ -764,9 +908,9 @@ extern "C" int fkm_debug_window_bins(fkm_ctx* ctx, const fkm_config* cfg, const 
     CK(dmalloc(ctx, &d_b, std::max<size_t>(8, nw * 8))); CK(dmalloc(ctx, &d_i, std::max<size_t>(4, nw * 4))); CK(dmalloc(ctx, (void**)&d_o, std::max<size_t>(4, n_pos * 4)));
     CK(cudaMemcpyAsync(d_b, bases, nw * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_i, inv, nw * 4, cudaMemcpyHostToDevice, ctx->stream));
-    ScanSetup S; S.grid = 1; S.smem = 0;
-    if (cfg->k > 32) { rc = scan_setup<true, 2>(ctx, cfg, B, d_b, d_i, n_pos, &S); if (!rc) { S.P.dbg_bins = d_o; k_scan<true, 2><<<S.grid, kScanThreads, S.smem, ctx->stream>>>(S.P); } }
-    else { rc = scan_setup<false, 2>(ctx, cfg, B, d_b, d_i, n_pos, &S); if (!rc) { S.P.dbg_bins = d_o; k_scan<false, 2><<<S.grid, kScanThreads, S.smem, ctx->stream>>>(S.P); } }
+    ScanSetup S; S.grid = 1; S.smem = 0; S.fn = nullptr;
+    rc = scan_setup<2>(ctx, cfg, B, d_b, d_i, n_pos, &S);
+    if (!rc) { S.P.dbg_bins = d_o; S.fn<<<S.grid, kScanThreads, S.smem, ctx->stream>>>(S.P); }
     if (!rc) { CKL(); CK(cudaMemcpyAsync(bins_out, d_o, n_pos * 4, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream)); }
     dfree(ctx, d_b); dfree(ctx, d_i); dfree(ctx, d_o);
     return rc;

@@ -74,6 +74,7 @@ typedef struct fkm_stats {
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t gpu_launches;       /* kernels launched by this job                             */
     uint64_t n_batches;
+    uint64_t n_fallbacks;        /* times the asynchronous count phase had to be redone synchronously */
     double   ms_total;           /* host wall time of the call                               */
     double   ms_stage[8];        /* 0 parse/pack+H2D 1 histogram 2 scatter 3 count 4 compact/reduce 5 digest 6 D2H/write 7 spare (device, CUDA events) */
 } fkm_stats;
@@ -85,7 +86,7 @@ const char* fkm_last_error(void);
 int  fkm_ctx_create(int device, void* stream, fkm_ctx** out);
 void fkm_ctx_destroy(fkm_ctx* ctx);
 int  fkm_ctx_sync(fkm_ctx* ctx);
-/* tuning knobs (optional): name in {"table_budget_bytes","sort_budget_keys","load_factor"} */
+/* tuning knobs (optional): name in {"table_budget_bytes","l2_table_bytes","sort_budget_keys","load_factor"} */
 int  fkm_ctx_set(fkm_ctx* ctx, const char* name, double value);
 
 /* b = min(4^m, max_b) and outputDir = outputDirectory + prefix + "k"+k+"_m"+m+"_x"+x+"_b"+b+"_s"+sequenceType

@@ -192,6 +192,7 @@ def test_small_table_budget_batches_and_retry(ctx, oracle):
     c2 = fk.Context(0)
     try:
         c2.set("table_budget_bytes", 1 << 20)
+        c2.set("l2_table_bytes", 0)                        # synchronous batches only
         res, st = c2.count_fasta(cfg(28, 10, 3, 2048, 1), fasta)
         assert st["n_batches"] > 4
         assert_same(res.sorted_arrays(), want, "tiny budget")
@@ -199,6 +200,41 @@ def test_small_table_budget_batches_and_retry(ctx, oracle):
         res, st = c2.count_fasta(cfg(28, 10, 3, 2048, 0), fasta)
         assert st["n_batches"] > 4
         assert_same(res.arrays(), want, "tiny sort budget")
+    finally:
+        c2.close()
+
+
+def test_async_phase_overflow_falls_back(oracle):
+    """A wrong distinct/k-mer estimate overflows the L2-resident tables: the job must notice and redo the
+    bins synchronously with the same result."""
+    spec = dict(seeds=(17, 18, 19), genome_len=400000, n_reads=40000, read_len=100)
+    fasta = fk.synth_fasta(spec).tobytes()
+    want = oracle.count(fasta, 28, 10, 3, 2048, 1, threads=8)
+    c2 = fk.Context(0)
+    try:
+        res, st = c2.count_fasta(cfg(28, 10, 3, 2048, 1), fasta)
+        assert st["n_fallbacks"] == 0 and st["n_batches"] >= 2
+        assert_same(res.sorted_arrays(), want, "async phase")
+        c2.set("debug_rho_scale", 0.02)
+        res, st = c2.count_fasta(cfg(28, 10, 3, 2048, 1), fasta)
+        assert st["n_fallbacks"] == 1
+        assert_same(res.sorted_arrays(), want, "after fallback")
+        assert (st["digest_sum"], st["digest_xor"]) == (want["stats"]["digest_sum"], want["stats"]["digest_xor"])
+        c2.set("debug_rho_scale", 1.0)
+        c2.set("debug_event_scale", 0.001)                 # run-event list too small: second scan writes the records directly
+        for ht in (1, 0):
+            res, st = c2.count_fasta(cfg(28, 10, 3, 2048, ht), fasta)
+            assert st["n_fallbacks"] == 1
+            assert_same(res.sorted_arrays(), want, "event overflow ht%d" % ht)
+        c2.set("debug_event_scale", 1.0)
+        c2.set("l2_table_bytes", 1 << 16)                  # many tiny asynchronous batches
+        res, st = c2.count_fasta(cfg(28, 10, 3, 2048, 1), fasta)
+        assert st["n_fallbacks"] == 0 and st["n_batches"] > 100
+        assert_same(res.sorted_arrays(), want, "tiny async batches")
+        for k, m in ((55, 13), (33, 9)):                   # wide keys through the same phases
+            w2 = oracle.count(fasta, k, m, 3, 2048, 1, threads=8)
+            res, st = c2.count_fasta(cfg(k, m, 3, 2048, 1), fasta)
+            assert_same(res.sorted_arrays(), w2, "wide async k=%d" % k)
     finally:
         c2.close()
 
