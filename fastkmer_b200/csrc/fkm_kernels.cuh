@@ -529,6 +529,7 @@ __device__ __forceinline__ key128 kmer_at_wide(const uint64_t* rec, int j, int k
 template <bool WIDE>
 __global__ void __launch_bounds__(256) k_count_ht(const CountParams P) {
     typedef typename Traits<WIDE>::Slot Slot;
+    typedef typename Traits<WIDE>::Key Key;
     constexpr int RW = Traits<WIDE>::kRecWords;
     __shared__ uint64_t s_rec[8][32 * RW];
     __shared__ uint32_t s_off[8][32];
@@ -565,19 +566,66 @@ __global__ void __launch_bounds__(256) k_count_ht(const CountParams P) {
         Slot* tbl = reinterpret_cast<Slot*>(P.table) + tb0;
         const uint32_t le_mask = (2u << lane) - 1u;
         uint32_t cb = 0;
-        for (uint32_t tb = 0; tb < T; tb += 32) {
-            const uint32_t p = excl - tb;
-            const uint32_t M = __reduce_or_sync(FULL, (n > 0 && p < 32u) ? (1u << p) : 0u);
-            const uint32_t t = tb + lane;
-            if (t < T) {
-                const int ri = (int)(cb + __popc(M & le_mask)) - 1;
-                const int j = (int)(t - s_off[warp][ri]);
-                int c;
-                if constexpr (!WIDE) c = ht_insert(reinterpret_cast<SlotN*>(tbl), size, kmer_at_narrow(&s_rec[warp][ri * RW], j, P.k), P.max_probe);
-                else c = ht_insert(reinterpret_cast<SlotW*>(tbl), size, kmer_at_wide(&s_rec[warp][ri * RW], j, P.k), P.max_probe);
-                if (c < 0) ovf = true; else claims += (unsigned)c;
+        // U independent k-mers per lane and iteration; the probe loop is a per-key state
+        // machine (0 = read the slot, 1 = CAS the empty slot, 2 = done), so U memory
+        // operations per lane are in flight during every round trip to L2 / HBM.
+        constexpr int U = 4;
+        for (uint32_t tb = 0; tb < T; tb += 32 * U) {
+            Key key[U]; unsigned long long slot[U]; int state[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                state[u] = 2; slot[u] = 0; key[u] = Key();
+                const uint32_t bb = tb + 32u * u;
+                if (bb < T) {                                                       // warp-uniform
+                    const uint32_t p = excl - bb;
+                    const uint32_t M = __reduce_or_sync(FULL, (n > 0 && p < 32u) ? (1u << p) : 0u);
+                    const uint32_t t = bb + lane;
+                    if (t < T) {
+                        const int ri = (int)(cb + __popc(M & le_mask)) - 1;
+                        const int j = (int)(t - s_off[warp][ri]);
+                        if constexpr (!WIDE) key[u] = kmer_at_narrow(&s_rec[warp][ri * RW], j, P.k);
+                        else key[u] = kmer_at_wide(&s_rec[warp][ri * RW], j, P.k);
+                        slot[u] = slot_of(key_hash(key[u]), size);
+                        state[u] = 0;
+                    }
+                    cb += __popc(M);
+                }
             }
-            cb += __popc(M);
+            for (int round = 0;; round++) {
+                Key got[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    if constexpr (!WIDE) {
+                        SlotN* sp = reinterpret_cast<SlotN*>(tbl) + slot[u];
+                        if (state[u] == 0) got[u] = __ldcg(&sp->key);
+                        else if (state[u] == 1) got[u] = atomicCAS((unsigned long long*)&sp->key, ~0ull, (unsigned long long)key[u]);
+                    } else {
+                        SlotW* sp = reinterpret_cast<SlotW*>(tbl) + slot[u];
+                        if (state[u] == 0) { got[u].lo = __ldcg(&sp->key.lo); got[u].hi = __ldcg(&sp->key.hi); }
+                        else if (state[u] == 1) { const key128 empty = {~0ull, ~0ull}; got[u] = cas128(&sp->key, empty, key[u]); }
+                    }
+                }
+                bool more = false;
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    if (state[u] == 2) continue;
+                    bool is_empty, maybe_empty;
+                    if constexpr (!WIDE) { is_empty = got[u] == ~0ull; maybe_empty = is_empty; }
+                    else {      // a half equal to all-ones may be a torn read of a slot being claimed: the CAS decides
+                        is_empty = got[u].lo == ~0ull && got[u].hi == ~0ull;
+                        maybe_empty = got[u].lo == ~0ull || got[u].hi == ~0ull;
+                    }
+                    uint32_t* cp;
+                    if constexpr (!WIDE) cp = &(reinterpret_cast<SlotN*>(tbl) + slot[u])->cnt;
+                    else cp = &(reinterpret_cast<SlotW*>(tbl) + slot[u])->cnt;
+                    if (state[u] == 1 && is_empty) { claims++; atomicAdd(cp, 1u); state[u] = 2; }
+                    else if (key_eq(got[u], key[u])) { atomicAdd(cp, 1u); state[u] = 2; }
+                    else if (state[u] == 0 && maybe_empty) { state[u] = 1; more = true; }
+                    else { if (++slot[u] == size) slot[u] = 0; state[u] = 0; more = true; }
+                }
+                if (!more) break;
+                if (round > 2 * P.max_probe) { ovf = true; break; }
+            }
         }
         const unsigned int tot = __reduce_add_sync(FULL, claims);
         if (lane == 0 && tot) atomicAdd(&P.bin_distinct[bin0], (unsigned long long)tot);
