@@ -251,6 +251,8 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         assert se["digest_sum"] == st["digest_sum"] and se["n_kmers"] == st["n_kmers"], "host path and resident path disagree"
+        if dist is not None:
+            assert se["digest_sum_global"] == st["digest_sum_global"] and se["total_count_global"] == se["n_kmers_global"]
         e2e = {"value": n_bases_total / (dt / args.steps), "unit": "bases/s", "h2d_bytes_per_step": int(se["h2d_bytes"]),
                "d2h_bytes_per_step": int(se["d2h_bytes"]), "ms_per_step": dt / args.steps * 1e3,
                "ms_h2d_and_parse": se["ms_stage"][0]}
@@ -286,6 +288,13 @@ def main():
                 "avg_launch_ms": count_ms / n_count_launches,
                 "pipeline": {"bytes_alg": bytes_alg, "achieved": bytes_alg / (ms_step * 1e-3) / 1e9 / world,
                              "frac": bytes_alg / (ms_step * 1e-3) / 1e9 / world / peak}}
+    shuffle = None
+    if world > 1:
+        # the bin exchange: bytes this rank sent to its peers and the time of the all-to-all (rank 0's view)
+        sent, xms = st.get("exchange_bytes_sent", 0), st.get("exchange_ms", 0.0)
+        gbs = sent / (xms * 1e-3) / 1e9 if xms else None
+        shuffle = {"bytes_sent_per_gpu": int(sent), "ms": xms, "GBps_per_gpu": gbs, "nvlink_peak_GBps": 770.0,
+                   "frac": gbs / 770.0 if gbs else None, "peak_source": "measured peer copy, B200_PROFILING.md"}
     line = {"metric": "bases_per_sec", "value": value, "unit": "bases/s", "kmers_per_sec": n_kmers_total / (ms_step * 1e-3),
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
@@ -295,7 +304,8 @@ def main():
                        "l2": "inputs (%.1f GB packed) larger than L2, no flush" % (n_pos * 3 / 8 / 1e9)},
             "stage_ms": {"histogram": stage[1], "scatter": stage[2], "count": stage[3], "compact": stage[4], "digest": stage[5],
                          "device_pipeline": stage[7]},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "shuffle": shuffle}
     print(json.dumps(line))
     ctx.close()
     if dist is not None:

@@ -82,6 +82,12 @@ def load_library():
         "fkm_synth_packed_device": (C.c_int, [vp, C.POINTER(fkm_synth), C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]),
         "fkm_device_free": (C.c_int, [vp, vp]),
         "fkm_debug_window_bins": (C.c_int, [vp, cfgp, vp, vp, u64, vp]),
+        "fkm_record_bytes": (i32, [cfgp]),
+        "fkm_mg_scan": (C.c_int, [vp, cfgp, vp, vp, u64, vp, vp]),
+        "fkm_mg_scan_fasta": (C.c_int, [vp, cfgp, vp, u64, vp, vp, C.POINTER(u64)]),
+        "fkm_mg_scatter": (C.c_int, [vp, vp, vp]),
+        "fkm_mg_regroup": (C.c_int, [vp, cfgp, vp, u64, vp, vp, u64, C.POINTER(vp)]),
+        "fkm_mg_count": (C.c_int, [vp, cfgp, vp, vp, vp, C.POINTER(vp), stp]),
         "fkm_debug_pack_fasta_device": (C.c_int, [vp, vp, u64, vp, vp, u64, C.POINTER(u64), C.POINTER(u64)]),
         "fkm_total_launches": (u64, []),
     }
@@ -118,6 +124,10 @@ def _stats(st):
         v = getattr(st, name)
         d[name] = list(v) if name == "ms_stage" else v
     return d
+
+
+def record_bytes(configuration):
+    return int(load_library().fkm_record_bytes(C.byref(_cfg(configuration))))
 
 
 def derive(configuration):
@@ -297,6 +307,49 @@ class Context:
             if p.value == ptr:
                 self._dev_bufs.remove(p)
         _check(load_library().fkm_device_free(self._h, C.c_void_p(ptr)))
+
+    # ---- staged entry points (multi-GPU; see fastkmer_b200/multigpu.py)
+    def mg_scan(self, configuration, d_bases, d_inv, n_positions):
+        """-> (hist_rec, hist_kmer) uint64[b]: records / k-mers this shard puts into every bin."""
+        b = int(min(4 ** configuration.m, configuration.max_b))
+        rec = np.zeros(b, dtype=np.uint64)
+        kmer = np.zeros(b, dtype=np.uint64)
+        cfg = _cfg(configuration)
+        _check(load_library().fkm_mg_scan(self._h, C.byref(cfg), C.c_void_p(d_bases), C.c_void_p(d_inv), n_positions,
+                                          rec.ctypes.data, kmer.ctypes.data))
+        return rec, kmer
+
+    def mg_scan_fasta(self, configuration, fasta):
+        arr = np.frombuffer(fasta, dtype=np.uint8) if isinstance(fasta, (bytes, bytearray)) else fasta
+        b = int(min(4 ** configuration.m, configuration.max_b))
+        rec = np.zeros(b, dtype=np.uint64)
+        kmer = np.zeros(b, dtype=np.uint64)
+        nb = C.c_uint64()
+        cfg = _cfg(configuration)
+        _check(load_library().fkm_mg_scan_fasta(self._h, C.byref(cfg), arr.ctypes.data, arr.size, rec.ctypes.data, kmer.ctypes.data,
+                                                C.byref(nb)))
+        return rec, kmer, nb.value
+
+    def mg_scatter(self, bin_base, d_send):
+        bin_base = np.ascontiguousarray(bin_base, dtype=np.uint64)
+        _check(load_library().fkm_mg_scatter(self._h, bin_base.ctypes.data, C.c_void_p(d_send)))
+
+    def mg_regroup(self, configuration, d_recv, n_records, seg_src, seg_dst):
+        seg_src = np.ascontiguousarray(seg_src, dtype=np.uint64)
+        seg_dst = np.ascontiguousarray(seg_dst, dtype=np.uint64)
+        out = C.c_void_p()
+        cfg = _cfg(configuration)
+        _check(load_library().fkm_mg_regroup(self._h, C.byref(cfg), C.c_void_p(d_recv), n_records, seg_src.ctypes.data,
+                                             seg_dst.ctypes.data, len(seg_dst), C.byref(out)))
+        return out.value or 0
+
+    def mg_count(self, configuration, d_records, bin_rec, bin_kmer, want_result=True):
+        bin_rec = np.ascontiguousarray(bin_rec, dtype=np.uint64)
+        bin_kmer = np.ascontiguousarray(bin_kmer, dtype=np.uint64)
+        st, cfg, h = fkm_stats(), _cfg(configuration), C.c_void_p()
+        _check(load_library().fkm_mg_count(self._h, C.byref(cfg), C.c_void_p(d_records), bin_rec.ctypes.data, bin_kmer.ctypes.data,
+                                           C.byref(h) if want_result else None, C.byref(st)))
+        return (CountResult(h, configuration.k, self) if want_result else None), _stats(st)
 
     def pack_fasta_device(self, fasta: bytes):
         """Device ingest of FASTA text, copied back: (bases, inv, n_positions, n_bases) — test hook."""

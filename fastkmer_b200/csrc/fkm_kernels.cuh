@@ -376,6 +376,23 @@ __global__ void __launch_bounds__(256) k_scatter_events(const ScatterParams P) {
     }
 }
 
+// multi-GPU: records received source-major -> bin-major.  Segment i of the receive buffer
+// ([seg_src[i], seg_src[i+1])) holds one (source rank, bin) pair and goes to seg_dst[i].
+struct RegroupParams {
+    const void* in; void* out; unsigned long long n; int rec_words;
+    const unsigned long long* seg_src; const unsigned long long* seg_dst; int n_seg;
+};
+__global__ void __launch_bounds__(256) k_regroup(const RegroupParams P) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    int lo = 0, hi = P.n_seg;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (P.seg_src[mid] <= i) lo = mid; else hi = mid; }
+    const unsigned long long o = P.seg_dst[lo] + (i - P.seg_src[lo]);
+    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(P.in); ulonglong2* dst = reinterpret_cast<ulonglong2*>(P.out);
+    if (P.rec_words == 2) dst[o] = __ldcs(src + i);
+    else { dst[2 * o] = __ldcs(src + 2 * i); dst[2 * o + 1] = __ldcs(src + 2 * i + 1); }
+}
+
 // ------------------------------------------------------------------ record -> k-mers
 // Walks the n canonical k-mers of one record; F(key) is called once per k-mer.
 template <typename F>

@@ -95,6 +95,7 @@ struct fkm_ctx {
     uint64_t job_launches = 0;
     uint64_t gen = 0;                 // job generation: results of older jobs are invalid
     Arena arena;
+    struct ScanState* mg_scan = nullptr;   // state between fkm_mg_scan and fkm_mg_scatter
     cudaEvent_t ev[10];
     cudaEvent_t evs[24];              // sampled per-kernel timings inside the asynchronous phase
 };
@@ -113,6 +114,9 @@ struct fkm_result {
     std::vector<uint64_t> out_base;      // B+1
     uint64_t total = 0;
 };
+
+struct ScanState;
+static void free_scan_state(ScanState* p);      // defined after ScanState
 
 extern "C" const char* fkm_last_error(void) { return g_err.c_str(); }
 extern "C" uint64_t fkm_total_launches(void) { return g_launches.load(); }
@@ -144,6 +148,7 @@ extern "C" void fkm_ctx_destroy(fkm_ctx* c) {
     for (auto& ev : c->evs) cudaEventDestroy(ev);
     cudaStreamSynchronize(c->stream);
     c->arena.destroy();
+    free_scan_state(c->mg_scan);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -265,9 +270,89 @@ struct Trace {
 static inline uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
 // ------------------------------------------------------------------ the pipeline
+// What the scan stage leaves behind for the scatter stage (kept in the context between the
+// staged multi-GPU entry points; a local inside the single-GPU pipeline).
+struct ScanState {
+    fkm_config cfg; int32_t B = 0;
+    const void* d_bases = nullptr; const void* d_inv = nullptr; uint64_t n_pos = 0;
+    unsigned long long *d_hist_rec = nullptr, *d_hist_kmer = nullptr, *d_small = nullptr;
+    int* d_ovf = nullptr; ulonglong2* d_events = nullptr;
+    unsigned long long n_events = 0; int ev_ovf = 0;
+    std::vector<unsigned long long> h_rec, h_kmer;
+    bool valid = false;
+};
+
+static void free_scan_state(ScanState* p) { delete p; }
+
+// stage 1: one scan of the input: exact bin histogram (records, k-mers) + the list of run events
+static int stage_scan(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const void* d_bases, const void* d_inv, uint64_t n_pos,
+                      ScanState* S, fkm_stats* st) {
+    cudaStream_t s = ctx->stream;
+    const size_t bB = (size_t)B * 8;
+    S->cfg = *cfg; S->B = B; S->d_bases = d_bases; S->d_inv = d_inv; S->n_pos = n_pos;
+    S->h_rec.assign((size_t)B, 0); S->h_kmer.assign((size_t)B, 0);
+    CK(dmalloc(ctx, &S->d_hist_rec, bB)); CK(dmalloc(ctx, &S->d_hist_kmer, bB));
+    CK(dmalloc(ctx, &S->d_small, 64)); CK(dmalloc(ctx, &S->d_ovf, 8));
+    CK(cudaMemsetAsync(S->d_hist_rec, 0, bB, s)); CK(cudaMemsetAsync(S->d_hist_kmer, 0, bB, s));
+    CK(cudaMemsetAsync(S->d_small, 0, 64, s)); CK(cudaMemsetAsync(S->d_ovf, 0, 8, s));
+    const int w_mm = cfg->k - cfg->m + 1;
+    // runs average ~(w+1)/2 windows on random sequence; leave generous head-room, an overflow falls back to a second scan
+    const uint64_t ev_cap = (uint64_t)(((double)n_pos * std::min(0.5, 2.4 / (double)(w_mm + 1)) + (double)(1u << 20)) * ctx->debug_event_scale) + 64;
+    CK(dmalloc(ctx, &S->d_events, (size_t)ev_cap * 16));
+    CK(cudaEventRecord(ctx->ev[0], s));
+    {
+        ScanSetup Q; int rc = scan_setup<0>(ctx, cfg, B, d_bases, d_inv, n_pos, &Q); if (rc) return rc;
+        Q.P.hist_rec = S->d_hist_rec; Q.P.hist_kmer = S->d_hist_kmer;
+        Q.P.events = S->d_events; Q.P.ev_cap = ev_cap; Q.P.ev_count = S->d_small; Q.P.ev_overflow = S->d_ovf;
+        if (n_pos) { Q.fn<<<Q.grid, kScanThreads, Q.smem, s>>>(Q.P); CKL(); }
+    }
+    CK(cudaEventRecord(ctx->ev[1], s));
+    CK(cudaMemcpyAsync(S->h_rec.data(), S->d_hist_rec, bB, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(S->h_kmer.data(), S->d_hist_kmer, bB, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&S->n_events, S->d_small, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&S->ev_ovf, S->d_ovf, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    st->d2h_bytes += 2 * bB + 12;
+    float ms; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); st->ms_stage[1] = ms;
+    S->valid = true;
+    return FKM_OK;
+}
+
+// stage 2: run events -> super-k-mer records at d_records[bin_base[bin] + ...] (the "shuffle").  bin_base is any
+// per-bin record offset table: bin-major on one GPU, owner-major for the multi-GPU send buffer.
+static int stage_scatter(fkm_ctx* ctx, ScanState* S, const unsigned long long* d_bin_base, unsigned long long* d_cursor,
+                         void* d_records, uint64_t n_rec, fkm_stats* st) {
+    cudaStream_t s = ctx->stream;
+    const fkm_config* cfg = &S->cfg;
+    const bool wide = cfg->k > 32;
+    CK(cudaEventRecord(ctx->ev[1], s));
+    if (!S->ev_ovf) {
+        ScatterParams Q;
+        Q.events = S->d_events; Q.n_events = S->n_events; Q.bases = (const uint64_t*)S->d_bases; Q.n_words = (S->n_pos + 31) / 32;
+        Q.B = (uint32_t)S->B; Q.cap = wide ? (125 - cfg->k) : (61 - cfg->k); Q.k = cfg->k;
+        Q.bin_base = d_bin_base; Q.cursor = d_cursor; Q.records = d_records;
+        if (S->n_events) {
+            const unsigned grid = (unsigned)((S->n_events + 255) / 256);
+            if (wide) k_scatter_events<true><<<grid, 256, 0, s>>>(Q); else k_scatter_events<false><<<grid, 256, 0, s>>>(Q);
+            CKL();
+        }
+    } else {
+        // the event list was too small for this input: scan again, writing the records directly
+        st->n_fallbacks++;
+        ScanSetup Q; int rc = scan_setup<1>(ctx, cfg, S->B, S->d_bases, S->d_inv, S->n_pos, &Q); if (rc) return rc;
+        Q.P.bin_base = d_bin_base; Q.P.cursor = d_cursor; Q.P.records = d_records;
+        if (n_rec) { Q.fn<<<Q.grid, kScanThreads, Q.smem, s>>>(Q.P); CKL(); }
+    }
+    CK(cudaEventRecord(ctx->ev[2], s));
+    return FKM_OK;
+}
+
+// records that are already bin-major on this device (multi-GPU: after the exchange)
+struct PreScattered { const void* d_records; const uint64_t* bin_rec; const uint64_t* bin_kmer; };
+
 template <bool WIDE>
 static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const void* d_bases, const void* d_inv,
-                        uint64_t n_pos, fkm_result* res, fkm_stats* st) {
+                        uint64_t n_pos, fkm_result* res, fkm_stats* st, const PreScattered* pre) {
     typedef typename Traits<WIDE>::Key Key;
     typedef typename Traits<WIDE>::Slot Slot;
     cudaStream_t s = ctx->stream;
@@ -276,7 +361,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
     res->B = B; res->k = cfg->k; res->wide = WIDE; res->sorted = !cfg->use_ht; res->device = ctx->device;
     res->out_base.assign((size_t)B + 1, 0);
 
-    unsigned long long *d_hist_rec = nullptr, *d_hist_kmer = nullptr, *d_bin_base = nullptr, *d_cursor = nullptr,
+    unsigned long long *d_bin_base = nullptr, *d_cursor = nullptr,
                        *d_distinct = nullptr, *d_out_base = nullptr, *d_small = nullptr, *d_tbl_base = nullptr;
     void* d_records = nullptr; void* d_table = nullptr; int* d_ovf = nullptr; unsigned long long* d_acc = nullptr;
     void *d_keysA = nullptr, *d_keysB = nullptr; unsigned int *d_tile_seg = nullptr, *d_seg_tile0 = nullptr, *d_tile_hist = nullptr, *d_tile_heads = nullptr;
@@ -284,7 +369,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
     int rc = FKM_OK;
     // everything below frees through this lambda
     auto cleanup = [&]() {
-        dfree(ctx, d_hist_rec); dfree(ctx, d_hist_kmer); dfree(ctx, d_bin_base); dfree(ctx, d_cursor); dfree(ctx, d_distinct);
+        dfree(ctx, d_bin_base); dfree(ctx, d_cursor); dfree(ctx, d_distinct);
         dfree(ctx, d_out_base); dfree(ctx, d_small); dfree(ctx, d_tbl_base); dfree(ctx, d_records); dfree(ctx, d_table); dfree(ctx, d_ovf);
         dfree(ctx, d_keysA); dfree(ctx, d_keysB); dfree(ctx, d_tile_seg); dfree(ctx, d_seg_tile0); dfree(ctx, d_tile_hist); dfree(ctx, d_tile_heads); dfree(ctx, d_first);
     };
@@ -294,64 +379,38 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
 
     Trace tr;
     const size_t bB = (size_t)B * 8;
-    CKC(dmalloc(ctx, &d_hist_rec, bB)); CKC(dmalloc(ctx, &d_hist_kmer, bB)); CKC(dmalloc(ctx, &d_bin_base, bB + 8));
+    CKC(dmalloc(ctx, &d_bin_base, bB + 8));
     CKC(dmalloc(ctx, &d_cursor, bB)); CKC(dmalloc(ctx, &d_distinct, bB)); CKC(dmalloc(ctx, &d_out_base, bB + 8));
-    // d_small: [0] batch total, [4] event count
     CKC(dmalloc(ctx, &d_small, 64)); CKC(dmalloc(ctx, &d_ovf, 8)); CKC(dmalloc(ctx, &d_tbl_base, bB + 8));
     CKC(dmalloc(ctx, &d_acc, 192 * 8));
     CKC(cudaMemsetAsync(d_acc, 0, 192 * 8, s));
-    CKC(cudaMemsetAsync(d_hist_rec, 0, bB, s)); CKC(cudaMemsetAsync(d_hist_kmer, 0, bB, s));
     CKC(cudaMemsetAsync(d_cursor, 0, bB, s)); CKC(cudaMemsetAsync(d_distinct, 0, bB, s));
     CKC(cudaMemsetAsync(d_out_base, 0, bB + 8, s)); CKC(cudaMemsetAsync(d_small, 0, 64, s));
 
-    // ---- stage 1: one scan of the input: exact bin histogram + the list of run events
-    CKC(cudaEventRecord(ctx->ev[0], s));
-    std::vector<unsigned long long> h_rec((size_t)B), h_kmer((size_t)B), h_base((size_t)B + 1);
-    const int w_mm = cfg->k - cfg->m + 1;
-    // runs average ~(w+1)/2 windows on random sequence; leave generous head-room, an overflow falls back to a second scan
-    const uint64_t ev_cap = (uint64_t)(((double)n_pos * std::min(0.5, 2.4 / (double)(w_mm + 1)) + (double)(1u << 20)) * ctx->debug_event_scale) + 64;
-    ulonglong2* d_events = nullptr;
-    CKC(dmalloc(ctx, &d_events, (size_t)ev_cap * 16));
-    {
-        ScanSetup S; rc = scan_setup<0>(ctx, cfg, B, d_bases, d_inv, n_pos, &S); if (rc) { cleanup(); return rc; }
-        S.P.hist_rec = d_hist_rec; S.P.hist_kmer = d_hist_kmer;
-        S.P.events = d_events; S.P.ev_cap = ev_cap; S.P.ev_count = d_small + 4; S.P.ev_overflow = d_ovf;
-        CKC(cudaMemsetAsync(d_ovf, 0, 8, s));
-        if (n_pos) { S.fn<<<S.grid, kScanThreads, S.smem, s>>>(S.P); CKLC(); }
+    std::vector<unsigned long long> h_rec, h_kmer, h_base((size_t)B + 1);
+    ScanState scan;
+    if (!pre) {
+        rc = stage_scan(ctx, cfg, B, d_bases, d_inv, n_pos, &scan, st); if (rc) return rc;
+        h_rec.swap(scan.h_rec); h_kmer.swap(scan.h_kmer);
+        tr.mark("histogram done");
+    } else {
+        h_rec.assign(pre->bin_rec, pre->bin_rec + B); h_kmer.assign(pre->bin_kmer, pre->bin_kmer + B);
+        CKC(cudaEventRecord(ctx->ev[0], s));
     }
-    CKC(cudaEventRecord(ctx->ev[1], s));
-    unsigned long long n_events = 0; int ev_ovf = 0;
-    CKC(cudaMemcpyAsync(h_rec.data(), d_hist_rec, bB, cudaMemcpyDeviceToHost, s));
-    CKC(cudaMemcpyAsync(h_kmer.data(), d_hist_kmer, bB, cudaMemcpyDeviceToHost, s));
-    CKC(cudaMemcpyAsync(&n_events, d_small + 4, 8, cudaMemcpyDeviceToHost, s));
-    CKC(cudaMemcpyAsync(&ev_ovf, d_ovf, 4, cudaMemcpyDeviceToHost, s));
-    CKC(cudaStreamSynchronize(s));
-    tr.mark("histogram done");
-    st->d2h_bytes += 2 * bB + 12;
     uint64_t n_rec = 0, n_kmers = 0, nonempty = 0;
     for (int b = 0; b < B; b++) { h_base[(size_t)b] = n_rec; n_rec += h_rec[(size_t)b]; n_kmers += h_kmer[(size_t)b]; nonempty += h_rec[(size_t)b] ? 1 : 0; }
     h_base[(size_t)B] = n_rec;
     st->n_kmers = n_kmers; st->n_superkmers = n_rec; st->superkmer_bytes = n_rec * rec_bytes; st->n_nonempty_bins = nonempty;
-
-    // ---- stage 2: scatter super-k-mer records, bin-major (the "shuffle")
-    CKC(dmalloc(ctx, &d_records, std::max<size_t>(16, (size_t)n_rec * rec_bytes)));
-    tr.mark("records allocated", (long long)n_rec);
     CKC(cudaMemcpyAsync(d_bin_base, h_base.data(), bB + 8, cudaMemcpyHostToDevice, s));
     st->h2d_bytes += bB + 8;
-    if (!ev_ovf) {
-        ScatterParams Q;
-        Q.events = d_events; Q.n_events = n_events; Q.bases = (const uint64_t*)d_bases; Q.n_words = (n_pos + 31) / 32;
-        Q.B = (uint32_t)B; Q.cap = (cfg->k > 32) ? (125 - cfg->k) : (61 - cfg->k); Q.k = cfg->k;
-        Q.bin_base = d_bin_base; Q.cursor = d_cursor; Q.records = d_records;
-        if (n_events) { k_scatter_events<WIDE><<<(unsigned)((n_events + 255) / 256), 256, 0, s>>>(Q); CKLC(); }
+    if (!pre) {
+        CKC(dmalloc(ctx, &d_records, std::max<size_t>(16, (size_t)n_rec * rec_bytes)));
+        tr.mark("records allocated", (long long)n_rec);
+        rc = stage_scatter(ctx, &scan, d_bin_base, d_cursor, d_records, n_rec, st); if (rc) return rc;
     } else {
-        // the event list was too small for this input: scan again, writing the records directly
-        st->n_fallbacks++;
-        ScanSetup S; rc = scan_setup<1>(ctx, cfg, B, d_bases, d_inv, n_pos, &S); if (rc) { cleanup(); return rc; }
-        S.P.bin_base = d_bin_base; S.P.cursor = d_cursor; S.P.records = d_records;
-        if (n_rec) { S.fn<<<S.grid, kScanThreads, S.smem, s>>>(S.P); CKLC(); }
+        d_records = const_cast<void*>(pre->d_records);
+        CKC(cudaEventRecord(ctx->ev[2], s));
     }
-    CKC(cudaEventRecord(ctx->ev[2], s));
 
     // ---- stage 3/4: per-bin exact count, batches of consecutive bins
     uint64_t out_total = 0;
@@ -661,8 +720,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
     for (int b = 0; b < B; b++) if (res->out_base[(size_t)b + 1] < res->out_base[(size_t)b]) res->out_base[(size_t)b + 1] = res->out_base[(size_t)b];
     st->n_distinct = out_total; st->digest_sum = acc[0]; st->digest_xor = acc[1]; st->total_count = acc[2];
     float ms;
-    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); st->ms_stage[1] = ms;
-    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); st->ms_stage[2] = ms;
+    if (!pre) { cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); st->ms_stage[2] = ms; }
     st->ms_stage[3] = ms_count; st->ms_stage[4] = ms_compact;
     cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); st->ms_stage[5] = ms;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]); st->ms_stage[7] = ms;      // whole device pipeline
@@ -676,7 +734,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
 }
 
 static int count_device(fkm_ctx* ctx, const fkm_config* cfg, const void* d_bases, const void* d_inv, uint64_t n_pos,
-                        fkm_result** out, fkm_stats* stats) {
+                        fkm_result** out, fkm_stats* stats, const PreScattered* pre = nullptr) {
     int32_t B = 0; int rc = validate(cfg, &B); if (rc) return rc;
     if (!ctx) return fkm_set_error(FKM_EINVAL, "ctx is NULL");
     CK(cudaSetDevice(ctx->device));
@@ -687,8 +745,8 @@ static int count_device(fkm_ctx* ctx, const fkm_config* cfg, const void* d_bases
     st->n_positions = n_pos;
     auto t0 = std::chrono::steady_clock::now();
     fkm_result* res = new fkm_result();
-    rc = (cfg->k > 32) ? run_pipeline<true>(ctx, cfg, B, d_bases, d_inv, n_pos, res, st)
-                       : run_pipeline<false>(ctx, cfg, B, d_bases, d_inv, n_pos, res, st);
+    rc = (cfg->k > 32) ? run_pipeline<true>(ctx, cfg, B, d_bases, d_inv, n_pos, res, st, pre)
+                       : run_pipeline<false>(ctx, cfg, B, d_bases, d_inv, n_pos, res, st, pre);
     st->gpu_launches = ctx->job_launches;       // everything since job_begin (ingest included)
     st->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (rc) { fkm_result_free(res); return rc; }
@@ -829,6 +887,84 @@ extern "C" int fkm_execute_job(fkm_ctx* ctx, const fkm_config* cfg, fkm_stats* s
     }
     fkm_result_free(res);
     return rc;
+}
+
+// ------------------------------------------------------------------ staged entry points (multi-GPU)
+static int upload_and_ingest(fkm_ctx* ctx, const uint8_t* fasta, uint64_t n_bytes, void** d_bases, void** d_inv,
+                             uint64_t* n_pos, uint64_t* n_bases);
+extern "C" int32_t fkm_record_bytes(const fkm_config* cfg) { return (cfg && cfg->k > 32) ? 32 : 16; }
+
+extern "C" int fkm_mg_scan(fkm_ctx* ctx, const fkm_config* cfg, const void* d_bases, const void* d_inv, uint64_t n_pos,
+                           uint64_t* hist_rec, uint64_t* hist_kmer) {
+    if (!ctx || !hist_rec || !hist_kmer) return fkm_set_error(FKM_EINVAL, "null argument");
+    int32_t B = 0; int rc = validate(cfg, &B); if (rc) return rc;
+    rc = job_begin(ctx); if (rc) return rc;
+    if (!ctx->mg_scan) ctx->mg_scan = new ScanState();
+    ctx->mg_scan->valid = false;
+    fkm_stats st; memset(&st, 0, sizeof st);
+    rc = stage_scan(ctx, cfg, B, d_bases, d_inv, n_pos, ctx->mg_scan, &st); if (rc) return rc;
+    for (int b = 0; b < B; b++) { hist_rec[b] = ctx->mg_scan->h_rec[(size_t)b]; hist_kmer[b] = ctx->mg_scan->h_kmer[(size_t)b]; }
+    return FKM_OK;
+}
+
+// same, from FASTA text in host memory (H2D + device ingest first)
+extern "C" int fkm_mg_scan_fasta(fkm_ctx* ctx, const fkm_config* cfg, const uint8_t* fasta, uint64_t n_bytes,
+                                 uint64_t* hist_rec, uint64_t* hist_kmer, uint64_t* n_bases) {
+    if (!ctx || !hist_rec || !hist_kmer) return fkm_set_error(FKM_EINVAL, "null argument");
+    int32_t B = 0; int rc = validate(cfg, &B); if (rc) return rc;
+    rc = job_begin(ctx); if (rc) return rc;
+    void *d_b = nullptr, *d_i = nullptr; uint64_t n_pos = 0, nb = 0;
+    rc = upload_and_ingest(ctx, fasta, n_bytes, &d_b, &d_i, &n_pos, &nb); if (rc) return rc;
+    if (n_bases) *n_bases = nb;
+    if (!ctx->mg_scan) ctx->mg_scan = new ScanState();
+    ctx->mg_scan->valid = false;
+    fkm_stats st; memset(&st, 0, sizeof st);
+    rc = stage_scan(ctx, cfg, B, d_b, d_i, n_pos, ctx->mg_scan, &st); if (rc) return rc;
+    for (int b = 0; b < B; b++) { hist_rec[b] = ctx->mg_scan->h_rec[(size_t)b]; hist_kmer[b] = ctx->mg_scan->h_kmer[(size_t)b]; }
+    return FKM_OK;
+}
+
+extern "C" int fkm_mg_scatter(fkm_ctx* ctx, const uint64_t* bin_base, void* d_send) {
+    if (!ctx || !bin_base || !ctx->mg_scan || !ctx->mg_scan->valid) return fkm_set_error(FKM_EINVAL, "fkm_mg_scatter needs a preceding fkm_mg_scan");
+    CK(cudaSetDevice(ctx->device));
+    ScanState* S = ctx->mg_scan;
+    const size_t bB = (size_t)S->B * 8;
+    unsigned long long *d_bin_base = nullptr, *d_cursor = nullptr;
+    CK(dmalloc(ctx, &d_bin_base, bB + 8)); CK(dmalloc(ctx, &d_cursor, bB));
+    CK(cudaMemcpyAsync(d_bin_base, bin_base, bB + 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(d_cursor, 0, bB, ctx->stream));
+    uint64_t n_rec = 0; for (int b = 0; b < S->B; b++) n_rec += S->h_rec[(size_t)b];
+    fkm_stats st; memset(&st, 0, sizeof st);
+    int rc = stage_scatter(ctx, S, d_bin_base, d_cursor, d_send, n_rec, &st); if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FKM_OK;
+}
+
+extern "C" int fkm_mg_regroup(fkm_ctx* ctx, const fkm_config* cfg, const void* d_recv, uint64_t n_records,
+                              const uint64_t* seg_src, const uint64_t* seg_dst, uint64_t n_seg, void** d_out) {
+    if (!ctx || !cfg || !d_out) return fkm_set_error(FKM_EINVAL, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    const int rb = fkm_record_bytes(cfg);
+    unsigned long long *d_src = nullptr, *d_dst = nullptr; void* out = nullptr;
+    CK(dmalloc(ctx, &out, std::max<uint64_t>(n_records, 1) * rb));
+    CK(dmalloc(ctx, &d_src, (n_seg + 1) * 8)); CK(dmalloc(ctx, &d_dst, (n_seg + 1) * 8));
+    if (n_records && n_seg) {
+        CK(cudaMemcpyAsync(d_src, seg_src, (n_seg + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_dst, seg_dst, n_seg * 8, cudaMemcpyHostToDevice, ctx->stream));
+        RegroupParams P; P.in = d_recv; P.out = out; P.n = n_records; P.rec_words = rb / 8; P.seg_src = d_src; P.seg_dst = d_dst; P.n_seg = (int)n_seg;
+        k_regroup<<<(unsigned)((n_records + 255) / 256), 256, 0, ctx->stream>>>(P); CKL();
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    *d_out = out;
+    return FKM_OK;
+}
+
+extern "C" int fkm_mg_count(fkm_ctx* ctx, const fkm_config* cfg, const void* d_records, const uint64_t* bin_rec, const uint64_t* bin_kmer,
+                            fkm_result** out, fkm_stats* stats) {
+    if (!ctx || !bin_rec || !bin_kmer) return fkm_set_error(FKM_EINVAL, "null argument");
+    if (stats) { stats->h2d_bytes = 0; stats->n_bases = 0; stats->ms_stage[0] = 0; }
+    PreScattered pre{d_records, bin_rec, bin_kmer};
+    return count_device(ctx, cfg, nullptr, nullptr, 0, out, stats, &pre);
 }
 
 // ------------------------------------------------------------------ results

@@ -1,0 +1,193 @@
+"""Multi-GPU k-mer counting: one process per GPU, reads split by range, bins owned per GPU.
+
+This replaces Spark's shuffle between the map and reduce stages of the reference
+(`reduceByKey(_ ++ _)`, SparkBinKmerCounter.scala:1035,1042, optionally behind the LPT
+`MultiprocessorSchedulingPartitioner`, MultiprocessorSchedulingPartitioner.scala:35-69):
+
+  1. every rank scans its own shard of the reads               (fkm_mg_scan: exact per-bin histogram)
+  2. the B-entry histograms are all-gathered                   (torch.distributed, <= 64 KB per rank)
+  3. bins are assigned to GPUs by LPT over the exact k-mer counts (plan_exchange; same on every rank)
+  4. each rank writes its records owner-major                  (fkm_mg_scatter)
+  5. ONE variable-size all-to-all moves the records            (dist.all_to_all_single over NCCL / NVLink)
+  6. received records are regrouped bin-major                  (fkm_mg_regroup)
+  7. every rank counts the bins it owns                        (fkm_mg_count) — embarrassingly parallel, because a
+     canonical k-mer's signature, hence bin, is strand- and position-independent
+
+plan_exchange() is pure host logic (numpy) and is covered by CPU tests with the gloo backend;
+emulate_ranks() runs all ranks' stages on ONE GPU (no collective) for the -m gpu tests.
+"""
+import numpy as np
+
+
+def assign_owners(bin_kmers, world):
+    """LPT (longest processing time first): bins by decreasing total k-mers, each to the least-loaded GPU.
+    Deterministic (ties by bin id), so every rank computes the same map."""
+    bin_kmers = np.asarray(bin_kmers, dtype=np.uint64)
+    order = np.lexsort((np.arange(bin_kmers.size), -bin_kmers.astype(np.int64)))
+    load = [0] * world
+    owner = np.zeros(bin_kmers.size, dtype=np.int32)
+    for b in order:
+        g = min(range(world), key=lambda r: (load[r], r))
+        owner[b] = g
+        load[g] += int(bin_kmers[b])
+    return owner
+
+
+def plan_exchange(H_rec, H_kmer, rank, world):
+    """H_rec, H_kmer: [world, B] records / k-mers every rank puts into every bin.
+    -> dict with everything rank `rank` needs for steps 4-7."""
+    H_rec = np.asarray(H_rec, dtype=np.uint64)
+    H_kmer = np.asarray(H_kmer, dtype=np.uint64)
+    B = H_rec.shape[1]
+    owner = assign_owners(H_kmer.sum(axis=0), world)
+    # send buffer: bins ordered by (owner, bin)
+    order = np.lexsort((np.arange(B), owner))
+    send_base = np.zeros(B + 1, dtype=np.uint64)
+    mine = H_rec[rank]
+    off = 0
+    for b in order:
+        send_base[b] = off
+        off += int(mine[b])
+    send_base[B] = off
+    send_splits = [int(mine[owner == g].sum()) for g in range(world)]
+    my_bins = np.nonzero(owner == rank)[0]
+    recv_splits = [int(H_rec[s][my_bins].sum()) for s in range(world)]
+    # bin-major layout of the bins this rank owns
+    bin_rec = np.zeros(B, dtype=np.uint64)
+    bin_kmer = np.zeros(B, dtype=np.uint64)
+    bin_rec[my_bins] = H_rec[:, my_bins].sum(axis=0)
+    bin_kmer[my_bins] = H_kmer[:, my_bins].sum(axis=0)
+    dst_base = np.zeros(B + 1, dtype=np.uint64)
+    dst_base[1:] = np.cumsum(bin_rec)
+    # receive buffer is source-major, each source's block holds this rank's bins in bin order
+    seg_src, seg_dst = [0], []
+    filled = {int(b): 0 for b in my_bins}
+    for s in range(world):
+        for b in my_bins:
+            n = int(H_rec[s][b])
+            if n == 0:
+                continue
+            seg_dst.append(int(dst_base[b]) + filled[int(b)])
+            filled[int(b)] += n
+            seg_src.append(seg_src[-1] + n)
+    return dict(owner=owner, send_base=send_base, send_splits=send_splits, recv_splits=recv_splits, bin_rec=bin_rec,
+                bin_kmer=bin_kmer, seg_src=np.asarray(seg_src, dtype=np.uint64), seg_dst=np.asarray(seg_dst, dtype=np.uint64),
+                n_send=int(send_base[B]), n_recv=int(sum(recv_splits)))
+
+
+def exchange_p2p(dist, outs, ins, rank):
+    """Variable-size all-to-all as point-to-point sends (for backends without alltoall, e.g. gloo on CPU).
+    outs[s] receives what rank s sends here; ins[g] goes to rank g."""
+    outs[rank].copy_(ins[rank])
+    reqs = []
+    for peer in range(len(ins)):
+        if peer == rank:
+            continue
+        if ins[peer].numel():
+            reqs.append(dist.isend(ins[peer].contiguous(), peer))
+        if outs[peer].numel():
+            reqs.append(dist.irecv(outs[peer], peer))
+    for r in reqs:
+        r.wait()
+
+
+class ShardedJob:
+    """One rank of a multi-GPU job (torch.distributed must be initialised with the NCCL backend)."""
+
+    def __init__(self, ctx, configuration, dist, rank, world):
+        import torch
+        self.torch, self.ctx, self.cfg, self.dist, self.rank, self.world = torch, ctx, configuration, dist, rank, world
+        from . import api
+        self.rec_bytes = api.record_bytes(configuration)
+        self.last_plan = None
+        self.last_exchange_ms = 0.0
+
+    def count_packed_device(self, d_bases, d_inv, n_positions, want_result=False):
+        rec, kmer = self.ctx.mg_scan(self.cfg, d_bases, d_inv, n_positions)
+        return self._exchange_and_count(rec, kmer, want_result)
+
+    def count_fasta(self, fasta, want_result=False):
+        """This rank's shard as FASTA text in (pinned) host memory."""
+        rec, kmer, n_bases = self.ctx.mg_scan_fasta(self.cfg, fasta)
+        out = self._exchange_and_count(rec, kmer, want_result)
+        st = out[1] if want_result else out
+        st["n_bases"] = n_bases
+        st["h2d_bytes"] = st["h2d_bytes"] + int(getattr(fasta, "size", len(fasta)))
+        return out
+
+    def _exchange_and_count(self, rec, kmer, want_result):
+        torch, dist = self.torch, self.dist
+        B = rec.size
+        mine = torch.from_numpy(np.concatenate([rec, kmer]).astype(np.int64)).cuda()
+        allh = torch.empty(self.world * 2 * B, dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(allh, mine)
+        allh = allh.cpu().numpy().reshape(self.world, 2, B).astype(np.uint64)
+        plan = plan_exchange(allh[:, 0, :], allh[:, 1, :], self.rank, self.world)
+        self.last_plan = plan
+        send = torch.empty((max(plan["n_send"], 1), self.rec_bytes), dtype=torch.uint8, device="cuda")
+        self.ctx.mg_scatter(plan["send_base"], send.data_ptr())
+        recv = torch.empty((max(plan["n_recv"], 1), self.rec_bytes), dtype=torch.uint8, device="cuda")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.all_to_all_single(recv[:plan["n_recv"]], send[:plan["n_send"]], plan["recv_splits"], plan["send_splits"])
+        e1.record()
+        torch.cuda.synchronize()
+        self.last_exchange_ms = e0.elapsed_time(e1)
+        d_records = self.ctx.mg_regroup(self.cfg, recv.data_ptr(), plan["n_recv"], plan["seg_src"], plan["seg_dst"])
+        res, st = self.ctx.mg_count(self.cfg, d_records, plan["bin_rec"], plan["bin_kmer"], want_result=want_result)
+        # job-wide totals
+        tot = torch.tensor([st["n_kmers"], st["n_distinct"], st["total_count"], st["n_superkmers"]], dtype=torch.int64, device="cuda")
+        dist.all_reduce(tot)
+        dig = torch.tensor([st["digest_sum"] - (1 << 64) if st["digest_sum"] >= (1 << 63) else st["digest_sum"],
+                            st["digest_xor"] - (1 << 64) if st["digest_xor"] >= (1 << 63) else st["digest_xor"]],
+                           dtype=torch.int64, device="cuda")
+        alld = torch.empty(self.world * 2, dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(alld, dig)
+        alld = alld.cpu().numpy().reshape(self.world, 2).astype(np.uint64)
+        st["n_kmers_global"], st["n_distinct_global"], st["total_count_global"], st["n_superkmers_global"] = [int(v) for v in tot.tolist()]
+        st["digest_sum_global"] = int(alld[:, 0].sum(dtype=np.uint64))
+        st["digest_xor_global"] = int(np.bitwise_xor.reduce(alld[:, 1]))
+        st["exchange_ms"] = self.last_exchange_ms
+        st["exchange_bytes_sent"] = (plan["n_send"] - plan["send_splits"][self.rank]) * self.rec_bytes
+        if want_result:
+            return res, st
+        return st
+
+
+def emulate_ranks(ctx, configuration, shards, world):
+    """All `world` ranks of a job on ONE GPU, stage by stage, without a collective (test helper).
+    shards: list of (d_bases, d_inv, n_positions).  -> (merged sorted arrays dict, list of per-rank stats)"""
+    import torch
+    from . import api
+    rb = api.record_bytes(configuration)
+    hists = [ctx.mg_scan(configuration, *sh) for sh in shards]       # first pass only for the histograms
+    H_rec = np.stack([h[0] for h in hists])
+    H_kmer = np.stack([h[1] for h in hists])
+    plans = [plan_exchange(H_rec, H_kmer, r, world) for r in range(world)]
+    sends = []
+    for r, sh in enumerate(shards):
+        ctx.mg_scan(configuration, *sh)                                # a job per rank (the scan state lives in the context)
+        send = torch.empty((max(plans[r]["n_send"], 1), rb), dtype=torch.uint8, device="cuda")
+        ctx.mg_scatter(plans[r]["send_base"], send.data_ptr())
+        sends.append(send)
+    merged = {"bin": [], "hi": [], "lo": [], "cnt": []}
+    stats = []
+    for r in range(world):
+        parts = []
+        for s_ in range(world):                                        # what all_to_all_single would deliver to rank r
+            o = sum(plans[s_]["send_splits"][:r])
+            parts.append(sends[s_][o:o + plans[s_]["send_splits"][r]])
+        recv = torch.cat(parts) if parts else torch.empty((0, rb), dtype=torch.uint8, device="cuda")
+        assert recv.shape[0] == plans[r]["n_recv"]
+        assert [p.shape[0] for p in parts] == plans[r]["recv_splits"]
+        recv = recv.contiguous()
+        ctx.mg_scan(configuration, shards[r][0], shards[r][1], 0)      # fresh job on the context (empty scan)
+        d_rec = ctx.mg_regroup(configuration, recv.data_ptr(), plans[r]["n_recv"], plans[r]["seg_src"], plans[r]["seg_dst"])
+        res, st = ctx.mg_count(configuration, d_rec, plans[r]["bin_rec"], plans[r]["bin_kmer"])
+        a = res.arrays()
+        for k_ in merged:
+            merged[k_].append(a[k_].copy())
+        stats.append(st)
+    out = {k_: np.concatenate(v) for k_, v in merged.items()}
+    order = np.lexsort((out["lo"], out["hi"], out["bin"]))
+    return {k_: v[order] for k_, v in out.items()}, stats, plans

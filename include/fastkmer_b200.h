@@ -154,6 +154,33 @@ int  fkm_synth_fasta_host(const fkm_synth* s, uint8_t* out, uint64_t cap, uint64
 int  fkm_synth_packed_device(fkm_ctx* ctx, const fkm_synth* s, void** d_bases, void** d_invalid, uint64_t* n_positions);
 int  fkm_device_free(fkm_ctx* ctx, void* d_ptr);
 
+/* ---- staged entry points: one process per GPU, bins owned per GPU ---------------
+ * The stages of fkm_count_packed_device, cut where Spark's shuffle sits
+ * (reduceByKey, SBKC:1035,1042), so that the host can exchange bins between GPUs:
+ *   fkm_mg_scan     scan this rank's shard; hist_rec / hist_kmer [b] receive the records and
+ *                   k-mers this shard puts into every bin (the role of getBinsEstimateSizes,
+ *                   SBKC:172-288, but exact).  Starts a job on the context.
+ *   fkm_mg_scatter  write the shard's super-k-mer records to d_send (caller-allocated,
+ *                   sum(hist_rec) * fkm_record_bytes bytes) at record offset bin_base[bin]
+ *                   (b+1 values; owner-major so that each peer's bins are contiguous).
+ *   (the host runs one variable-size all-to-all on the send buffers)
+ *   fkm_mg_regroup  received records are source-major; segment i = [seg_src[i], seg_src[i+1])
+ *                   moves to record offset seg_dst[i] of a bin-major buffer (returned in d_out,
+ *                   owned by the context until its next job).
+ *   fkm_mg_count    count the bins this rank owns: bin_rec / bin_kmer [b] = records and k-mers
+ *                   of bin b in d_records (0 for bins owned elsewhere).                        */
+int32_t fkm_record_bytes(const fkm_config* cfg);
+int  fkm_mg_scan(fkm_ctx* ctx, const fkm_config* cfg, const void* d_bases, const void* d_invalid, uint64_t n_positions,
+                 uint64_t* hist_rec, uint64_t* hist_kmer);
+/* fkm_mg_scan on FASTA text in host memory (copied to the GPU and parsed there) */
+int  fkm_mg_scan_fasta(fkm_ctx* ctx, const fkm_config* cfg, const uint8_t* fasta, uint64_t n_bytes,
+                       uint64_t* hist_rec, uint64_t* hist_kmer, uint64_t* n_bases);
+int  fkm_mg_scatter(fkm_ctx* ctx, const uint64_t* bin_base, void* d_send);
+int  fkm_mg_regroup(fkm_ctx* ctx, const fkm_config* cfg, const void* d_recv, uint64_t n_records,
+                    const uint64_t* seg_src, const uint64_t* seg_dst, uint64_t n_seg, void** d_out);
+int  fkm_mg_count(fkm_ctx* ctx, const fkm_config* cfg, const void* d_records, const uint64_t* bin_rec, const uint64_t* bin_kmer,
+                  fkm_result** out, fkm_stats* stats);
+
 /* ---- test hooks (stage-level parity against the oracle) ----------------------- */
 /* bin of every window start (−1 where the k-window holds an invalid position);
  * bins_out has n_positions entries.                                             */

@@ -326,3 +326,35 @@ def test_device_ingest_random_texts(ctx):
         db, di, dn, dbases = ctx.pack_fasta_device(text)
         assert (dn, dbases) == (hn, hbases)
         assert np.array_equal(db, hb) and np.array_equal(di, hi)
+
+
+# ---------------------------------------------------------------- multi-GPU stages, emulated rank by rank on one GPU
+@pytest.mark.parametrize("world,k,m,ht", [(2, 28, 10, 1), (3, 28, 10, 0), (4, 55, 13, 1), (2, 55, 13, 0)])
+def test_multigpu_stages_emulated(ctx, oracle, world, k, m, ht):
+    from fastkmer_b200 import multigpu
+    reads, L = 6000, 150
+    spec = dict(seeds=(31, 32, 33), genome_len=60000, n_reads=reads, read_len=L)
+    fasta = fk.synth_fasta(spec).tobytes()
+    want = oracle.count(fasta, k, m, 3, 2048, ht, threads=8)
+    per = reads // world
+    shards, bufs = [], []
+    for r in range(world):
+        n = per if r < world - 1 else reads - per * (world - 1)
+        sh = ctx.synth_packed_device(dict(spec, n_reads=n, first_read=r * per))
+        shards.append(sh)
+    c = cfg(k, m, 3, 2048, ht)
+    got, stats, plans = multigpu.emulate_ranks(ctx, c, shards, world)
+    assert_same(got, want, "emulated %d ranks" % world)
+    assert sum(s["n_kmers"] for s in stats) == want["stats"]["n_kmers"]
+    dsum = sum(s["digest_sum"] for s in stats) & ((1 << 64) - 1)
+    dxor = 0
+    for s in stats:
+        dxor ^= s["digest_xor"]
+    assert (dsum, dxor) == (want["stats"]["digest_sum"], want["stats"]["digest_xor"])
+    owners = plans[0]["owner"]
+    for r, s in enumerate(stats):                            # every rank counted only bins it owns
+        assert s["n_kmers"] == int(plans[r]["bin_kmer"].sum())
+    assert len(set(owners.tolist())) == world
+    for sh in shards:
+        ctx.free_device(sh[0])
+        ctx.free_device(sh[1])

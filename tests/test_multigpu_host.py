@@ -1,0 +1,113 @@
+"""CPU tests of the multi-GPU host logic (fastkmer_b200/multigpu.py): owner assignment and the exchange plan,
+run as a real 2-rank job over the gloo backend with fake records standing in for the GPU stages."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from fastkmer_b200 import multigpu as mg
+
+
+def test_assign_owners_is_lpt_and_deterministic():
+    kmers = np.array([5, 100, 7, 7, 50, 0, 49, 1], dtype=np.uint64)
+    owner = mg.assign_owners(kmers, 2)
+    assert owner.tolist() == mg.assign_owners(kmers, 2).tolist()
+    load = [int(kmers[owner == g].sum()) for g in range(2)]
+    assert abs(load[0] - load[1]) <= 7 and sum(load) == int(kmers.sum())
+    assert set(mg.assign_owners(kmers, 1).tolist()) == {0}
+    big = np.random.default_rng(0).integers(0, 10**6, 2048).astype(np.uint64)
+    o8 = mg.assign_owners(big, 8)
+    l8 = np.array([big[o8 == g].sum() for g in range(8)], dtype=np.float64)
+    assert l8.max() / l8.mean() < 1.01                       # LPT balances 2048 bins over 8 GPUs to < 1 %
+
+
+def test_plan_is_consistent_across_ranks():
+    rng = np.random.default_rng(3)
+    for G, B in ((2, 64), (3, 17), (8, 2048)):
+        Hr = rng.integers(0, 40, (G, B))
+        Hr[:, rng.integers(0, B, B // 4)] = 0                # empty bins
+        Hk = Hr * rng.integers(1, 30, (G, B))
+        plans = [mg.plan_exchange(Hr, Hk, r, G) for r in range(G)]
+        for r, p in enumerate(plans):
+            assert p["n_send"] == Hr[r].sum() and sum(p["send_splits"]) == p["n_send"]
+            assert p["recv_splits"] == [plans[s]["send_splits"][r] for s in range(G)]
+            assert p["seg_src"][-1] == p["n_recv"] == p["bin_rec"].sum()
+            assert (p["owner"] == plans[0]["owner"]).all()
+        assert sum(int(p["bin_kmer"].sum()) for p in plans) == Hk.sum()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, B, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(100 + rank)
+        rec = rng.integers(0, 30, B).astype(np.int64)
+        rec[rng.integers(0, B, B // 5)] = 0
+        kmer = rec * rng.integers(1, 20, B)
+        mine = torch.from_numpy(np.concatenate([rec, kmer]))
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        allh = torch.stack(gathered).numpy().reshape(world, 2, B)
+        plan = mg.plan_exchange(allh[:, 0, :], allh[:, 1, :], rank, world)
+        # fake "records": rows (source rank, bin, serial), laid out where fkm_mg_scatter would put them
+        send = np.full((plan["n_send"], 3), -1, dtype=np.int64)
+        for b in range(B):
+            o = int(plan["send_base"][b])
+            for i in range(int(rec[b])):
+                send[o + i] = (rank, b, i)
+        assert (send[:, 0] == rank).all()
+        send_t = torch.from_numpy(send)
+        recv_t = torch.empty((plan["n_recv"], 3), dtype=torch.int64)
+        outs = [t.contiguous() for t in recv_t.split(plan["recv_splits"])]
+        ins = list(send_t.split(plan["send_splits"]))
+        mg.exchange_p2p(dist, outs, ins, rank)                # gloo has no alltoall; NCCL runs use all_to_all_single
+        recv = torch.cat(outs).numpy() if outs else np.empty((0, 3), dtype=np.int64)
+        # what fkm_mg_regroup does
+        binned = np.full((plan["n_recv"], 3), -1, dtype=np.int64)
+        for i in range(len(plan["seg_dst"])):
+            a, e = int(plan["seg_src"][i]), int(plan["seg_src"][i + 1])
+            d = int(plan["seg_dst"][i])
+            binned[d:d + (e - a)] = recv[a:e]
+        ok = True
+        off = 0
+        for b in range(B):
+            n = int(plan["bin_rec"][b])
+            blk = binned[off:off + n]
+            if plan["owner"][b] == rank:
+                want = sorted((s, b, i) for s in range(world) for i in range(int(allh[s, 0, b])))
+                ok &= sorted(map(tuple, blk.tolist())) == want
+            else:
+                ok &= n == 0
+            off += n
+        ok &= off == plan["n_recv"]
+        out_q.put((rank, bool(ok), int(plan["bin_kmer"].sum())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_exchange_over_gloo(world):
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 97, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=90) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res)
