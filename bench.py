@@ -282,9 +282,15 @@ def main():
     n_count_launches = max(1, int(st["n_batches"]))
     count_bytes = (L_s / 4) / world
     count_ms = stage[3]
+    traffic = None
+    try:                                              # measured DRAM bytes per record of k_count_ht (one ncu --set full capture)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1c_count_ht_traffic.json")))
+        traffic = tj["dram_bytes_per_record"] * (st["n_superkmers"] / n_count_launches)
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "k_count_ht", "achieved": count_bytes / (count_ms * 1e-3) / 1e9 if count_ms else None,
                 "peak": peak, "unit": "GB/s", "frac": (count_bytes / (count_ms * 1e-3) / 1e9 / peak) if count_ms else None,
-                "traffic": None, "peak_source": peak_src, "launches_per_step": n_count_launches,
+                "traffic": traffic, "algorithmic_bytes_per_launch": count_bytes / n_count_launches, "peak_source": peak_src, "launches_per_step": n_count_launches,
                 "avg_launch_ms": count_ms / n_count_launches,
                 "pipeline": {"bytes_alg": bytes_alg, "achieved": bytes_alg / (ms_step * 1e-3) / 1e9 / world,
                              "frac": bytes_alg / (ms_step * 1e-3) / 1e9 / world / peak}}
