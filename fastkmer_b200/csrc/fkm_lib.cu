@@ -89,6 +89,7 @@ struct fkm_ctx {
     double table_budget_bytes = 4.0 * (1ull << 30);
     double sort_budget_keys = 256.0 * (1 << 20);
     double load_factor = 0.6;
+    double ingest_chunk_bytes = 256.0 * (1 << 20);   // FASTA text is streamed to the GPU in chunks of about this size
     double debug_event_scale = 1.0;   // test hook: scales the run-event list capacity (forces the second-scan fallback)
     double debug_rho_scale = 1.0;     // test hook: scales the learnt distinct/k-mer ratio (forces the overflow fallback)
     double l2_table_bytes = 1024.0 * (1 << 20); // tables of one asynchronous batch; 0 disables the asynchronous phase (measured: 0.25-16 GB all within 8%, profiles/r1_table_sweep.txt)
@@ -98,6 +99,8 @@ struct fkm_ctx {
     struct ScanState* mg_scan = nullptr;   // state between fkm_mg_scan and fkm_mg_scatter
     cudaEvent_t ev[10];
     cudaEvent_t evs[24];              // sampled per-kernel timings inside the asynchronous phase
+    cudaStream_t copy_stream = nullptr;   // H2D of FASTA chunks, overlapped with parsing / scanning on `stream`
+    cudaEvent_t copied[2];
 };
 
 // job-lifetime device memory (see Arena); "free" is a no-op, the arena is reset by the next job
@@ -138,6 +141,8 @@ extern "C" int fkm_ctx_create(int device, void* stream, fkm_ctx** out) {
     c->n_sm = p.multiProcessorCount; c->smem_optin = p.sharedMemPerBlockOptin;
     for (auto& ev : c->ev) CK(cudaEventCreate(&ev));
     for (auto& ev : c->evs) CK(cudaEventCreate(&ev));
+    CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (auto& ev : c->copied) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     *out = c;
     return FKM_OK;
 }
@@ -146,6 +151,8 @@ extern "C" void fkm_ctx_destroy(fkm_ctx* c) {
     cudaSetDevice(c->device);
     for (auto& ev : c->ev) cudaEventDestroy(ev);
     for (auto& ev : c->evs) cudaEventDestroy(ev);
+    for (auto& ev : c->copied) cudaEventDestroy(ev);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaStreamSynchronize(c->stream);
     c->arena.destroy();
     free_scan_state(c->mg_scan);
@@ -161,6 +168,7 @@ extern "C" int fkm_ctx_set(fkm_ctx* c, const char* name, double v) {
     else if (!strcmp(name, "l2_table_bytes")) c->l2_table_bytes = v;
     else if (!strcmp(name, "debug_rho_scale")) c->debug_rho_scale = v;
     else if (!strcmp(name, "debug_event_scale")) c->debug_event_scale = v;
+    else if (!strcmp(name, "ingest_chunk_bytes")) c->ingest_chunk_bytes = v;
     else return fkm_set_error(FKM_EINVAL, "unknown knob %s", name);
     return FKM_OK;
 }
@@ -271,50 +279,79 @@ static inline uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a
 
 // ------------------------------------------------------------------ the pipeline
 // What the scan stage leaves behind for the scatter stage (kept in the context between the
-// staged multi-GPU entry points; a local inside the single-GPU pipeline).
+// staged multi-GPU entry points; a local inside the single-GPU pipeline).  The input may be
+// scanned in several chunks (FASTA text streamed over PCIe, split at record boundaries):
+// every chunk has its own packed arrays and run-event list, the bin histogram is shared.
+struct ChunkScan {
+    const void* d_bases = nullptr; const void* d_inv = nullptr; uint64_t n_pos = 0;
+    ulonglong2* d_events = nullptr; uint64_t ev_cap = 0;
+    unsigned long long* d_count = nullptr;      // [0] events written
+    int* d_ovf = nullptr;
+    unsigned long long n_events = 0; int ev_ovf = 0;
+};
 struct ScanState {
     fkm_config cfg; int32_t B = 0;
-    const void* d_bases = nullptr; const void* d_inv = nullptr; uint64_t n_pos = 0;
-    unsigned long long *d_hist_rec = nullptr, *d_hist_kmer = nullptr, *d_small = nullptr;
-    int* d_ovf = nullptr; ulonglong2* d_events = nullptr;
-    unsigned long long n_events = 0; int ev_ovf = 0;
+    unsigned long long *d_hist_rec = nullptr, *d_hist_kmer = nullptr;
+    std::vector<ChunkScan> chunks;
     std::vector<unsigned long long> h_rec, h_kmer;
+    uint64_t n_pos_total = 0;
     bool valid = false;
 };
 
 static void free_scan_state(ScanState* p) { delete p; }
 
-// stage 1: one scan of the input: exact bin histogram (records, k-mers) + the list of run events
-static int stage_scan(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const void* d_bases, const void* d_inv, uint64_t n_pos,
-                      ScanState* S, fkm_stats* st) {
-    cudaStream_t s = ctx->stream;
+static int scan_begin(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, ScanState* S) {
     const size_t bB = (size_t)B * 8;
-    S->cfg = *cfg; S->B = B; S->d_bases = d_bases; S->d_inv = d_inv; S->n_pos = n_pos;
+    S->cfg = *cfg; S->B = B; S->chunks.clear(); S->n_pos_total = 0; S->valid = false;
     S->h_rec.assign((size_t)B, 0); S->h_kmer.assign((size_t)B, 0);
     CK(dmalloc(ctx, &S->d_hist_rec, bB)); CK(dmalloc(ctx, &S->d_hist_kmer, bB));
-    CK(dmalloc(ctx, &S->d_small, 64)); CK(dmalloc(ctx, &S->d_ovf, 8));
-    CK(cudaMemsetAsync(S->d_hist_rec, 0, bB, s)); CK(cudaMemsetAsync(S->d_hist_kmer, 0, bB, s));
-    CK(cudaMemsetAsync(S->d_small, 0, 64, s)); CK(cudaMemsetAsync(S->d_ovf, 0, 8, s));
+    CK(cudaMemsetAsync(S->d_hist_rec, 0, bB, ctx->stream)); CK(cudaMemsetAsync(S->d_hist_kmer, 0, bB, ctx->stream));
+    return FKM_OK;
+}
+// one scan launch (asynchronous): bin histogram += this chunk, run events of this chunk
+static int scan_chunk(fkm_ctx* ctx, ScanState* S, const void* d_bases, const void* d_inv, uint64_t n_pos) {
+    cudaStream_t s = ctx->stream;
+    const fkm_config* cfg = &S->cfg;
+    ChunkScan C;
+    C.d_bases = d_bases; C.d_inv = d_inv; C.n_pos = n_pos;
     const int w_mm = cfg->k - cfg->m + 1;
     // runs average ~(w+1)/2 windows on random sequence; leave generous head-room, an overflow falls back to a second scan
-    const uint64_t ev_cap = (uint64_t)(((double)n_pos * std::min(0.5, 2.4 / (double)(w_mm + 1)) + (double)(1u << 20)) * ctx->debug_event_scale) + 64;
-    CK(dmalloc(ctx, &S->d_events, (size_t)ev_cap * 16));
-    CK(cudaEventRecord(ctx->ev[0], s));
-    {
-        ScanSetup Q; int rc = scan_setup<0>(ctx, cfg, B, d_bases, d_inv, n_pos, &Q); if (rc) return rc;
-        Q.P.hist_rec = S->d_hist_rec; Q.P.hist_kmer = S->d_hist_kmer;
-        Q.P.events = S->d_events; Q.P.ev_cap = ev_cap; Q.P.ev_count = S->d_small; Q.P.ev_overflow = S->d_ovf;
-        if (n_pos) { Q.fn<<<Q.grid, kScanThreads, Q.smem, s>>>(Q.P); CKL(); }
-    }
-    CK(cudaEventRecord(ctx->ev[1], s));
+    C.ev_cap = (uint64_t)(((double)n_pos * std::min(0.5, 2.4 / (double)(w_mm + 1)) + (double)(1u << 20)) * ctx->debug_event_scale) + 64;
+    CK(dmalloc(ctx, &C.d_events, (size_t)C.ev_cap * 16));
+    CK(dmalloc(ctx, &C.d_count, 16)); CK(dmalloc(ctx, &C.d_ovf, 8));
+    CK(cudaMemsetAsync(C.d_count, 0, 16, s)); CK(cudaMemsetAsync(C.d_ovf, 0, 8, s));
+    ScanSetup Q; int rc = scan_setup<0>(ctx, cfg, S->B, d_bases, d_inv, n_pos, &Q); if (rc) return rc;
+    Q.P.hist_rec = S->d_hist_rec; Q.P.hist_kmer = S->d_hist_kmer;
+    Q.P.events = C.d_events; Q.P.ev_cap = C.ev_cap; Q.P.ev_count = C.d_count; Q.P.ev_overflow = C.d_ovf;
+    if (n_pos) { Q.fn<<<Q.grid, kScanThreads, Q.smem, s>>>(Q.P); CKL(); }
+    S->chunks.push_back(C);
+    S->n_pos_total += n_pos;
+    return FKM_OK;
+}
+static int scan_end(fkm_ctx* ctx, ScanState* S, fkm_stats* st) {
+    cudaStream_t s = ctx->stream;
+    const size_t bB = (size_t)S->B * 8;
     CK(cudaMemcpyAsync(S->h_rec.data(), S->d_hist_rec, bB, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(S->h_kmer.data(), S->d_hist_kmer, bB, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(&S->n_events, S->d_small, 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(&S->ev_ovf, S->d_ovf, 4, cudaMemcpyDeviceToHost, s));
+    for (ChunkScan& C : S->chunks) {
+        CK(cudaMemcpyAsync(&C.n_events, C.d_count, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(&C.ev_ovf, C.d_ovf, 4, cudaMemcpyDeviceToHost, s));
+    }
     CK(cudaStreamSynchronize(s));
-    st->d2h_bytes += 2 * bB + 12;
-    float ms; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); st->ms_stage[1] = ms;
+    st->d2h_bytes += 2 * bB + 12 * S->chunks.size();
     S->valid = true;
+    return FKM_OK;
+}
+
+// stage 1 on input that is already resident: one chunk
+static int stage_scan(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const void* d_bases, const void* d_inv, uint64_t n_pos,
+                      ScanState* S, fkm_stats* st) {
+    int rc = scan_begin(ctx, cfg, B, S); if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    rc = scan_chunk(ctx, S, d_bases, d_inv, n_pos); if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    rc = scan_end(ctx, S, st); if (rc) return rc;
+    float ms; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); st->ms_stage[1] = ms;
     return FKM_OK;
 }
 
@@ -326,22 +363,24 @@ static int stage_scatter(fkm_ctx* ctx, ScanState* S, const unsigned long long* d
     const fkm_config* cfg = &S->cfg;
     const bool wide = cfg->k > 32;
     CK(cudaEventRecord(ctx->ev[1], s));
-    if (!S->ev_ovf) {
-        ScatterParams Q;
-        Q.events = S->d_events; Q.n_events = S->n_events; Q.bases = (const uint64_t*)S->d_bases; Q.n_words = (S->n_pos + 31) / 32;
-        Q.B = (uint32_t)S->B; Q.cap = wide ? (125 - cfg->k) : (61 - cfg->k); Q.k = cfg->k;
-        Q.bin_base = d_bin_base; Q.cursor = d_cursor; Q.records = d_records;
-        if (S->n_events) {
-            const unsigned grid = (unsigned)((S->n_events + 255) / 256);
-            if (wide) k_scatter_events<true><<<grid, 256, 0, s>>>(Q); else k_scatter_events<false><<<grid, 256, 0, s>>>(Q);
-            CKL();
+    for (ChunkScan& C : S->chunks) {
+        if (!C.ev_ovf) {
+            ScatterParams Q;
+            Q.events = C.d_events; Q.n_events = C.n_events; Q.bases = (const uint64_t*)C.d_bases; Q.n_words = (C.n_pos + 31) / 32;
+            Q.B = (uint32_t)S->B; Q.cap = wide ? (125 - cfg->k) : (61 - cfg->k); Q.k = cfg->k;
+            Q.bin_base = d_bin_base; Q.cursor = d_cursor; Q.records = d_records;
+            if (C.n_events) {
+                const unsigned grid = (unsigned)((C.n_events + 255) / 256);
+                if (wide) k_scatter_events<true><<<grid, 256, 0, s>>>(Q); else k_scatter_events<false><<<grid, 256, 0, s>>>(Q);
+                CKL();
+            }
+        } else {
+            // the event list was too small for this chunk: scan it again, writing the records directly
+            st->n_fallbacks++;
+            ScanSetup Q; int rc = scan_setup<1>(ctx, cfg, S->B, C.d_bases, C.d_inv, C.n_pos, &Q); if (rc) return rc;
+            Q.P.bin_base = d_bin_base; Q.P.cursor = d_cursor; Q.P.records = d_records;
+            if (n_rec && C.n_pos) { Q.fn<<<Q.grid, kScanThreads, Q.smem, s>>>(Q.P); CKL(); }
         }
-    } else {
-        // the event list was too small for this input: scan again, writing the records directly
-        st->n_fallbacks++;
-        ScanSetup Q; int rc = scan_setup<1>(ctx, cfg, S->B, S->d_bases, S->d_inv, S->n_pos, &Q); if (rc) return rc;
-        Q.P.bin_base = d_bin_base; Q.P.cursor = d_cursor; Q.P.records = d_records;
-        if (n_rec) { Q.fn<<<Q.grid, kScanThreads, Q.smem, s>>>(Q.P); CKL(); }
     }
     CK(cudaEventRecord(ctx->ev[2], s));
     return FKM_OK;
@@ -352,7 +391,7 @@ struct PreScattered { const void* d_records; const uint64_t* bin_rec; const uint
 
 template <bool WIDE>
 static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const void* d_bases, const void* d_inv,
-                        uint64_t n_pos, fkm_result* res, fkm_stats* st, const PreScattered* pre) {
+                        uint64_t n_pos, fkm_result* res, fkm_stats* st, const PreScattered* pre, ScanState* scanned) {
     typedef typename Traits<WIDE>::Key Key;
     typedef typename Traits<WIDE>::Slot Slot;
     cudaStream_t s = ctx->stream;
@@ -388,10 +427,12 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
     CKC(cudaMemsetAsync(d_out_base, 0, bB + 8, s)); CKC(cudaMemsetAsync(d_small, 0, 64, s));
 
     std::vector<unsigned long long> h_rec, h_kmer, h_base((size_t)B + 1);
-    ScanState scan;
+    ScanState local_scan;
+    ScanState& scan = scanned ? *scanned : local_scan;
     if (!pre) {
-        rc = stage_scan(ctx, cfg, B, d_bases, d_inv, n_pos, &scan, st); if (rc) return rc;
-        h_rec.swap(scan.h_rec); h_kmer.swap(scan.h_kmer);
+        if (!scanned) { rc = stage_scan(ctx, cfg, B, d_bases, d_inv, n_pos, &scan, st); if (rc) return rc; }
+        else CKC(cudaEventRecord(ctx->ev[0], s));
+        h_rec = scan.h_rec; h_kmer = scan.h_kmer;
         tr.mark("histogram done");
     } else {
         h_rec.assign(pre->bin_rec, pre->bin_rec + B); h_kmer.assign(pre->bin_kmer, pre->bin_kmer + B);
@@ -734,7 +775,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
 }
 
 static int count_device(fkm_ctx* ctx, const fkm_config* cfg, const void* d_bases, const void* d_inv, uint64_t n_pos,
-                        fkm_result** out, fkm_stats* stats, const PreScattered* pre = nullptr) {
+                        fkm_result** out, fkm_stats* stats, const PreScattered* pre = nullptr, ScanState* scanned = nullptr) {
     int32_t B = 0; int rc = validate(cfg, &B); if (rc) return rc;
     if (!ctx) return fkm_set_error(FKM_EINVAL, "ctx is NULL");
     CK(cudaSetDevice(ctx->device));
@@ -745,8 +786,8 @@ static int count_device(fkm_ctx* ctx, const fkm_config* cfg, const void* d_bases
     st->n_positions = n_pos;
     auto t0 = std::chrono::steady_clock::now();
     fkm_result* res = new fkm_result();
-    rc = (cfg->k > 32) ? run_pipeline<true>(ctx, cfg, B, d_bases, d_inv, n_pos, res, st, pre)
-                       : run_pipeline<false>(ctx, cfg, B, d_bases, d_inv, n_pos, res, st, pre);
+    rc = (cfg->k > 32) ? run_pipeline<true>(ctx, cfg, B, d_bases, d_inv, n_pos, res, st, pre, scanned)
+                       : run_pipeline<false>(ctx, cfg, B, d_bases, d_inv, n_pos, res, st, pre, scanned);
     st->gpu_launches = ctx->job_launches;       // everything since job_begin (ingest included)
     st->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (rc) { fkm_result_free(res); return rc; }
@@ -831,19 +872,84 @@ static int upload_and_ingest(fkm_ctx* ctx, const uint8_t* fasta, uint64_t n_byte
     return rc;
 }
 
+// Cut points of a FASTA text at record boundaries ('>' at the start of a line), about `target` bytes apart.
+// A record longer than `target` (a long genome) simply makes a longer chunk.
+static void split_fasta(const uint8_t* t, uint64_t n, uint64_t target, std::vector<uint64_t>& cuts) {
+    cuts.clear(); cuts.push_back(0);
+    uint64_t pos = target;
+    while (pos < n) {
+        const uint8_t* p = t + pos;
+        uint64_t cut = n;
+        while (p < t + n) {
+            p = (const uint8_t*)memchr(p, '>', (size_t)(t + n - p));
+            if (!p) break;
+            if (p > t && p[-1] == '\n') { cut = (uint64_t)(p - t); break; }
+            p++;
+        }
+        if (cut >= n) break;
+        cuts.push_back(cut);
+        pos = cut + target;
+    }
+    cuts.push_back(n);
+}
+
+// Front end for FASTA text in host memory: the text is streamed to the GPU chunk by chunk on a copy
+// stream while earlier chunks are parsed (fkm_ingest.cuh) and scanned (k_scan) on the compute stream,
+// so the PCIe copy — the longest single step of an end-to-end job — hides the parse and the scan.
+static int front_end_fasta(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const uint8_t* fasta, uint64_t n_bytes,
+                           ScanState* S, uint64_t* n_bases_total) {
+    std::vector<uint64_t> cuts;
+    split_fasta(fasta, n_bytes, (uint64_t)std::max(4096.0, ctx->ingest_chunk_bytes), cuts);
+    const size_t nc = cuts.size() - 1;
+    uint64_t max_chunk = 16;
+    for (size_t c = 0; c < nc; c++) max_chunk = std::max(max_chunk, cuts[c + 1] - cuts[c]);
+    int rc = scan_begin(ctx, cfg, B, S); if (rc) return rc;
+    uint8_t* d_text[2] = {nullptr, nullptr};
+    CK(dmalloc(ctx, (void**)&d_text[0], max_chunk));
+    if (nc > 1) CK(dmalloc(ctx, (void**)&d_text[1], max_chunk));
+    *n_bases_total = 0;
+    auto enqueue_copy = [&](size_t c) -> int {
+        CK(cudaMemcpyAsync(d_text[c & 1], fasta + cuts[c], cuts[c + 1] - cuts[c], cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->copied[c & 1], ctx->copy_stream));
+        return FKM_OK;
+    };
+    rc = enqueue_copy(0); if (rc) return rc;
+    for (size_t c = 0; c < nc; c++) {
+        // chunk c+1 goes on the wire before the host blocks on chunk c; its buffer was released when
+        // the ingest of chunk c-1 completed (ingest_device synchronises)
+        if (c + 1 < nc) { rc = enqueue_copy(c + 1); if (rc) return rc; }
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->copied[c & 1], 0));
+        const uint64_t len = cuts[c + 1] - cuts[c];
+        void *d_b = nullptr, *d_i = nullptr;
+        const uint64_t cap_words = ingest_cap_words(len);
+        CK(dmalloc(ctx, &d_b, cap_words * 8)); CK(dmalloc(ctx, &d_i, cap_words * 4));
+        const Arena::Mark mk = ctx->arena.mark();
+        uint64_t n_pos = 0, n_bases = 0;
+        rc = ingest_device(ctx, d_text[c & 1], len, d_b, d_i, &n_pos, &n_bases);
+        ctx->arena.release(mk);
+        if (rc) return rc;
+        *n_bases_total += n_bases;
+        rc = scan_chunk(ctx, S, d_b, d_i, n_pos); if (rc) return rc;
+    }
+    return FKM_OK;
+}
+
 extern "C" int fkm_count_fasta(fkm_ctx* ctx, const fkm_config* cfg, const uint8_t* fasta, uint64_t n_bytes,
                                fkm_result** out, fkm_stats* stats) {
     if (!ctx) return fkm_set_error(FKM_EINVAL, "ctx is NULL");
     int32_t B = 0; int rc = validate(cfg, &B); if (rc) return rc;
     rc = job_begin(ctx); if (rc) return rc;
     auto t0 = std::chrono::steady_clock::now();
-    void *d_b = nullptr, *d_i = nullptr; uint64_t n_pos = 0, n_bases = 0;
-    rc = upload_and_ingest(ctx, fasta, n_bytes, &d_b, &d_i, &n_pos, &n_bases); if (rc) return rc;
     fkm_stats local; fkm_stats* st = stats ? stats : &local;
+    memset(st, 0, sizeof *st);
+    ScanState S; uint64_t n_bases = 0;
+    rc = front_end_fasta(ctx, cfg, B, fasta, n_bytes, &S, &n_bases); if (rc) return rc;
+    fkm_stats tmp; memset(&tmp, 0, sizeof tmp);
+    rc = scan_end(ctx, &S, &tmp); if (rc) return rc;
     const double ms_in = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    st->h2d_bytes = n_bytes + 32; st->n_bases = n_bases; st->ms_stage[0] = ms_in;
-    rc = count_device(ctx, cfg, d_b, d_i, n_pos, out, st);
-    st->d2h_bytes += 16; st->ms_total += ms_in;
+    st->h2d_bytes = n_bytes + 32 * S.chunks.size(); st->n_bases = n_bases; st->ms_stage[0] = ms_in;
+    rc = count_device(ctx, cfg, nullptr, nullptr, S.n_pos_total, out, st, nullptr, &S);
+    st->d2h_bytes += tmp.d2h_bytes + 16 * S.chunks.size(); st->ms_total += ms_in;
     return rc;
 }
 
@@ -890,8 +996,8 @@ extern "C" int fkm_execute_job(fkm_ctx* ctx, const fkm_config* cfg, fkm_stats* s
 }
 
 // ------------------------------------------------------------------ staged entry points (multi-GPU)
-static int upload_and_ingest(fkm_ctx* ctx, const uint8_t* fasta, uint64_t n_bytes, void** d_bases, void** d_inv,
-                             uint64_t* n_pos, uint64_t* n_bases);
+static int front_end_fasta(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const uint8_t* fasta, uint64_t n_bytes,
+                           ScanState* S, uint64_t* n_bases_total);
 extern "C" int32_t fkm_record_bytes(const fkm_config* cfg) { return (cfg && cfg->k > 32) ? 32 : 16; }
 
 extern "C" int fkm_mg_scan(fkm_ctx* ctx, const fkm_config* cfg, const void* d_bases, const void* d_inv, uint64_t n_pos,
@@ -913,13 +1019,12 @@ extern "C" int fkm_mg_scan_fasta(fkm_ctx* ctx, const fkm_config* cfg, const uint
     if (!ctx || !hist_rec || !hist_kmer) return fkm_set_error(FKM_EINVAL, "null argument");
     int32_t B = 0; int rc = validate(cfg, &B); if (rc) return rc;
     rc = job_begin(ctx); if (rc) return rc;
-    void *d_b = nullptr, *d_i = nullptr; uint64_t n_pos = 0, nb = 0;
-    rc = upload_and_ingest(ctx, fasta, n_bytes, &d_b, &d_i, &n_pos, &nb); if (rc) return rc;
-    if (n_bases) *n_bases = nb;
     if (!ctx->mg_scan) ctx->mg_scan = new ScanState();
-    ctx->mg_scan->valid = false;
+    uint64_t nb = 0;
+    rc = front_end_fasta(ctx, cfg, B, fasta, n_bytes, ctx->mg_scan, &nb); if (rc) return rc;
+    if (n_bases) *n_bases = nb;
     fkm_stats st; memset(&st, 0, sizeof st);
-    rc = stage_scan(ctx, cfg, B, d_b, d_i, n_pos, ctx->mg_scan, &st); if (rc) return rc;
+    rc = scan_end(ctx, ctx->mg_scan, &st); if (rc) return rc;
     for (int b = 0; b < B; b++) { hist_rec[b] = ctx->mg_scan->h_rec[(size_t)b]; hist_kmer[b] = ctx->mg_scan->h_kmer[(size_t)b]; }
     return FKM_OK;
 }

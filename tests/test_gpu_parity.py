@@ -328,6 +328,25 @@ def test_device_ingest_random_texts(ctx):
         assert np.array_equal(db, hb) and np.array_equal(di, hi)
 
 
+def test_streamed_fasta_chunks(oracle):
+    """FASTA text is copied and parsed in chunks cut at record boundaries: any chunk size gives the same counts."""
+    rng = random.Random(123)
+    fasta = _rand_fasta(rng, 600, 0, 400, width=60).encode()
+    long_rec = (">one long record\n" + "\n".join("".join(rng.choice("ACGT") for _ in range(70)) for _ in range(300)) + "\n").encode()
+    c2 = fk.Context(0)
+    try:
+        for text in (fasta, b"junk before\n" + fasta, long_rec, fasta + long_rec + fasta):
+            for ht, k, m in ((1, 28, 10), (0, 31, 11), (1, 55, 13)):
+                want = oracle.count(text, k, m, 3, 2048, ht, threads=8)
+                for chunk in (4096, 20000, 1 << 30):
+                    c2.set("ingest_chunk_bytes", chunk)
+                    res, st = c2.count_fasta(cfg(k, m, 3, 2048, ht), text)
+                    assert_same(res.sorted_arrays(), want, "chunk %d" % chunk)
+                    assert st["n_bases"] == want["stats"]["n_bases"] and st["n_kmers"] == want["stats"]["n_kmers"]
+    finally:
+        c2.close()
+
+
 # ---------------------------------------------------------------- multi-GPU stages, emulated rank by rank on one GPU
 @pytest.mark.parametrize("world,k,m,ht", [(2, 28, 10, 1), (3, 28, 10, 0), (4, 55, 13, 1), (2, 55, 13, 0)])
 def test_multigpu_stages_emulated(ctx, oracle, world, k, m, ht):
