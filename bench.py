@@ -26,16 +26,74 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-K, M, X, B = 28, 10, 3, 2048
-READ_LEN = 150
-COVERAGE = 30
-SEEDS = (2001, 2002, 2003)
-FULL_READS = 50_000_000
+# BASELINE.json configs (SURVEY §8(d) generator parameters).  Config 2 is the default: the one the metric is quoted on.
+CONFIGS = {
+    1: dict(k=28, m=10, x=3, B=2048, ht=0, kind="reads", reads=1_000_000, L=100, cov=20, seeds=(1001, 1002, 1003), seqtype=0,
+            name="BASELINE configs[0]: k=28 m=10 x=3 B=2048 useHT=0, 1M synthetic 100 bp reads"),
+    2: dict(k=28, m=10, x=3, B=2048, ht=1, kind="reads", reads=50_000_000, L=150, cov=30, seeds=(2001, 2002, 2003), seqtype=0,
+            name="BASELINE configs[1]: k=28 m=10 x=3 B=2048 useHT=1, 50M synthetic 150 bp reads"),
+    3: dict(k=31, m=11, x=3, B=4096, ht=0, kind="long", n_bases=1_200_000_000, seeds=(3001, 3002, 3003), seqtype=1,
+            name="BASELINE configs[2]: long sequence, synthetic 1.2 Gbp genome (5% repeats, 0.5% N runs), k=31 m=11 B=4096 useHT=0"),
+    4: dict(k=55, m=13, x=3, B=2048, ht=0, kind="reads", reads=50_000_000, L=150, cov=30, seeds=(4001, 4002, 4003), seqtype=0,
+            name="BASELINE configs[3] shape at 50M reads per GPU (the 1B-read set is 125M per GPU on 8): k=55 m=13 x=3 B=2048, 128-bit k-mers, useHT=0"),
+}
 
 
-def workload(reads_per_gpu, n_gpus):
-    total = reads_per_gpu * n_gpus
-    return dict(seeds=SEEDS, genome_len=max(READ_LEN * 2, total * READ_LEN // COVERAGE), n_reads=reads_per_gpu, read_len=READ_LEN)
+class Workload:
+    def __init__(self, cid, reads_override=None, ht_override=None):
+        self.c = dict(CONFIGS[cid])
+        if reads_override and self.c["kind"] == "reads":
+            self.c["reads"] = reads_override
+        if ht_override is not None:
+            self.c["ht"] = ht_override
+        self.kind = self.c["kind"]
+
+    def tc(self, fk):
+        c = self.c
+        return fk.TestConfiguration("", "", c["k"], c["m"], c["x"], max_b=c["B"], useHT=bool(c["ht"]), write=False, sequenceType=c["seqtype"])
+
+    @property
+    def scaling(self):
+        return "weak" if self.kind == "reads" else "strong"
+
+    def n_bases_total(self, world):
+        return self.c["reads"] * self.c["L"] * world if self.kind == "reads" else self.c["n_bases"]
+
+    def spec(self, rank, world):
+        c = self.c
+        if self.kind == "reads":
+            total = c["reads"] * world
+            return dict(seeds=c["seeds"], genome_len=max(c["L"] * 2, total * c["L"] // c["cov"]), n_reads=c["reads"], read_len=c["L"],
+                        first_read=rank * c["reads"])
+        per = c["n_bases"] // world                          # byte-range shard with a (k-1)-base halo
+        first = rank * per
+        n = (per if rank < world - 1 else c["n_bases"] - first) + (c["k"] - 1 if rank < world - 1 else 0)
+        return dict(seeds=c["seeds"], first_pos=first, n_bases=n)
+
+    def device_input(self, ctx, rank, world):
+        sp = self.spec(rank, world)
+        return ctx.synth_packed_device(sp) if self.kind == "reads" else ctx.synth_long_packed_device(sp)
+
+    def host_fasta(self, api, fk, rank, world):
+        sp = self.spec(rank, world)
+        n = api.C.c_uint64()
+        if self.kind == "reads":
+            s = api._synth(sp)
+            api._check(api.load_library().fkm_synth_fasta_host(api.C.byref(s), None, 0, api.C.byref(n)))
+            return fk.synth_fasta(sp, out=api.host_alloc(n.value))
+        s = api._synth_long(sp)
+        api._check(api.load_library().fkm_synth_long_fasta_host(api.C.byref(s), None, 0, api.C.byref(n)))
+        return fk.synth_long_fasta(sp, out=api.host_alloc(n.value))
+
+    def cpu_sample(self, fk):
+        """bounded sample of the same workload for the CPU oracle -> (fasta uint8 array, description)"""
+        c = self.c
+        if self.kind == "reads":
+            reads = min(c["reads"], 500_000)
+            sp = dict(seeds=c["seeds"], genome_len=reads * c["L"] // c["cov"], n_reads=reads, read_len=c["L"])
+            return fk.synth_fasta(sp), "%d reads x %d bp of the same generator" % (reads, c["L"])
+        n = min(c["n_bases"], 40_000_000)
+        return fk.synth_long_fasta(dict(seeds=c["seeds"], n_bases=n)), "first %d bp of the same synthetic genome" % n
 
 
 def measured_peaks():
@@ -87,49 +145,41 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_sample_spec(n_gpus):
-    # bounded sample of the same workload: 1/100 of one GPU's reads, same genome coverage model
-    reads = 500_000
-    return dict(seeds=SEEDS, genome_len=reads * READ_LEN // COVERAGE, n_reads=reads, read_len=READ_LEN)
-
-
-def run_cpu_oracle(threads, spec):
-    """Times the CPU oracle (port of the reference algorithm) on `spec`.  -> dict"""
+def run_cpu_oracle(threads, wl):
+    """Times the CPU oracle (port of the reference algorithm) on a bounded sample of the workload.  -> dict"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
     import fastkmer_b200 as fk
     oracle = oracle_lib.load()
-    fasta = fk.synth_fasta(spec)                      # host generator of the product lib: data only, no counting
+    fasta, desc = wl.cpu_sample(fk)                   # host generator of the product lib: data only, no counting
+    c = wl.c
     t0 = time.perf_counter()
-    res = oracle.count(fasta, K, M, X, B, 1, threads=threads, sorted_=False)
+    res = oracle.count(fasta, c["k"], c["m"], c["x"], c["B"], c["ht"], threads=threads, sorted_=False)
     dt = time.perf_counter() - t0
     st = res["stats"]
     return {"seconds": dt, "n_bases": st["n_bases"], "n_kmers": st["n_kmers"], "n_distinct": st["n_distinct"],
-            "n_superkmers_ref": st["n_superkmers"], "superkmer_bases_ref": st["superkmer_bases"]}
+            "n_superkmers_ref": st["n_superkmers"], "superkmer_bases_ref": st["superkmer_bases"], "desc": desc}
 
 
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    wl = Workload(args.config, args.reads, args.ht)
     threads = os.cpu_count() or 1
-    spec = cpu_sample_spec(args.gpus)
-    for _ in range(args.warmup if args.warmup < 2 else 1):     # the CPU path has no warm-up effects worth more than one pass
-        run_cpu_oracle(threads, spec)
+    run_cpu_oracle(threads, wl)                       # one warm-up pass (page cache, library load)
     t = []
     last = None
     for _ in range(args.steps):
-        last = run_cpu_oracle(threads, spec)
+        last = run_cpu_oracle(threads, wl)
         t.append(last["seconds"])
     sec = sum(t) / len(t)
     value = last["n_bases"] / sec
-    sample = "%d reads x %d bp (1/%d of one GPU's reads), oracle port of the reference algorithm, useHT=1" % (
-        spec["n_reads"], READ_LEN, FULL_READS // spec["n_reads"])
+    sample = last["desc"] + ", oracle port of the reference algorithm (Spark cannot run here)"
     line = {"impl": "reference", "metric": "bases_per_sec", "value": value, "unit": "bases/s", "kmers_per_sec": last["n_kmers"] / sec,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "k=28 m=10 x=3 B=2048 useHT=1, synthetic 150 bp reads (BASELINE configs[1] shape), bounded sample",
-                       "sample_reads": spec["n_reads"]},
+            "scaling": wl.scaling, "vs_baseline": None, "dtype": "u64" if wl.c["k"] <= 32 else "u128", "data": "synthetic",
+            "config": {"workload": wl.c["name"] + " — bounded sample: " + last["desc"]},
             "cpu_baseline": {"value": value, "unit": "bases/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -141,7 +191,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--reads", type=int, default=FULL_READS, help="reads per GPU (default: the full configs[1] size)")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json config (1-based); default 2 = configs[1]")
+    ap.add_argument("--reads", type=int, default=None, help="reads per GPU (override, read configs only)")
+    ap.add_argument("--ht", type=int, default=None, help="override useHT")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--set", action="append", default=[], help="context knob name=value (tuning experiments)")
@@ -175,9 +227,8 @@ def main():
     for kv in args.set:
         name, val = kv.split("=")
         ctx.set(name, float(val))
-    cfg = fk.TestConfiguration("", "", K, M, X, max_b=B, useHT=True, write=False)
-    spec = workload(args.reads, world)
-    spec["first_read"] = rank * args.reads
+    wl = Workload(args.config, args.reads, args.ht)
+    cfg = wl.tc(fk)
 
     if world > 1:
         from fastkmer_b200 import multigpu
@@ -186,7 +237,7 @@ def main():
         job = None
 
     # ---------------- device-resident input ----------------
-    d_b, d_i, n_pos = ctx.synth_packed_device(spec)
+    d_b, d_i, n_pos = wl.device_input(ctx, rank, world)
 
     def step_resident():
         if job is None:
@@ -219,7 +270,7 @@ def main():
         ms = float(t.item())
     ms_step = ms / args.steps
     stage = [s / args.steps for s in stage]
-    n_bases_total = args.reads * READ_LEN * world
+    n_bases_total = wl.n_bases_total(world)
     n_kmers_total = st["n_kmers_global"] if "n_kmers_global" in st else st["n_kmers"]
     n_distinct_total = st["n_distinct_global"] if "n_distinct_global" in st else st["n_distinct"]
     value = n_bases_total / (ms_step * 1e-3)
@@ -227,11 +278,7 @@ def main():
     # ---------------- end to end from host FASTA ----------------
     e2e = None
     if not args.no_e2e:
-        nbytes = api.C.c_uint64()
-        s = api._synth(spec)
-        api._check(api.load_library().fkm_synth_fasta_host(api.C.byref(s), None, 0, api.C.byref(nbytes)))
-        pinned = api.host_alloc(nbytes.value)
-        fasta = fk.synth_fasta(spec, out=pinned)
+        fasta = wl.host_fasta(api, fk, rank, world)
 
         def step_e2e():
             if job is None:
@@ -262,23 +309,22 @@ def main():
 
     # ---------------- CPU baseline (oracle port) on a bounded sample ----------------
     cpu = None
-    ls_per_kmer = 3.73                                   # SURVEY §8(d) planning ratio for k28/m10 (reference cutting rule)
+    ls_per_kmer = {28: 3.73, 31: 3.77, 55: 3.48}.get(wl.c["k"], 3.7)     # SURVEY §8(d) planning ratios (reference cutting rule)
     if not args.no_cpu and world == 1:
         threads = os.cpu_count() or 1
-        cs = cpu_sample_spec(world)
-        r = run_cpu_oracle(threads, cs)
+        r = run_cpu_oracle(threads, wl)
         ls_per_kmer = r["superkmer_bases_ref"] / max(1, r["n_kmers"])
         cpu = {"value": r["n_bases"] / r["seconds"], "unit": "bases/s", "cores": threads, "kind": "port",
-               "kmers_per_sec": r["n_kmers"] / r["seconds"],
-               "sample": "%d reads x %d bp of the same generator, %.1f s" % (cs["n_reads"], READ_LEN, r["seconds"])}
+               "kmers_per_sec": r["n_kmers"] / r["seconds"], "sample": "%s, %.1f s" % (r["desc"], r["seconds"])}
 
     # ---------------- roofline ----------------
     peak, peak_src = measured_peaks()
     # algorithmic bytes of the whole pipeline, SURVEY §8(d): N_b/4 + 2*L_s/4 + D*(W+4), L_s under the reference's cutting rule
     L_s = ls_per_kmer * n_kmers_total
-    bytes_alg = n_bases_total / 4 + 2 * L_s / 4 + n_distinct_total * 12
-    # dominant kernel: k_count_ht (stage 3).  It reads the super-k-mer stream once (L_s/4 algorithmic bytes); the
-    # distinct (k-mer,count) pairs leave through k_compact_ht (stage 4).
+    key_bytes = 8 if wl.c["k"] <= 32 else 16
+    bytes_alg = n_bases_total / 4 + 2 * L_s / 4 + n_distinct_total * (key_bytes + 4)
+    # dominant kernel: the count stage (stage 3; k_count_ht for useHT=1, k_expand + radix passes for useHT=0).  It reads
+    # the super-k-mer stream once (L_s/4 algorithmic bytes); the distinct (k-mer,count) pairs leave through stage 4.
     n_count_launches = max(1, int(st["n_batches"]))
     count_bytes = (L_s / 4) / world
     count_ms = stage[3]
@@ -288,7 +334,9 @@ def main():
         traffic = tj["dram_bytes_per_record"] * (st["n_superkmers"] / n_count_launches)
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_count_ht", "achieved": count_bytes / (count_ms * 1e-3) / 1e9 if count_ms else None,
+    if not wl.c["ht"] or wl.c["k"] > 32:
+        traffic = None                                # the ncu capture is of the 64-bit hash-table kernel
+    roofline = {"bound": "hbm", "kernel": "k_count_ht" if wl.c["ht"] else "k_expand+k_radix_*", "achieved": count_bytes / (count_ms * 1e-3) / 1e9 if count_ms else None,
                 "peak": peak, "unit": "GB/s", "frac": (count_bytes / (count_ms * 1e-3) / 1e9 / peak) if count_ms else None,
                 "traffic": traffic, "algorithmic_bytes_per_launch": count_bytes / n_count_launches, "peak_source": peak_src, "launches_per_step": n_count_launches,
                 "avg_launch_ms": count_ms / n_count_launches,
@@ -303,9 +351,9 @@ def main():
                    "frac": gbs / 770.0 if gbs else None, "peak_source": "measured peer copy, B200_PROFILING.md"}
     line = {"metric": "bases_per_sec", "value": value, "unit": "bases/s", "kmers_per_sec": n_kmers_total / (ms_step * 1e-3),
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: k=28 m=10 x=3 B=2048 useHT=1, %d synthetic %d bp reads per GPU (30x genome, 1%% subst, 0.1%% N)"
-                                   % (args.reads, READ_LEN), "reads_per_gpu": args.reads, "n_bases": n_bases_total,
+            "scaling": wl.scaling, "vs_baseline": None, "dtype": "u64" if wl.c["k"] <= 32 else "u128", "data": "synthetic",
+            "config": {"workload": wl.c["name"] + (" (per GPU; 1% substitutions, 0.1% N)" if wl.kind == "reads" else ""),
+                       "reads_per_gpu": wl.c.get("reads"), "n_bases": n_bases_total,
                        "n_kmers": int(n_kmers_total), "n_distinct": int(n_distinct_total),
                        "l2": "inputs (%.1f GB packed) larger than L2, no flush" % (n_pos * 3 / 8 / 1e9)},
             "stage_ms": {"histogram": stage[1], "scatter": stage[2], "count": stage[3], "compact": stage[4], "digest": stage[5],

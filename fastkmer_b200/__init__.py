@@ -12,8 +12,8 @@ All compute runs in libfastkmer_b200.so (hand-written sm_100a kernels).  There i
 fallback: importing works anywhere, creating a Context without a CUDA device raises.
 """
 from .config import TestConfiguration
-from .api import Context, CountResult, FkmError, Stats, lib_path, load_library, pack_fasta, synth_fasta
+from .api import Context, CountResult, FkmError, Stats, lib_path, load_library, pack_fasta, synth_fasta, synth_long_fasta
 from .counter import LocalTestKmerCounter, SparkBinKmerCounter, TestKmerCounter
 
 __all__ = ["TestConfiguration", "Context", "CountResult", "FkmError", "Stats", "lib_path", "load_library",
-           "pack_fasta", "synth_fasta", "SparkBinKmerCounter", "LocalTestKmerCounter", "TestKmerCounter"]
+           "pack_fasta", "synth_fasta", "synth_long_fasta", "SparkBinKmerCounter", "LocalTestKmerCounter", "TestKmerCounter"]

@@ -34,6 +34,10 @@ class fkm_synth(C.Structure):
                                           "read_len", "first_read")]
 
 
+class fkm_synth_long(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("seed_genome", "seed_repeats", "seed_n", "first_pos", "n_bases")]
+
+
 class Stats(dict):
     """fkm_stats as a dict (plus attribute access)."""
     __getattr__ = dict.__getitem__
@@ -80,6 +84,8 @@ def load_library():
         "fkm_result_free": (None, [vp]),
         "fkm_synth_fasta_host": (C.c_int, [C.POINTER(fkm_synth), vp, u64, C.POINTER(u64)]),
         "fkm_synth_packed_device": (C.c_int, [vp, C.POINTER(fkm_synth), C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]),
+        "fkm_synth_long_fasta_host": (C.c_int, [C.POINTER(fkm_synth_long), vp, u64, C.POINTER(u64)]),
+        "fkm_synth_long_packed_device": (C.c_int, [vp, C.POINTER(fkm_synth_long), C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]),
         "fkm_device_free": (C.c_int, [vp, vp]),
         "fkm_debug_window_bins": (C.c_int, [vp, cfgp, vp, vp, u64, vp]),
         "fkm_record_bytes": (i32, [cfgp]),
@@ -171,6 +177,25 @@ def synth_fasta(spec, out=None) -> np.ndarray:
     if out is None:
         out = np.empty(n.value, dtype=np.uint8)
     _check(lib.fkm_synth_fasta_host(C.byref(s), out.ctypes.data, out.size, C.byref(n)))
+    return out[:n.value]
+
+
+def _synth_long(spec):
+    s = fkm_synth_long()
+    s.seed_genome, s.seed_repeats, s.seed_n = spec["seeds"]
+    s.first_pos, s.n_bases = spec.get("first_pos", 0), spec["n_bases"]
+    return s
+
+
+def synth_long_fasta(spec, out=None) -> np.ndarray:
+    """One long synthetic record (BASELINE config 3).  spec: dict(seeds=(G,rep,N), n_bases[, first_pos])."""
+    lib = load_library()
+    s = _synth_long(spec)
+    n = C.c_uint64()
+    _check(lib.fkm_synth_long_fasta_host(C.byref(s), None, 0, C.byref(n)))
+    if out is None:
+        out = np.empty(n.value, dtype=np.uint8)
+    _check(lib.fkm_synth_long_fasta_host(C.byref(s), out.ctypes.data, out.size, C.byref(n)))
     return out[:n.value]
 
 
@@ -299,6 +324,13 @@ class Context:
         s = _synth(spec)
         b, i, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
         _check(load_library().fkm_synth_packed_device(self._h, C.byref(s), C.byref(b), C.byref(i), C.byref(n)))
+        self._dev_bufs += [b, i]
+        return b.value, i.value, n.value
+
+    def synth_long_packed_device(self, spec):
+        s = _synth_long(spec)
+        b, i, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        _check(load_library().fkm_synth_long_packed_device(self._h, C.byref(s), C.byref(b), C.byref(i), C.byref(n)))
         self._dev_bufs += [b, i]
         return b.value, i.value, n.value
 

@@ -51,4 +51,19 @@ FKM_HD uint32_t synth_base(const SynthSpec& S, uint64_t r, uint64_t j, uint64_t 
     return b;
 }
 
+// Long-sequence generator (BASELINE config 3): position i of one synthetic genome.
+// iid bases; 5 % of the 5-kb blocks are copies of one of 1000 repeat templates; 0.5 % of the
+// 1-kb blocks are runs of 'N'.  Counter-based, so any shard [first, first+n) can be generated alone.
+struct LongSpec { uint64_t seedG, seedRep, seedN, first_pos; };
+FKM_HD uint32_t synth_long_base(const LongSpec& S, uint64_t i, bool& invalid) {
+    invalid = (mix64(S.seedN + i / 1000ull) % 200ull) == 0ull;
+    const uint64_t blk = i / 5000ull;
+    const uint64_t r = mix64(S.seedRep + blk);
+    if ((r % 20ull) == 0ull) {
+        const uint64_t t = (r >> 20) % 1000ull;
+        return (uint32_t)(mix64(S.seedG ^ 0x5bd1e995ull ^ (t * 5000ull + i % 5000ull) * 0x9E3779B97F4A7C15ull) >> 62);
+    }
+    return (uint32_t)(mix64(S.seedG + i) >> 62);
+}
+
 }  // namespace fkm

@@ -169,3 +169,32 @@ extern "C" int fkm_synth_fasta_host(const fkm_synth* s, uint8_t* out, uint64_t c
     for (auto& q : th) q.join();
     return FKM_OK;
 }
+
+// BASELINE config 3: one long record, 70-column lines
+extern "C" int fkm_synth_long_fasta_host(const fkm_synth_long* s, uint8_t* out, uint64_t cap, uint64_t* n_bytes) {
+    if (!s) return fkm_set_error(FKM_EINVAL, "bad synthetic spec");
+    const uint64_t n = s->n_bases, W = 70;
+    const char* hdr = ">chr1 synthetic\n";
+    const uint64_t hl = strlen(hdr);
+    const uint64_t total = hl + n + (n + W - 1) / W;
+    if (n_bytes) *n_bytes = total;
+    if (!out) return FKM_OK;
+    if (cap < total) return fkm_set_error(FKM_EINVAL, "FASTA buffer too small");
+    memcpy(out, hdr, hl);
+    fkm::LongSpec S{s->seed_genome, s->seed_repeats, s->seed_n, s->first_pos};
+    unsigned nt = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
+    const uint64_t lines = (n + W - 1) / W;
+    auto work = [&](unsigned t) {
+        for (uint64_t ln = lines * t / nt; ln < lines * (t + 1) / nt; ln++) {
+            uint8_t* p = out + hl + ln * (W + 1);
+            const uint64_t a = ln * W, e = std::min(n, a + W);
+            for (uint64_t i = a; i < e; i++) { bool bad; uint32_t b = fkm::synth_long_base(S, S.first_pos + i, bad); *p++ = bad ? 'N' : (uint8_t)"ACGT"[b]; }
+            *p = '\n';
+        }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& q : th) q.join();
+    return FKM_OK;
+}

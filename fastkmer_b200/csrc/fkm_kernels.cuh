@@ -1073,4 +1073,19 @@ __global__ void __launch_bounds__(256) k_synth(const SynthParams P) {
     P.bases[wi] = bw; P.inv[wi] = iw;
 }
 
+// one long sequence, positions [first_pos, first_pos + n_pos - 1) followed by the record separator
+struct SynthLongParams { LongSpec S; uint64_t n_pos, n_words; uint64_t* bases; uint32_t* inv; };
+__global__ void __launch_bounds__(256) k_synth_long(const SynthLongParams P) {
+    uint64_t wi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= P.n_words) return;
+    uint64_t bw = 0; uint32_t iw = 0;
+    for (int t = 0; t < 32; t++) {
+        const uint64_t p = (wi << 5) + t;
+        uint32_t b = 0; bool bad = true;
+        if (p + 1 < P.n_pos) { b = synth_long_base(P.S, P.S.first_pos + p, bad); if (bad) b = 0; }
+        bw = (bw << 2) | b; iw = (iw << 1) | (bad ? 1u : 0u);
+    }
+    P.bases[wi] = bw; P.inv[wi] = iw;
+}
+
 }  // namespace fkm

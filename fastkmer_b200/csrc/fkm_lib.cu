@@ -876,17 +876,21 @@ static int upload_and_ingest(fkm_ctx* ctx, const uint8_t* fasta, uint64_t n_byte
 // A record longer than `target` (a long genome) simply makes a longer chunk.
 static void split_fasta(const uint8_t* t, uint64_t n, uint64_t target, std::vector<uint64_t>& cuts) {
     cuts.clear(); cuts.push_back(0);
+    // a header is searched only in a window after each target point (short reads always have one there);
+    // inside a long record no cut is made and the host never scans the whole text
+    const uint64_t window = std::max<uint64_t>(1u << 16, target / 8);
     uint64_t pos = target;
     while (pos < n) {
         const uint8_t* p = t + pos;
+        const uint8_t* lim = t + std::min<uint64_t>(n, pos + window);
         uint64_t cut = n;
-        while (p < t + n) {
-            p = (const uint8_t*)memchr(p, '>', (size_t)(t + n - p));
+        while (p < lim) {
+            p = (const uint8_t*)memchr(p, '>', (size_t)(lim - p));
             if (!p) break;
             if (p > t && p[-1] == '\n') { cut = (uint64_t)(p - t); break; }
             p++;
         }
-        if (cut >= n) break;
+        if (cut >= n) { pos += target; continue; }
         cuts.push_back(cut);
         pos = cut + target;
     }
@@ -1133,6 +1137,21 @@ extern "C" int fkm_synth_packed_device(fkm_ctx* ctx, const fkm_synth* sy, void**
     *d_bases = P.bases; *d_inv = P.inv; if (n_positions) *n_positions = P.n_pos;
     return FKM_OK;
 }
+extern "C" int fkm_synth_long_packed_device(fkm_ctx* ctx, const fkm_synth_long* sy, void** d_bases, void** d_inv, uint64_t* n_positions) {
+    if (!ctx || !sy || !d_bases || !d_inv) return fkm_set_error(FKM_EINVAL, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    SynthLongParams P;
+    P.S = LongSpec{sy->seed_genome, sy->seed_repeats, sy->seed_n, sy->first_pos};
+    P.n_pos = sy->n_bases + 1; P.n_words = (P.n_pos + 31) / 32;
+    CK(cudaMalloc((void**)&P.bases, std::max<size_t>(8, P.n_words * 8)));
+    cudaError_t e = cudaMalloc((void**)&P.inv, std::max<size_t>(4, P.n_words * 4));
+    if (e != cudaSuccess) { cudaFree(P.bases); CK(e); }
+    k_synth_long<<<(unsigned)((P.n_words + 255) / 256), 256, 0, ctx->stream>>>(P); CKL();
+    CK(cudaStreamSynchronize(ctx->stream));
+    *d_bases = P.bases; *d_inv = P.inv; if (n_positions) *n_positions = P.n_pos;
+    return FKM_OK;
+}
+
 extern "C" int fkm_device_free(fkm_ctx* ctx, void* p) {
     if (!ctx) return fkm_set_error(FKM_EINVAL, "ctx is NULL");
     CK(cudaSetDevice(ctx->device)); CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFree(p));

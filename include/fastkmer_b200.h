@@ -152,6 +152,11 @@ int  fkm_synth_fasta_host(const fkm_synth* s, uint8_t* out, uint64_t cap, uint64
 /* packed layout generated directly in device memory (owned by ctx until
  * fkm_device_free).  d_bases / d_invalid receive device pointers.              */
 int  fkm_synth_packed_device(fkm_ctx* ctx, const fkm_synth* s, void** d_bases, void** d_invalid, uint64_t* n_positions);
+/* One long sequence (BASELINE config 3): bases [first_pos, first_pos + n_bases) of a synthetic genome with
+ * 5 % 5-kb repeats and 0.5 % 1-kb N runs, as a single record ('>chr\n' + 70-column lines on the host).      */
+typedef struct fkm_synth_long { uint64_t seed_genome, seed_repeats, seed_n, first_pos, n_bases; } fkm_synth_long;
+int  fkm_synth_long_fasta_host(const fkm_synth_long* s, uint8_t* out, uint64_t cap, uint64_t* n_bytes);
+int  fkm_synth_long_packed_device(fkm_ctx* ctx, const fkm_synth_long* s, void** d_bases, void** d_invalid, uint64_t* n_positions);
 int  fkm_device_free(fkm_ctx* ctx, void* d_ptr);
 
 /* ---- staged entry points: one process per GPU, bins owned per GPU ---------------

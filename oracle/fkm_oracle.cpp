@@ -372,18 +372,43 @@ Result* run(const uint8_t* fasta, size_t n, int k, int m, int x, int max_b, int 
     std::vector<MapStats> stats((size_t)threads);
     {
         std::atomic<size_t> next(0);
-        const size_t chunk = 256;
+        size_t chunk = 256;
+        // map tasks: whole records, except that a long record is cut into pieces of kPiece window starts
+        // (k-1 bytes of look-ahead), the way FASTdoop's FASTAlongInputFormat hands one PartialSequence per
+        // input split to getSuperKmers (SBKC:62-63,1012); every k-window is still seen exactly once.
+        const size_t kPiece = (size_t)4 << 20;
+        struct Task { size_t rec, first, last; };          // byte range [first,last) of the record's text
+        std::vector<Task> tasks;
+        for (size_t r = 0; r < recs.size(); r++) {
+            const size_t len = recs[r].second - recs[r].first;
+            if (len <= 2 * kPiece) tasks.push_back(Task{r, 0, len});
+            else for (size_t a = 0; a < len; a += kPiece) tasks.push_back(Task{r, a, std::min(len, a + kPiece)});
+        }
+        chunk = std::max<size_t>(1, std::min<size_t>(256, tasks.size() / ((size_t)threads * 8 + 1)));
         auto work = [&](int t) {
             std::vector<uint8_t> cur;
             for (;;) {
                 size_t b = next.fetch_add(chunk);
-                if (b >= recs.size()) break;
-                size_t e = std::min(recs.size(), b + chunk);
-                for (size_t r = b; r < e; r++) {
+                if (b >= tasks.size()) break;
+                size_t e = std::min(tasks.size(), b + chunk);
+                for (size_t ti = b; ti < e; ti++) {
+                    const Task& T = tasks[ti];
+                    const uint8_t* txt = fasta + recs[T.rec].first;
+                    const size_t rec_len = recs[T.rec].second - recs[T.rec].first;
                     cur.clear();
-                    for (size_t i = recs[r].first; i < recs[r].second; i++)
-                        if (fasta[i] != '\n') cur.push_back(fasta[i]);               // SBKC:63-64 replaceAll("\n","")
+                    for (size_t i = T.first; i < T.last; i++) if (txt[i] != '\n') cur.push_back(txt[i]);   // SBKC:63-64 replaceAll("\n","")
+                    if (T.last < rec_len) {                 // look-ahead: the next k-1 sequence bytes
+                        size_t need = (size_t)k - 1;
+                        for (size_t i = T.last; i < rec_len && need; i++) if (txt[i] != '\n') { cur.push_back(txt[i]); need--; }
+                    }
+                    const uint64_t nb0 = stats[(size_t)t].n_bases;
                     scan_record(cur.data(), (int64_t)cur.size(), k, m, B, norm.data(), per_thread[(size_t)t], stats[(size_t)t]);
+                    if (T.last < rec_len) {                 // do not count the look-ahead bytes twice
+                        size_t la = 0, need = (size_t)k - 1;
+                        for (size_t i = T.last; i < rec_len && need; i++) if (txt[i] != '\n') { la++; need--; }
+                        stats[(size_t)t].n_bases = nb0 + (uint64_t)(cur.size() - la);
+                    }
+                    if (T.first != 0) stats[(size_t)t].n_records--;
                 }
             }
         };
