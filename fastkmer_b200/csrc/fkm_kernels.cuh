@@ -787,63 +787,85 @@ __global__ void __launch_bounds__(256) k_expand(const ExpandParams P) {
     }
 }
 
-// ------------------------------------------------------------------ K6b: segmented LSD radix sort
+// ------------------------------------------------------------------ K6b: segmented radix sort
 // Segments = bins of the batch.  Tiles of 2048 keys never straddle a segment.
+//
+// Fast path (MSD first): ONE global partition pass on the top `bits` (<= 10) bits of the key
+// (k_radix_hist / k_radix_scan / k_radix_scatter with nd = 2^bits digits), k_form_chunks groups the
+// resulting sub-buckets into chunks of <= kLocalCap keys, and k_radix_local sorts every chunk
+// completely inside shared memory (LSD, 8-bit digits) and writes it back in place: the whole
+// segment is then ascending.  HBM traffic: 2 reads + 1 write (partition) + 1 read + 1 write.
+// Fallback (a sub-bucket larger than a chunk): the same three kernels run one LSD pass per 8 bits.
 static constexpr int kSortTile = 2048;
+static constexpr int kMaxDigits = 1024;
 struct SortParams {
     const void* in; void* out;
     const unsigned long long* seg_base;      // [n_seg+1] key offsets
     const unsigned int* tile_seg;            // [n_tiles] segment of each tile
     const unsigned int* seg_tile0;           // [n_seg+1] first tile of each segment
-    unsigned int* tile_hist;                 // [n_tiles*256]
-    unsigned int n_tiles; int n_seg; int shift;   // digit = (key >> shift) & 255
+    unsigned int* tile_hist;                 // [n_tiles*nd]
+    unsigned int* seg_digit_tot;             // [n_seg*nd] keys per (segment, digit), or NULL
+    unsigned int n_tiles; int n_seg; int shift; int nd;   // digit = (key >> shift) & (nd-1)
 };
-template <bool WIDE> __device__ __forceinline__ unsigned int digit_of(typename Traits<WIDE>::Key key, int shift);
-template <> __device__ __forceinline__ unsigned int digit_of<false>(uint64_t key, int shift) { return (unsigned int)(key >> shift) & 255u; }
-template <> __device__ __forceinline__ unsigned int digit_of<true>(key128 key, int shift) {
-    return (unsigned int)((shift >= 64) ? (key.hi >> (shift - 64)) : (key.lo >> shift)) & 255u;
+template <bool WIDE> __device__ __forceinline__ unsigned int digit_of(typename Traits<WIDE>::Key key, int shift, unsigned int mask);
+template <> __device__ __forceinline__ unsigned int digit_of<false>(uint64_t key, int shift, unsigned int mask) { return (unsigned int)(key >> shift) & mask; }
+template <> __device__ __forceinline__ unsigned int digit_of<true>(key128 key, int shift, unsigned int mask) {
+    uint64_t v;
+    if (shift >= 64) v = key.hi >> (shift - 64);
+    else v = shift ? ((key.lo >> shift) | (key.hi << (64 - shift))) : key.lo;
+    return (unsigned int)v & mask;
 }
 
 template <bool WIDE>
 __global__ void __launch_bounds__(256) k_radix_hist(const SortParams P) {
     typedef typename Traits<WIDE>::Key Key;
-    __shared__ unsigned int s_h[256];
+    __shared__ unsigned int s_h[kMaxDigits];
     const unsigned int t = blockIdx.x;
     const unsigned int seg = P.tile_seg[t];
     const unsigned long long lo = P.seg_base[seg] + (unsigned long long)(t - P.seg_tile0[seg]) * kSortTile;
     const unsigned long long hi = min(lo + (unsigned long long)kSortTile, P.seg_base[seg + 1]);
-    s_h[threadIdx.x] = 0;
+    for (int d = threadIdx.x; d < P.nd; d += 256) s_h[d] = 0;
     __syncthreads();
     const Key* in = reinterpret_cast<const Key*>(P.in);
-    for (unsigned long long i = lo + threadIdx.x; i < hi; i += 256) atomicAdd(&s_h[digit_of<WIDE>(in[i], P.shift)], 1u);
+    const unsigned int mask = (unsigned int)P.nd - 1u;
+    for (unsigned long long i = lo + threadIdx.x; i < hi; i += 256) atomicAdd(&s_h[digit_of<WIDE>(in[i], P.shift, mask)], 1u);
     __syncthreads();
-    P.tile_hist[(size_t)t * 256 + threadIdx.x] = s_h[threadIdx.x];
+    for (int d = threadIdx.x; d < P.nd; d += 256) P.tile_hist[(size_t)t * P.nd + d] = s_h[d];
 }
 
-// one CTA per segment, thread d owns digit d: tile_hist[t][d] <- exclusive offset of
-// (digit d, tile t) inside the segment (digit-major, tile-minor).
+// one CTA per segment: tile_hist[t][d] <- exclusive offset of (digit d, tile t) inside the
+// segment (digit-major, tile-minor); seg_digit_tot[seg][d] <- keys of the segment with digit d.
 __global__ void __launch_bounds__(256) k_radix_scan(const SortParams P) {
-    __shared__ unsigned int s_tot[256];
+    __shared__ unsigned int s_tot[kMaxDigits];
+    __shared__ unsigned int s_base[kMaxDigits];
     const int seg = blockIdx.x;
     const unsigned int t0 = P.seg_tile0[seg], t1 = P.seg_tile0[seg + 1];
-    const int d = threadIdx.x;
-    unsigned int tot = 0;
-    for (unsigned int t = t0; t < t1; t++) tot += P.tile_hist[(size_t)t * 256 + d];
-    s_tot[d] = tot;
-    __syncthreads();
-    // exclusive scan over digits (256 values) — simple Hillis-Steele in shared memory
-    unsigned int v = tot;
-    for (int o = 1; o < 256; o <<= 1) {
-        unsigned int add = (d >= o) ? s_tot[d - o] : 0u;
-        __syncthreads();
-        v += add; s_tot[d] = v;
-        __syncthreads();
+    for (int d = threadIdx.x; d < P.nd; d += 256) {
+        unsigned int tot = 0;
+        for (unsigned int t = t0; t < t1; t++) tot += P.tile_hist[(size_t)t * P.nd + d];
+        s_tot[d] = tot;
+        if (P.seg_digit_tot) P.seg_digit_tot[(size_t)seg * P.nd + d] = tot;
     }
-    unsigned int run = v - tot;
-    for (unsigned int t = t0; t < t1; t++) {
-        unsigned int c = P.tile_hist[(size_t)t * 256 + d];
-        P.tile_hist[(size_t)t * 256 + d] = run;
-        run += c;
+    __syncthreads();
+    if (threadIdx.x < 32) {                       // exclusive scan over the digits by one warp
+        unsigned int carry = 0;
+        for (int d0 = 0; d0 < P.nd; d0 += 32) {
+            const unsigned int v = s_tot[d0 + threadIdx.x];
+            unsigned int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { unsigned int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((int)threadIdx.x >= o) incl += t; }
+            s_base[d0 + threadIdx.x] = carry + incl - v;
+            carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        }
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < P.nd; d += 256) {
+        unsigned int run = s_base[d];
+        for (unsigned int t = t0; t < t1; t++) {
+            unsigned int c = P.tile_hist[(size_t)t * P.nd + d];
+            P.tile_hist[(size_t)t * P.nd + d] = run;
+            run += c;
+        }
     }
 }
 
@@ -852,16 +874,17 @@ __global__ void __launch_bounds__(256) k_radix_scan(const SortParams P) {
 template <bool WIDE>
 __global__ void __launch_bounds__(256) k_radix_scatter(const SortParams P) {
     typedef typename Traits<WIDE>::Key Key;
-    __shared__ unsigned int s_wc[8][256];
-    __shared__ unsigned int s_off[256];
+    __shared__ unsigned int s_wc[8][kMaxDigits];
+    __shared__ unsigned int s_off[kMaxDigits];
     const unsigned int t = blockIdx.x;
     const unsigned int seg = P.tile_seg[t];
     const unsigned long long seg0 = P.seg_base[seg];
     const unsigned long long lo = seg0 + (unsigned long long)(t - P.seg_tile0[seg]) * kSortTile;
     const unsigned long long hi = min(lo + (unsigned long long)kSortTile, P.seg_base[seg + 1]);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < 8 * 256; i += 256) (&s_wc[0][0])[i] = 0;
-    s_off[threadIdx.x] = P.tile_hist[(size_t)t * 256 + threadIdx.x];
+    const unsigned int mask = (unsigned int)P.nd - 1u;
+    for (int w = 0; w < 8; w++) for (int d = threadIdx.x; d < P.nd; d += 256) s_wc[w][d] = 0;
+    for (int d = threadIdx.x; d < P.nd; d += 256) s_off[d] = P.tile_hist[(size_t)t * P.nd + d];
     __syncthreads();
     const Key* in = reinterpret_cast<const Key*>(P.in);
     Key* out = reinterpret_cast<Key*>(P.out);
@@ -871,7 +894,7 @@ __global__ void __launch_bounds__(256) k_radix_scatter(const SortParams P) {
         const unsigned long long i = lo + (unsigned long long)(warp * 256 + rd * 32 + lane);
         const bool ok = i < hi;
         if (ok) keys[rd] = in[i];
-        const unsigned int d = ok ? digit_of<WIDE>(keys[rd], P.shift) : (256u + (unsigned)lane);
+        const unsigned int d = ok ? digit_of<WIDE>(keys[rd], P.shift, mask) : ((unsigned)kMaxDigits + (unsigned)lane);
         const unsigned int peers = __match_any_sync(0xFFFFFFFFu, d);
         unsigned int old = 0;
         if (ok) old = s_wc[warp][d];
@@ -882,15 +905,113 @@ __global__ void __launch_bounds__(256) k_radix_scatter(const SortParams P) {
         dig[rd] = d;
     }
     __syncthreads();
-    {   // exclusive prefix over the 8 warps for digit = threadIdx.x
+    for (int d = threadIdx.x; d < P.nd; d += 256) {      // exclusive prefix over the 8 warps
         unsigned int run = 0;
 #pragma unroll
-        for (int wi = 0; wi < 8; wi++) { unsigned int c = s_wc[wi][threadIdx.x]; s_wc[wi][threadIdx.x] = run; run += c; }
+        for (int wi = 0; wi < 8; wi++) { unsigned int c = s_wc[wi][d]; s_wc[wi][d] = run; run += c; }
     }
     __syncthreads();
 #pragma unroll
     for (int rd = 0; rd < 8; rd++) {
-        if (dig[rd] < 256u) out[seg0 + s_off[dig[rd]] + s_wc[warp][dig[rd]] + rank[rd]] = keys[rd];
+        if (dig[rd] < (unsigned)kMaxDigits) out[seg0 + s_off[dig[rd]] + s_wc[warp][dig[rd]] + rank[rd]] = keys[rd];
+    }
+}
+
+// groups the sub-buckets of every segment into chunks of <= cap keys (one thread per segment);
+// sets *too_big when a single sub-bucket exceeds cap.
+struct ChunkDesc { unsigned long long start; unsigned int n; unsigned int pad; };
+__global__ void k_form_chunks(const unsigned long long* seg_base, const unsigned int* seg_digit_tot, int n_seg, int nd,
+                              unsigned int cap, ChunkDesc* chunks, unsigned int max_chunks, unsigned int* n_chunks, int* too_big) {
+    const int seg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (seg >= n_seg) return;
+    unsigned long long start = seg_base[seg];
+    unsigned int acc = 0;
+    auto emit = [&](unsigned int n) {
+        if (!n) return;
+        const unsigned int c = atomicAdd(n_chunks, 1u);
+        if (c < max_chunks) { chunks[c].start = start; chunks[c].n = n; chunks[c].pad = 0; } else *too_big = 1;
+        start += n;
+    };
+    for (int d = 0; d < nd; d++) {
+        const unsigned int c = seg_digit_tot[(size_t)seg * nd + d];
+        if (c > cap) *too_big = 1;
+        if (acc + c > cap) { emit(acc); acc = 0; }
+        acc += c;
+    }
+    emit(acc);
+}
+
+// One CTA sorts one chunk (<= kLocalCap keys) completely in shared memory: LSD over all
+// `n_pass` 8-bit digits of the key, two key buffers, per-warp digit counters, stable ranks
+// from match.any.  512 threads; warp w owns keys [w*per_warp, (w+1)*per_warp) of the chunk.
+template <bool WIDE> struct LocalSort { static constexpr int kCap = WIDE ? 5120 : 10240; };
+template <bool WIDE>
+__global__ void __launch_bounds__(512) k_radix_local(const void* in, void* out, const ChunkDesc* chunks, unsigned int n_chunks, int n_pass) {
+    typedef typename Traits<WIDE>::Key Key;
+    constexpr int CAP = LocalSort<WIDE>::kCap;
+    constexpr int NW = 16;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Key* bufA = reinterpret_cast<Key*>(smem_raw);
+    Key* bufB = bufA + CAP;
+    unsigned short* s_rank = reinterpret_cast<unsigned short*>(bufB + CAP);
+    unsigned int* s_wc = reinterpret_cast<unsigned int*>(s_rank + CAP);        // [NW][256]
+    __shared__ unsigned int s_warp_tot[NW];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const Key* gin = reinterpret_cast<const Key*>(in);
+    Key* gout = reinterpret_cast<Key*>(out);
+    for (unsigned int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const unsigned long long start = chunks[c].start;
+        const int n = (int)chunks[c].n;
+        const int per_warp = ((n + NW - 1) / NW + 31) & ~31;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += 512) bufA[i] = gin[start + i];
+        Key* src = bufA; Key* dst = bufB;
+        for (int p = 0; p < n_pass; p++) {
+            const int shift = 8 * p;
+            for (int i = threadIdx.x; i < NW * 256; i += 512) s_wc[i] = 0;
+            __syncthreads();
+            const int w0 = warp * per_warp, w1 = min(n, w0 + per_warp);
+            for (int i0 = w0; i0 < w1; i0 += 32) {
+                const int i = i0 + lane;
+                const bool ok = i < w1;
+                unsigned int d = 256u + (unsigned)lane;
+                if (ok) d = digit_of<WIDE>(src[i], shift, 255u);
+                const unsigned int peers = __match_any_sync(0xFFFFFFFFu, d);
+                unsigned int old = 0;
+                if (ok) old = s_wc[warp * 256 + d];
+                __syncwarp();
+                if (ok && (peers & ((1u << lane) - 1u)) == 0u) s_wc[warp * 256 + d] = old + __popc(peers);
+                __syncwarp();
+                if (ok) s_rank[i] = (unsigned short)(old + __popc(peers & ((1u << lane) - 1u)));
+            }
+            __syncthreads();
+            if (threadIdx.x < 256) {            // digit d = threadIdx.x: prefix over warps, then over digits
+                const int d = threadIdx.x;
+                unsigned int run = 0;
+#pragma unroll
+                for (int w = 0; w < NW; w++) { unsigned int t = s_wc[w * 256 + d]; s_wc[w * 256 + d] = run; run += t; }
+                unsigned int incl = run;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { unsigned int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+                if (lane == 31) s_warp_tot[warp] = incl;
+                asm volatile("bar.sync 1, 256;");
+                unsigned int base = incl - run;
+                for (int w = 0; w < warp; w++) base += s_warp_tot[w];
+#pragma unroll
+                for (int w = 0; w < NW; w++) s_wc[w * 256 + d] += base;
+            }
+            __syncthreads();
+            for (int i0 = w0; i0 < w1; i0 += 32) {
+                const int i = i0 + lane;
+                if (i < w1) {
+                    const Key key = src[i];
+                    dst[s_wc[warp * 256 + digit_of<WIDE>(key, shift, 255u)] + s_rank[i]] = key;
+                }
+            }
+            __syncthreads();
+            Key* t = src; src = dst; dst = t;
+        }
+        for (int i = threadIdx.x; i < n; i += 512) gout[start + i] = src[i];
     }
 }
 

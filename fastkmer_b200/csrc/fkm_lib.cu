@@ -91,6 +91,7 @@ struct fkm_ctx {
     double load_factor = 0.6;
     double ingest_chunk_bytes = 256.0 * (1 << 20);   // FASTA text is streamed to the GPU in chunks of about this size
     double debug_event_scale = 1.0;   // test hook: scales the run-event list capacity (forces the second-scan fallback)
+    double debug_force_lsd = 0.0;     // sort path: 0 = auto (MSD + shared-memory chunk sort for 64-bit keys, LSD passes for 128-bit), 1 = LSD, 2 = MSD
     double debug_rho_scale = 1.0;     // test hook: scales the learnt distinct/k-mer ratio (forces the overflow fallback)
     double l2_table_bytes = 1024.0 * (1 << 20); // tables of one asynchronous batch; 0 disables the asynchronous phase (measured: 0.25-16 GB all within 8%, profiles/r1_table_sweep.txt)
     uint64_t job_launches = 0;
@@ -167,6 +168,7 @@ extern "C" int fkm_ctx_set(fkm_ctx* c, const char* name, double v) {
     else if (!strcmp(name, "load_factor")) c->load_factor = v;
     else if (!strcmp(name, "l2_table_bytes")) c->l2_table_bytes = v;
     else if (!strcmp(name, "debug_rho_scale")) c->debug_rho_scale = v;
+    else if (!strcmp(name, "debug_force_lsd")) c->debug_force_lsd = v;
     else if (!strcmp(name, "debug_event_scale")) c->debug_event_scale = v;
     else if (!strcmp(name, "ingest_chunk_bytes")) c->ingest_chunk_bytes = v;
     else return fkm_set_error(FKM_EINVAL, "unknown knob %s", name);
@@ -644,40 +646,61 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
     } else {
         const uint64_t budget_keys = std::max<uint64_t>(kSortTile, (uint64_t)ctx->sort_budget_keys);
         const int n_pass = (2 * cfg->k + 7) / 8;
-        uint64_t key_cap = 0, tile_cap = 0, first_cap = 0;
-        std::vector<unsigned long long> kb; std::vector<unsigned int> tseg, st0;
-        int lo = 0;
-        while (lo < B) {
-            kb.clear(); kb.push_back(0); tseg.clear(); st0.clear(); st0.push_back(0);
-            int hi = lo; uint64_t nk = 0;
+        const uint64_t local_cap = LocalSort<WIDE>::kCap;
+        const size_t local_smem = (size_t)2 * local_cap * sizeof(Key) + local_cap * 2 + 16 * 256 * 4;
+        CKC(cudaFuncSetAttribute(k_radix_local<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)local_smem));
+        // plan every batch first, so that each scratch array is allocated once at its largest size
+        struct SortBatch { int lo, hi; uint64_t nk, n_tiles, max_bin; int bits; };   // bits: 0 no partition, 8/10 MSD partition, -1 LSD passes
+        std::vector<SortBatch> plan;
+        uint64_t max_nk = 0, max_tiles = 0, max_hist = 0, max_sdt = 1, max_chunks = 1;
+        for (int lo = 0; lo < B;) {
+            SortBatch sb; sb.lo = lo; sb.nk = 0; sb.n_tiles = 0; sb.max_bin = 0;
+            int hi = lo;
             while (hi < B) {
-                uint64_t c = h_kmer[(size_t)hi];
-                if (hi > lo && nk + c > budget_keys) break;
-                nk += c; kb.push_back(nk);
-                uint64_t nt = (c + kSortTile - 1) / kSortTile;
-                for (uint64_t t = 0; t < nt; t++) tseg.push_back((unsigned)(hi - lo));
-                st0.push_back((unsigned)tseg.size());
+                const uint64_t c = h_kmer[(size_t)hi];
+                if (hi > lo && sb.nk + c > budget_keys) break;
+                sb.nk += c; sb.n_tiles += (c + kSortTile - 1) / kSortTile; sb.max_bin = std::max(sb.max_bin, c);
                 hi++;
             }
-            const uint64_t n_tiles = tseg.size();
+            sb.hi = hi;
+            const uint64_t need = (sb.max_bin * 4 + local_cap - 1) / local_cap;      // sub-buckets wanted (4x head-room for skew)
+            // measured (profiles/README.md): the shared-memory chunk sort wins for 64-bit keys (config 3: 189 -> 158 ms),
+            // not for 128-bit keys (config 4 shape: 1258 -> 1328 ms), which keep the LSD passes.  debug_force_lsd: 1 = LSD, 2 = MSD.
+            const bool want_msd = ctx->debug_force_lsd >= 2.0 ? true : ctx->debug_force_lsd >= 1.0 ? false : !WIDE;
+            sb.bits = !want_msd ? -1 : need <= 1 ? 0 : need <= 256 ? 8 : need <= 1024 ? 10 : -1;
+            if (sb.bits > 2 * cfg->k) sb.bits = -1;
+            const uint64_t nd = sb.bits > 0 ? (1ull << sb.bits) : 256;
+            max_nk = std::max(max_nk, sb.nk); max_tiles = std::max(max_tiles, sb.n_tiles);
+            max_hist = std::max(max_hist, sb.n_tiles * nd);
+            if (sb.bits >= 0) {
+                max_sdt = std::max<uint64_t>(max_sdt, (uint64_t)(hi - lo) * (sb.bits ? nd : 1));
+                max_chunks = std::max<uint64_t>(max_chunks, 2 * sb.nk / local_cap + (uint64_t)(hi - lo) + 16);
+            }
+            plan.push_back(sb);
+            lo = hi;
+        }
+        unsigned int* d_sdt = nullptr; ChunkDesc* d_chunks = nullptr;
+        CKC(dmalloc(ctx, &d_keysA, std::max<uint64_t>(max_nk, 1) * sizeof(Key))); CKC(dmalloc(ctx, &d_keysB, std::max<uint64_t>(max_nk, 1) * sizeof(Key)));
+        CKC(dmalloc(ctx, &d_tile_seg, std::max<uint64_t>(max_tiles, 1) * 4)); CKC(dmalloc(ctx, &d_tile_hist, std::max<uint64_t>(max_hist, 1) * 4));
+        CKC(dmalloc(ctx, &d_tile_heads, (max_tiles + 1) * 4)); CKC(dmalloc(ctx, &d_seg_tile0, ((size_t)B + 1) * 4));
+        CKC(dmalloc(ctx, &d_sdt, max_sdt * 4)); CKC(dmalloc(ctx, &d_chunks, max_chunks * sizeof(ChunkDesc)));
+        CKC(dmalloc(ctx, &d_first, (max_nk + 1) * 8));          // run heads of one batch (at most one per key)
+        std::vector<unsigned long long> kb; std::vector<unsigned int> tseg, st0, sdt0;
+        for (const SortBatch& sb : plan) {
+            const int lo = sb.lo, hi = sb.hi;
+            const uint64_t nk = sb.nk, n_tiles = sb.n_tiles;
             const int n_seg = hi - lo;
             if (n_tiles == 0) {          // only empty bins: just carry the output offset forward
                 k_bin_offsets<<<1, 256, 0, s>>>(d_distinct, d_out_base, lo, hi, d_small); CKLC();
-                lo = hi;
                 continue;
             }
-            if (nk > key_cap) {
-                dfree(ctx, d_keysA); dfree(ctx, d_keysB); d_keysA = d_keysB = nullptr;
-                CKC(dmalloc(ctx, &d_keysA, (size_t)nk * sizeof(Key))); CKC(dmalloc(ctx, &d_keysB, (size_t)nk * sizeof(Key)));
-                key_cap = nk;
+            kb.clear(); kb.push_back(0); tseg.clear(); st0.clear(); st0.push_back(0); sdt0.clear();
+            for (int b = lo; b < hi; b++) {
+                const uint64_t c = h_kmer[(size_t)b];
+                kb.push_back(kb.back() + c); sdt0.push_back((unsigned)c);
+                for (uint64_t t = 0; t < (c + kSortTile - 1) / kSortTile; t++) tseg.push_back((unsigned)(b - lo));
+                st0.push_back((unsigned)tseg.size());
             }
-            if (n_tiles > tile_cap) {
-                dfree(ctx, d_tile_seg); dfree(ctx, d_tile_hist); dfree(ctx, d_tile_heads); d_tile_seg = d_tile_hist = d_tile_heads = nullptr;
-                CKC(dmalloc(ctx, &d_tile_seg, (size_t)n_tiles * 4)); CKC(dmalloc(ctx, &d_tile_hist, (size_t)n_tiles * 256 * 4));
-                CKC(dmalloc(ctx, &d_tile_heads, (size_t)(n_tiles + 1) * 4));
-                tile_cap = n_tiles;
-            }
-            if (!d_seg_tile0) CKC(dmalloc(ctx, &d_seg_tile0, ((size_t)B + 1) * 4));
             CKC(cudaMemcpyAsync(d_tbl_base, kb.data(), kb.size() * 8, cudaMemcpyHostToDevice, s));
             CKC(cudaMemcpyAsync(d_tile_seg, tseg.data(), (size_t)n_tiles * 4, cudaMemcpyHostToDevice, s));
             CKC(cudaMemcpyAsync(d_seg_tile0, st0.data(), st0.size() * 4, cudaMemcpyHostToDevice, s));
@@ -691,14 +714,52 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
             k_expand<WIDE><<<(unsigned)((nr + 255) / 256), 256, 0, s>>>(E); CKLC();
             SortParams Q;
             Q.seg_base = d_tbl_base; Q.tile_seg = d_tile_seg; Q.seg_tile0 = d_seg_tile0; Q.tile_hist = d_tile_hist;
-            Q.n_tiles = (unsigned)n_tiles; Q.n_seg = n_seg;
+            Q.n_tiles = (unsigned)n_tiles; Q.n_seg = n_seg; Q.seg_digit_tot = nullptr;
             void* in = d_keysA; void* out = d_keysB;
-            for (int p = 0; p < n_pass; p++) {
-                Q.in = in; Q.out = out; Q.shift = 8 * p;
-                k_radix_hist<WIDE><<<(unsigned)n_tiles, 256, 0, s>>>(Q); CKLC();
-                k_radix_scan<<<n_seg, 256, 0, s>>>(Q); CKLC();
-                k_radix_scatter<WIDE><<<(unsigned)n_tiles, 256, 0, s>>>(Q); CKLC();
-                std::swap(in, out);
+            bool sorted_done = false;
+            if (sb.bits >= 0) {
+                // MSD partition on the top bits (skipped when every bin already fits one chunk) ...
+                int nd = 1;
+                if (sb.bits > 0) {
+                    nd = 1 << sb.bits;
+                    Q.in = in; Q.out = out; Q.shift = 2 * cfg->k - sb.bits; Q.nd = nd; Q.seg_digit_tot = d_sdt;
+                    k_radix_hist<WIDE><<<(unsigned)n_tiles, 256, 0, s>>>(Q); CKLC();
+                    k_radix_scan<<<n_seg, 256, 0, s>>>(Q); CKLC();
+                    k_radix_scatter<WIDE><<<(unsigned)n_tiles, 256, 0, s>>>(Q); CKLC();
+                    Q.seg_digit_tot = nullptr;
+                } else {
+                    CKC(cudaMemcpyAsync(d_sdt, sdt0.data(), sdt0.size() * 4, cudaMemcpyHostToDevice, s));
+                }
+                // ... then chunks of <= local_cap keys, each sorted completely in shared memory
+                const uint64_t cap_chunks = 2 * nk / local_cap + (uint64_t)n_seg + 16;
+                CKC(cudaMemsetAsync(d_ovf, 0, 8, s));
+                k_form_chunks<<<(n_seg + 127) / 128, 128, 0, s>>>(d_tbl_base, d_sdt, n_seg, nd, (unsigned)local_cap, d_chunks,
+                                                                  (unsigned)cap_chunks, (unsigned int*)(d_ovf + 1), d_ovf); CKLC();
+                int flags[2] = {0, 0};
+                CKC(cudaMemcpyAsync(flags, d_ovf, 8, cudaMemcpyDeviceToHost, s));
+                CKC(cudaStreamSynchronize(s));
+                st->d2h_bytes += 8;
+                if (!flags[0]) {
+                    const void* src = sb.bits > 0 ? out : in;
+                    void* dst = sb.bits > 0 ? in : out;
+                    const unsigned n_chunks = (unsigned)flags[1];
+                    const unsigned grid = std::min<unsigned>(n_chunks, (unsigned)ctx->n_sm * 4);
+                    if (n_chunks) { k_radix_local<WIDE><<<grid, 512, local_smem, s>>>(src, dst, d_chunks, n_chunks, n_pass); CKLC(); }
+                    in = dst;
+                    sorted_done = true;
+                } else {
+                    st->n_fallbacks++;           // a sub-bucket larger than a chunk: LSD passes over the (untouched) expanded keys
+                }
+            }
+            if (!sorted_done) {
+                in = d_keysA; out = d_keysB;
+                for (int p = 0; p < n_pass; p++) {
+                    Q.in = in; Q.out = out; Q.shift = 8 * p; Q.nd = 256;
+                    k_radix_hist<WIDE><<<(unsigned)n_tiles, 256, 0, s>>>(Q); CKLC();
+                    k_radix_scan<<<n_seg, 256, 0, s>>>(Q); CKLC();
+                    k_radix_scatter<WIDE><<<(unsigned)n_tiles, 256, 0, s>>>(Q); CKLC();
+                    std::swap(in, out);
+                }
             }
             CKC(cudaEventRecord(ctx->ev[7], s));
             RleParams R;
@@ -717,11 +778,6 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
             cudaError_t e2 = dmalloc(ctx, &ch.cnt, (size_t)batch_total * 4);
             if (e2 != cudaSuccess) { dfree(ctx, ch.keys); CKC(e2); }
             res->chunks.push_back(ch);
-            if (batch_total + 1 > first_cap) {
-                dfree(ctx, d_first); d_first = nullptr;
-                CKC(dmalloc(ctx, &d_first, (size_t)(batch_total + 1) * 8));
-                first_cap = batch_total + 1;
-            }
             R.out_keys = ch.keys; R.out_cnt = ch.cnt; R.first_idx = d_first;
             k_rle<WIDE, 1><<<(unsigned)n_tiles, 256, 0, s>>>(R); CKLC();
             k_rle_counts<<<(unsigned)((batch_total + 255) / 256), 256, 0, s>>>(d_first, batch_total, nk, ch.cnt, 0); CKLC();
@@ -730,7 +786,6 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
             { float ms; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); ms_count += ms; cudaEventElapsedTime(&ms, ctx->ev[7], ctx->ev[8]); ms_compact += ms; }
             out_total += batch_total;
             st->n_batches++;
-            lo = hi;
         }
     }
     CKC(cudaEventRecord(ctx->ev[3], s));

@@ -328,6 +328,32 @@ def test_device_ingest_random_texts(ctx):
         assert np.array_equal(db, hb) and np.array_equal(di, hi)
 
 
+def test_sort_path_variants(oracle):
+    """useHT=0: MSD partition + shared-memory chunk sort (default), the no-partition case (small bins), the LSD
+    fallback when one sub-bucket is larger than a chunk, and forced LSD passes all give the reference's ordered output."""
+    rng = random.Random(77)
+    spec = dict(seeds=(61, 62, 63), genome_len=200000, n_reads=30000, read_len=150)
+    reads = fk.synth_fasta(spec).tobytes()
+    skew = (">poly\n" + "A" * 60000 + "\n>rnd\n" + "".join(rng.choice("ACGT") for _ in range(50000)) + "\n").encode()
+    c2 = fk.Context(0)
+    try:
+        for text, B, expect_fallback in ((reads, 2048, False), (reads, 4, False), (reads, 1, False), (skew, 64, True)):
+            for k, m in ((28, 10), (55, 13), (31, 11)):
+                want = oracle.count(text, k, m, 3, B, 0, threads=8)
+                c2.set("debug_force_lsd", 2)
+                res, st = c2.count_fasta(cfg(k, m, 3, B, 0), text)
+                assert_same(res.arrays(), want, "msd B=%d k=%d" % (B, k))          # already in file order
+                assert (st["n_fallbacks"] > 0) == expect_fallback
+                c2.set("debug_force_lsd", 0)
+                res, st = c2.count_fasta(cfg(k, m, 3, B, 0), text)
+                assert_same(res.arrays(), want, "auto B=%d k=%d" % (B, k))
+                c2.set("debug_force_lsd", 1)
+                res, st = c2.count_fasta(cfg(k, m, 3, B, 0), text)
+                assert_same(res.arrays(), want, "lsd B=%d k=%d" % (B, k))
+    finally:
+        c2.close()
+
+
 def test_streamed_fasta_chunks(oracle):
     """FASTA text is copied and parsed in chunks cut at record boundaries: any chunk size gives the same counts."""
     rng = random.Random(123)
