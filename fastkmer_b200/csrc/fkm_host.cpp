@@ -88,6 +88,12 @@ static int mkdir_p(const std::string& dir) {
     return 0;
 }
 
+int fkm_make_dirs(const char* dir) {
+    if (mkdir_p(dir) != 0) return fkm_set_error(FKM_EIO, "cannot create %s: %s", dir, strerror(errno));
+    return FKM_OK;
+}
+
+// host-side formatter (kept for reference / small results; fkm_result_write formats on the device)
 int fkm_write_bins(const char* out_dir, int32_t B, int32_t k, int sorted, const uint64_t* out_base,
                    const uint64_t* hi, const uint64_t* lo, const uint32_t* cnt) {
     if (mkdir_p(out_dir) != 0) return fkm_set_error(FKM_EIO, "cannot create %s: %s", out_dir, strerror(errno));

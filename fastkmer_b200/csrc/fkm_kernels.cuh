@@ -1170,6 +1170,68 @@ __global__ void __launch_bounds__(256) k_digest(const DigestParams P) {
     }
 }
 
+// ------------------------------------------------------------------ K7: text output (SBKC:579-606, 725-734; UTIL:416-454)
+// Lines "<k letters>\t<decimal count>\n" for entries [first, first+n) of a result chunk.  Tile = 256 entries.
+// PASS 0: bytes per tile.  PASS 1: format into shared memory, then one coalesced copy to `text`.
+struct FmtParams {
+    const void* keys; const uint32_t* cnt; unsigned long long first, n; int k;
+    unsigned long long* tile_off;     // [n_tiles+1] bytes per tile -> (after the scan) text offset of each tile
+    uint8_t* text;
+    const unsigned long long* bounds; unsigned long long* bound_off; int n_bounds;   // entry index -> text offset (bin boundaries)
+};
+__device__ __forceinline__ int dec_digits(uint32_t v) {
+    return v < 10u ? 1 : v < 100u ? 2 : v < 1000u ? 3 : v < 10000u ? 4 : v < 100000u ? 5 : v < 1000000u ? 6 :
+           v < 10000000u ? 7 : v < 100000000u ? 8 : v < 1000000000u ? 9 : 10;
+}
+template <bool WIDE, int PASS>
+__global__ void __launch_bounds__(256) k_fmt(const FmtParams P) {
+    __shared__ unsigned int s_warp[8];
+    __shared__ uint8_t s_text[PASS ? 256 * (64 + 12) : 4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x;
+    uint32_t c = 0; unsigned int len = 0;
+    if (i < P.n) { c = P.cnt[P.first + i]; len = (unsigned)P.k + 2u + (unsigned)dec_digits(c); }
+    unsigned int incl = len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { unsigned int t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned int wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { unsigned int t = s_warp[w]; if (w < warp) wbase += t; total += t; }
+    if (PASS == 0) { if (threadIdx.x == 0) P.tile_off[blockIdx.x] = total; return; }
+    if (i < P.n) {
+        uint8_t* o = s_text + wbase + incl - len;
+        uint64_t hi = 0, lo;
+        if constexpr (!WIDE) lo = reinterpret_cast<const uint64_t*>(P.keys)[P.first + i];
+        else { key128 kk = reinterpret_cast<const key128*>(P.keys)[P.first + i]; hi = kk.hi; lo = kk.lo; }
+        for (int j = 0; j < P.k; j++) {                       // first base most significant (UTIL:416-454)
+            const int bit = 2 * (P.k - 1 - j);
+            const unsigned int sym = (unsigned int)((bit >= 64 ? (hi >> (bit - 64)) : (lo >> bit)) & 3ull);
+            o[j] = (uint8_t)"ACGT"[sym];
+        }
+        o[P.k] = (uint8_t)'\t';
+        const int nd = dec_digits(c);
+        uint32_t v = c;
+        for (int j = nd - 1; j >= 0; j--) { o[P.k + 1 + j] = (uint8_t)('0' + v % 10u); v /= 10u; }
+        o[P.k + 1 + nd] = (uint8_t)'\n';
+    }
+    __syncthreads();
+    const unsigned long long base = P.tile_off[blockIdx.x];
+    for (unsigned int j = threadIdx.x; j < total; j += 256) P.text[base + j] = s_text[j];
+}
+// text offset of entry bounds[b] (relative to `first`): its tile's offset plus the lines before it in the tile
+template <bool WIDE>
+__global__ void k_fmt_bounds(const FmtParams P) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= P.n_bounds) return;
+    const unsigned long long e = P.bounds[b];                 // 0 <= e <= n
+    const unsigned long long tile = e >> 8;
+    unsigned long long off = P.tile_off[tile];
+    for (unsigned long long i = tile << 8; i < e; i++) off += (unsigned)P.k + 2u + (unsigned)dec_digits(P.cnt[P.first + i]);
+    P.bound_off[b] = off;
+}
+
 // ------------------------------------------------------------------ synthetic reads
 struct SynthParams { SynthSpec S; uint64_t n_pos, n_words; uint64_t* bases; uint32_t* inv; };
 // one thread per 32 positions; position p -> read p/(L+1), offset p%(L+1); offset L is the separator

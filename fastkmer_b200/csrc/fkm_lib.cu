@@ -1167,11 +1167,85 @@ extern "C" int fkm_result_copy(const fkm_result* r, int32_t* bin, uint64_t* key_
             for (uint64_t i = r->out_base[(size_t)b]; i < r->out_base[(size_t)b + 1]; i++) bin[i] = b;
     return FKM_OK;
 }
+// Per-bin text files (SBKC:550-606 sort path with the "EOF" trailer, SBKC:715-734 HT path).  The lines are
+// formatted on the device (k_fmt), copied to pinned host memory in pieces and appended to <out_dir>/bin<id>.
+template <bool WIDE>
+static int write_result_device(fkm_ctx* ctx, const fkm_result* r, const char* out_dir) {
+    typedef typename Traits<WIDE>::Key Key;
+    cudaStream_t s = ctx->stream;
+    int rc = fkm_make_dirs(out_dir); if (rc) return rc;
+    const uint64_t piece = (uint64_t)32 << 20;                                   // entries per device pass
+    const uint64_t max_line = (uint64_t)r->k + 12;
+    const uint64_t n_tiles_max = (piece + 255) / 256;
+    unsigned long long *d_tile = nullptr, *d_bounds = nullptr, *d_boff = nullptr; uint8_t* d_text = nullptr;
+    const Arena::Mark mk = ctx->arena.mark();
+    CK(dmalloc(ctx, &d_tile, (n_tiles_max + 1) * 8));
+    CK(dmalloc(ctx, &d_bounds, ((size_t)r->B + 2) * 8)); CK(dmalloc(ctx, &d_boff, ((size_t)r->B + 2) * 8));
+    CK(dmalloc(ctx, (void**)&d_text, std::min<uint64_t>(piece, std::max<uint64_t>(r->total, 1)) * max_line));
+    uint8_t* h_text = nullptr;
+    CK(cudaMallocHost((void**)&h_text, std::min<uint64_t>(piece, std::max<uint64_t>(r->total, 1)) * max_line));
+    std::vector<unsigned long long> bounds, boff;
+    std::vector<int> bbin;
+    FILE* f = nullptr; int open_bin = -1;
+    auto close_bin = [&]() { if (f) { if (r->sorted) fputs("EOF", f); fclose(f); f = nullptr; } };
+    uint64_t origin = 0;
+    int bin = 0;
+    rc = FKM_OK;
+    for (const Chunk& ch : r->chunks) {
+        for (uint64_t first = 0; first < ch.n && !rc; first += piece) {
+            const uint64_t n = std::min(piece, ch.n - first);
+            const uint64_t g0 = origin + first, g1 = g0 + n;                     // global entry range of this piece
+            // bin boundaries inside the piece
+            bounds.clear(); bbin.clear();
+            while (bin < r->B && r->out_base[(size_t)bin + 1] <= g0) bin++;
+            int b = bin;
+            bounds.push_back(0); bbin.push_back(b);
+            while (b < r->B && r->out_base[(size_t)b + 1] < g1) { b++; bounds.push_back(r->out_base[(size_t)b] - g0); bbin.push_back(b); }
+            bounds.push_back(n);
+            FmtParams P;
+            P.keys = ch.keys; P.cnt = ch.cnt; P.first = first; P.n = n; P.k = r->k; P.tile_off = d_tile; P.text = d_text;
+            P.bounds = d_bounds; P.bound_off = d_boff; P.n_bounds = (int)bounds.size();
+            const unsigned n_tiles = (unsigned)((n + 255) / 256);
+            auto fail = [&](cudaError_t e) { return fkm_set_error(FKM_ECUDA, "text output: %s", cudaGetErrorString(e)); };
+            cudaError_t e = cudaMemcpyAsync(d_bounds, bounds.data(), bounds.size() * 8, cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) { rc = fail(e); break; }
+            k_fmt<WIDE, 0><<<n_tiles, 256, 0, s>>>(P); g_launches++;
+            k_scan1<0><<<1, 1024, 0, s>>>((long long*)d_tile, n_tiles); g_launches++;
+            k_fmt<WIDE, 1><<<n_tiles, 256, 0, s>>>(P); g_launches++;
+            k_fmt_bounds<WIDE><<<(P.n_bounds + 127) / 128, 128, 0, s>>>(P); g_launches++;
+            boff.resize(bounds.size());
+            e = cudaMemcpyAsync(boff.data(), d_boff, bounds.size() * 8, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) { rc = fail(e); break; }
+            e = cudaMemcpyAsync(h_text, d_text, boff.back(), cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) { rc = fail(e); break; }
+            for (size_t j = 0; j + 1 < bounds.size(); j++) {
+                if (boff[j + 1] == boff[j]) continue;
+                if (bbin[j] != open_bin) {
+                    close_bin();
+                    const std::string path = std::string(out_dir) + "/bin" + std::to_string(bbin[j]);
+                    f = fopen(path.c_str(), "wb"); open_bin = bbin[j];
+                    if (!f) { rc = fkm_set_error(FKM_EIO, "cannot create %s", path.c_str()); break; }
+                }
+                if (fwrite(h_text + boff[j], 1, boff[j + 1] - boff[j], f) != boff[j + 1] - boff[j]) { rc = fkm_set_error(FKM_EIO, "short write under %s", out_dir); break; }
+            }
+        }
+        origin += ch.n;
+        if (rc) break;
+    }
+    close_bin();
+    cudaFreeHost(h_text);
+    ctx->arena.release(mk);
+    return rc;
+}
+
 extern "C" int fkm_result_write(const fkm_result* r, const char* out_dir) {
     if (!r || !out_dir) return fkm_set_error(FKM_EINVAL, "null argument");
-    std::vector<uint64_t> hi(r->total), lo(r->total); std::vector<uint32_t> cnt(r->total);
-    int rc = fkm_result_copy(r, nullptr, hi.data(), lo.data(), cnt.data()); if (rc) return rc;
-    return fkm_write_bins(out_dir, r->B, r->k, r->sorted, r->out_base.data(), hi.data(), lo.data(), cnt.data());
+    if (r->total && r->gen != r->ctx->gen)
+        return fkm_set_error(FKM_EINVAL, "result was invalidated by a later job on the same context (write it first)");
+    CK(cudaSetDevice(r->device));
+    return r->wide ? write_result_device<true>(r->ctx, r, out_dir) : write_result_device<false>(r->ctx, r, out_dir);
 }
 extern "C" void fkm_result_free(fkm_result* r) { delete r; }   // device arrays belong to the context arena
 

@@ -268,6 +268,29 @@ def test_execute_job_writes_reference_layout(ctx, oracle, tmp_path, ht):
     assert not (tmp_path / "none").exists()
 
 
+@pytest.mark.parametrize("k,m,ht", [(28, 10, 0), (55, 13, 1), (33, 9, 0)])
+def test_device_formatted_files_at_depth(ctx, oracle, tmp_path, k, m, ht):
+    """Counts with 1-3 digits, 64- and 128-bit k-mers, several bins per device pass: every file byte-identical
+    to the reference layout built from the oracle."""
+    spec = dict(seeds=(71, 72, 73), genome_len=3000, n_reads=20000, read_len=150)       # 1000x coverage
+    fasta = fk.synth_fasta(spec).tobytes()
+    want = oracle.count(fasta, k, m, 3, 512, ht, threads=8)
+    assert int(want["cnt"].max()) >= 100
+    res, st = ctx.count_fasta(cfg(k, m, 3, 512, ht), fasta)
+    out = tmp_path / "o"
+    res.write(str(out))
+    by_bin = {}
+    for b, h, l, c in zip(want["bin"], want["hi"], want["lo"], want["cnt"]):
+        by_bin.setdefault(int(b), []).append(b"%s\t%d\n" % (oracle_lib.kmer_str(h, l, k).encode(), int(c)))
+    assert sorted(os.listdir(out)) == sorted("bin%d" % b for b in by_bin)
+    for b, lines in by_bin.items():
+        data = (out / ("bin%d" % b)).read_bytes()
+        if ht:
+            assert sorted(data.splitlines(keepends=True)) == sorted(lines)
+        else:
+            assert data == b"".join(lines) + b"EOF"
+
+
 def test_cli_matches_reference_argv(oracle, tmp_path):
     fasta = oracle.gen_lcg_fasta(45, 300, 60, 40)
     inp = tmp_path / "g4.fasta"
