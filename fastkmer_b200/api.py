@@ -94,6 +94,7 @@ def load_library():
         "fkm_mg_scatter": (C.c_int, [vp, vp, vp]),
         "fkm_mg_regroup": (C.c_int, [vp, cfgp, vp, u64, vp, vp, u64, C.POINTER(vp)]),
         "fkm_mg_count": (C.c_int, [vp, cfgp, vp, vp, vp, C.POINTER(vp), stp]),
+        "fkm_multiseq_fasta": (C.c_int, [vp, cfgp, vp, u64, i32, C.POINTER(i32), C.c_char_p, vp, C.POINTER(vp), stp]),
         "fkm_debug_pack_fasta_device": (C.c_int, [vp, vp, u64, vp, vp, u64, C.POINTER(u64), C.POINTER(u64)]),
         "fkm_total_launches": (u64, []),
     }
@@ -382,6 +383,19 @@ class Context:
         _check(load_library().fkm_mg_count(self._h, C.byref(cfg), C.c_void_p(d_records), bin_rec.ctypes.data, bin_kmer.ctypes.data,
                                            C.byref(h) if want_result else None, C.byref(st)))
         return (CountResult(h, configuration.k, self) if want_result else None), _stats(st)
+
+    def multiseq_fasta(self, configuration, fasta, max_samples=64, want_result=False):
+        """Multi-sample job (skc.multisequence).  -> (sample names, S x S float64 squared-euclidean distances,
+        merged CountResult | None, Stats)"""
+        arr = np.frombuffer(fasta, dtype=np.uint8) if isinstance(fasta, (bytes, bytearray)) else fasta
+        st, cfg, h, ns = fkm_stats(), _cfg(configuration), C.c_void_p(), C.c_int32()
+        names = C.create_string_buffer(64 * max_samples)
+        dist = np.zeros((max_samples, max_samples), dtype=np.float64)
+        _check(load_library().fkm_multiseq_fasta(self._h, C.byref(cfg), arr.ctypes.data, arr.size, max_samples, C.byref(ns), names,
+                                                 dist.ctypes.data, C.byref(h) if want_result else None, C.byref(st)))
+        S = ns.value
+        tags = [names.raw[64 * i:64 * (i + 1)].split(b"\0", 1)[0].decode() for i in range(S)]
+        return tags, dist[:S, :S].copy(), (CountResult(h, configuration.k, self) if want_result else None), _stats(st)
 
     def pack_fasta_device(self, fasta: bytes):
         """Device ingest of FASTA text, copied back: (bases, inv, n_positions, n_bases) — test hook."""

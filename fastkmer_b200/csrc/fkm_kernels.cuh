@@ -1232,6 +1232,40 @@ __global__ void k_fmt_bounds(const FmtParams P) {
     P.bound_off[b] = off;
 }
 
+// ------------------------------------------------------------------ K8: multi-sample distances
+// (MSKC:458-520, multiseq/SquaredEuclidean.java:19-27.)  Two per-bin sorted results A and B of the same
+// configuration: acc += sum over k-mers present in both of cntA * cntB (a sparse dot product; the squared
+// euclidean distance of the count vectors is dot(A,A) + dot(B,B) - 2 dot(A,B)).  One thread per entry of A,
+// binary search inside the same bin of B.
+struct DotParams {
+    const void* keysA; const uint32_t* cntA; const unsigned long long* baseA; unsigned long long nA;
+    const void* keysB; const uint32_t* cntB; const unsigned long long* baseB;
+    int B; unsigned long long* acc;
+};
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_sparse_dot(const DotParams P) {
+    typedef typename Traits<WIDE>::Key Key;
+    const Key* ka = reinterpret_cast<const Key*>(P.keysA); const Key* kb = reinterpret_cast<const Key*>(P.keysB);
+    unsigned long long sum = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.nA;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const int bin = find_bin(P.baseA, 0, P.B, i);
+        unsigned long long lo = P.baseB[bin], hi = P.baseB[bin + 1];
+        const Key key = ka[i];
+        while (lo < hi) {
+            const unsigned long long mid = (lo + hi) >> 1;
+            const Key km = kb[mid];
+            bool less;
+            if constexpr (!WIDE) less = km < key; else less = key_less(km, key);
+            if (less) lo = mid + 1; else hi = mid;
+        }
+        if (lo < P.baseB[bin + 1] && key_eq(kb[lo], key)) sum += (unsigned long long)P.cntA[i] * (unsigned long long)P.cntB[lo];
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+    if ((threadIdx.x & 31) == 0 && sum) atomicAdd(P.acc, sum);
+}
+
 // ------------------------------------------------------------------ synthetic reads
 struct SynthParams { SynthSpec S; uint64_t n_pos, n_words; uint64_t* bases; uint32_t* inv; };
 // one thread per 32 positions; position p -> read p/(L+1), offset p%(L+1); offset L is the separator

@@ -111,6 +111,7 @@ static inline void dfree(fkm_ctx*, void*) {}
 
 struct Chunk { void* keys = nullptr; uint32_t* cnt = nullptr; uint64_t n = 0; };
 struct fkm_result {
+    bool eof_trailer = true;                      // sorted files end with "EOF" (SBKC:606); the multisequence writer has none (MSKC:524-526)
     fkm_ctx* ctx = nullptr; uint64_t gen = 0;     // arrays live in ctx's arena until its next job
     int device = 0;
     int32_t B = 0, k = 0; bool wide = false; bool sorted = false;
@@ -1131,6 +1132,121 @@ extern "C" int fkm_mg_count(fkm_ctx* ctx, const fkm_config* cfg, const void* d_r
     return count_device(ctx, cfg, nullptr, nullptr, 0, out, stats, &pre);
 }
 
+// ------------------------------------------------------------------ multi-sample distances
+// The reference's prototype (skc.multisequence, MSKC:29-165,300-547) tags super-k-mers with the sample a read came
+// from, keeps per-sample counts of every distinct k-mer of a bin and adds (c_a - c_b)^2 to the distance of every
+// sample pair (multiseq/SquaredEuclidean.java:19-32); the shipped job never executes (MSKC:585-588), so the
+// semantics are the intended ones of SURVEY App. A.7: the sample of a read is the leading \w+ of its header.
+// Here: reads are split by sample on the host, every sample is counted with the sorted pipeline, and
+// k_sparse_dot gives sum_k c_a(k) c_b(k) for every pair, all in 64-bit integers.
+struct SampleCounts { void* keys = nullptr; uint32_t* cnt = nullptr; unsigned long long* base = nullptr; uint64_t n = 0; };
+
+extern "C" int fkm_multiseq_fasta(fkm_ctx* ctx, const fkm_config* cfg, const uint8_t* fasta, uint64_t n_bytes, int32_t max_samples,
+                                  int32_t* n_samples, char* names, double* dist, fkm_result** merged, fkm_stats* stats) {
+    if (!ctx || !n_samples || !dist || max_samples < 1) return fkm_set_error(FKM_EINVAL, "bad argument");
+    int32_t B = 0; int rc = validate(cfg, &B); if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    // ---- split the records by sample tag (first run of [A-Za-z0-9_] of the header)
+    std::vector<std::string> tags; std::vector<std::vector<uint8_t>> texts;
+    {
+        const uint8_t* t = fasta; uint64_t i = 0; bool bol = true;
+        while (i < n_bytes && !(bol && t[i] == '>')) { bol = (t[i] == '\n'); i++; }
+        while (i < n_bytes) {
+            const uint64_t rec0 = i;
+            uint64_t j = i + 1;
+            auto isw = [](uint8_t c) { return (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z') || (c >= '0' && c <= '9') || c == '_'; };
+            while (j < n_bytes && t[j] != '\n' && !isw(t[j])) j++;
+            uint64_t e = j; while (e < n_bytes && isw(t[e])) e++;
+            std::string tag((const char*)t + j, (size_t)(e - j));
+            while (i < n_bytes && t[i] != '\n') i++;
+            if (i < n_bytes) i++;
+            bol = true;
+            while (i < n_bytes && !(bol && t[i] == '>')) { bol = (t[i] == '\n'); i++; }
+            size_t sidx = 0; while (sidx < tags.size() && tags[sidx] != tag) sidx++;
+            if (sidx == tags.size()) {
+                if ((int32_t)tags.size() == max_samples) return fkm_set_error(FKM_EINVAL, "more than %d samples in the input", max_samples);
+                tags.push_back(tag); texts.emplace_back();
+            }
+            texts[sidx].insert(texts[sidx].end(), t + rec0, t + i);
+            if (texts[sidx].empty() || texts[sidx].back() != '\n') texts[sidx].push_back('\n');
+        }
+    }
+    const int S = (int)tags.size();
+    *n_samples = S;
+    if (names) for (int a = 0; a < S; a++) { memset(names + 64 * a, 0, 64); strncpy(names + 64 * a, tags[a].c_str(), 63); }
+    for (int a = 0; a < max_samples * max_samples; a++) dist[a] = 0.0;
+    // ---- count every sample (sorted per bin), keep the results in plain device memory
+    fkm_config c2 = *cfg; c2.use_ht = 0; if (c2.x < 1) c2.x = 1;
+    const bool wide = cfg->k > 32;
+    const size_t ksz = wide ? 16 : 8;
+    std::vector<SampleCounts> sc((size_t)S);
+    auto release = [&]() { for (auto& q : sc) { cudaFree(q.keys); cudaFree(q.cnt); cudaFree(q.base); } };
+    fkm_stats total; memset(&total, 0, sizeof total);
+    for (int a = 0; a < S && !rc; a++) {
+        fkm_result* r = nullptr; fkm_stats st;
+        rc = fkm_count_fasta(ctx, &c2, texts[(size_t)a].data(), texts[(size_t)a].size(), &r, &st);
+        if (rc) break;
+        SampleCounts& q = sc[(size_t)a];
+        q.n = r->total;
+        cudaError_t e = cudaMalloc(&q.keys, std::max<uint64_t>(q.n, 1) * ksz);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&q.cnt, std::max<uint64_t>(q.n, 1) * 4);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&q.base, ((size_t)B + 1) * 8);
+        uint64_t o = 0;
+        for (const Chunk& ch : r->chunks) {
+            if (e != cudaSuccess || !ch.n) continue;
+            e = cudaMemcpyAsync((char*)q.keys + o * ksz, ch.keys, ch.n * ksz, cudaMemcpyDeviceToDevice, ctx->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(q.cnt + o, ch.cnt, ch.n * 4, cudaMemcpyDeviceToDevice, ctx->stream);
+            o += ch.n;
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(q.base, r->out_base.data(), ((size_t)B + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        fkm_result_free(r);
+        if (e != cudaSuccess) rc = fkm_set_error(FKM_ECUDA, "multiseq copy: %s", cudaGetErrorString(e));
+        total.n_bases += st.n_bases; total.n_kmers += st.n_kmers; total.n_distinct += st.n_distinct; total.total_count += st.total_count;
+        total.gpu_launches += st.gpu_launches; total.h2d_bytes += st.h2d_bytes; total.d2h_bytes += st.d2h_bytes; total.ms_total += st.ms_total;
+    }
+    // ---- pairwise sparse dot products
+    std::vector<unsigned long long> dot((size_t)S * S, 0);
+    if (!rc && S) {
+        unsigned long long* d_acc = nullptr;
+        cudaError_t e = cudaMalloc((void**)&d_acc, (size_t)S * S * 8);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_acc, 0, (size_t)S * S * 8, ctx->stream);
+        for (int a = 0; a < S && e == cudaSuccess; a++)
+            for (int b = a; b < S; b++) {
+                if (!sc[(size_t)a].n || !sc[(size_t)b].n) continue;
+                DotParams P;
+                P.keysA = sc[(size_t)a].keys; P.cntA = sc[(size_t)a].cnt; P.baseA = sc[(size_t)a].base; P.nA = sc[(size_t)a].n;
+                P.keysB = sc[(size_t)b].keys; P.cntB = sc[(size_t)b].cnt; P.baseB = sc[(size_t)b].base; P.B = B; P.acc = d_acc + (size_t)a * S + b;
+                const int grid = (int)std::min<uint64_t>((P.nA + 255) / 256, (uint64_t)ctx->n_sm * 8);
+                if (wide) k_sparse_dot<true><<<grid, 256, 0, ctx->stream>>>(P); else k_sparse_dot<false><<<grid, 256, 0, ctx->stream>>>(P);
+                g_launches++; total.gpu_launches++;
+            }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dot.data(), d_acc, (size_t)S * S * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        cudaFree(d_acc);
+        if (e != cudaSuccess) rc = fkm_set_error(FKM_ECUDA, "multiseq distances: %s", cudaGetErrorString(e));
+    }
+    release();
+    if (rc) return rc;
+    for (int a = 0; a < S; a++)
+        for (int b = a + 1; b < S; b++) {
+            // sum_k (c_a - c_b)^2 = dot(a,a) + dot(b,b) - 2 dot(a,b), exact in 64-bit integers, then to double
+            const unsigned long long v = dot[(size_t)a * S + a] + dot[(size_t)b * S + b] - 2ull * dot[(size_t)a * S + b];
+            dist[(size_t)a * max_samples + b] = dist[(size_t)b * max_samples + a] = (double)v;
+        }
+    // ---- the merged counts (kmer, sum over samples): the ordinary job on the whole input (MSKC:487,524)
+    if (merged || cfg->write) {
+        fkm_result* r = nullptr; fkm_stats st;
+        rc = fkm_count_fasta(ctx, &c2, fasta, n_bytes, &r, &st); if (rc) return rc;
+        r->eof_trailer = false;
+        total.n_nonempty_bins = st.n_nonempty_bins; total.digest_sum = st.digest_sum; total.digest_xor = st.digest_xor;
+        total.gpu_launches += st.gpu_launches; total.ms_total += st.ms_total;
+        if (merged) *merged = r; else fkm_result_free(r);
+    }
+    if (stats) *stats = total;
+    return FKM_OK;
+}
+
 // ------------------------------------------------------------------ results
 extern "C" uint64_t fkm_result_size(const fkm_result* r) { return r ? r->total : 0; }
 extern "C" int32_t fkm_result_num_bins(const fkm_result* r) { return r ? r->B : 0; }
@@ -1187,7 +1303,7 @@ static int write_result_device(fkm_ctx* ctx, const fkm_result* r, const char* ou
     std::vector<unsigned long long> bounds, boff;
     std::vector<int> bbin;
     FILE* f = nullptr; int open_bin = -1;
-    auto close_bin = [&]() { if (f) { if (r->sorted) fputs("EOF", f); fclose(f); f = nullptr; } };
+    auto close_bin = [&]() { if (f) { if (r->sorted && r->eof_trailer) fputs("EOF", f); fclose(f); f = nullptr; } };
     uint64_t origin = 0;
     int bin = 0;
     rc = FKM_OK;

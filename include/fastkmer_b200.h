@@ -186,6 +186,15 @@ int  fkm_mg_regroup(fkm_ctx* ctx, const fkm_config* cfg, const void* d_recv, uin
 int  fkm_mg_count(fkm_ctx* ctx, const fkm_config* cfg, const void* d_records, const uint64_t* bin_rec, const uint64_t* bin_kmer,
                   fkm_result** out, fkm_stats* stats);
 
+/* ---- multi-sample distances (skc.multisequence) -----------------
+ * Reads carry a sample tag = the leading run of [A-Za-z0-9_] of their header.  For every pair of samples
+ * dist[a*max_samples + b] = sum over distinct canonical k-mers of (c_a - c_b)^2 (squared euclidean distance of the
+ * per-sample count vectors: SparkMultiSequenceKmerCounter.scala:458-520, multiseq/SquaredEuclidean.java:19-32).
+ * names receives max_samples x 64 bytes (NUL-padded tags in order of first appearance) or may be NULL.  *merged, when
+ * requested, holds (k-mer, sum of counts) per bin, ascending, written without the "EOF" trailer (MSKC:487,524).  */
+int  fkm_multiseq_fasta(fkm_ctx* ctx, const fkm_config* cfg, const uint8_t* fasta, uint64_t n_bytes, int32_t max_samples,
+                        int32_t* n_samples, char* names, double* dist, fkm_result** merged, fkm_stats* stats);
+
 /* ---- test hooks (stage-level parity against the oracle) ----------------------- */
 /* bin of every window start (−1 where the k-window holds an invalid position);
  * bins_out has n_positions entries.                                             */

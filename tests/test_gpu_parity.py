@@ -426,3 +426,80 @@ def test_multigpu_stages_emulated(ctx, oracle, world, k, m, ht):
     for sh in shards:
         ctx.free_device(sh[0])
         ctx.free_device(sh[1])
+
+
+# ---------------------------------------------------------------- multi-sample distances (BASELINE config 5 shape)
+def _multiseq_input(n_samples, reads_per_sample, L, seed):
+    """Samples = a common ancestor with per-sample substitutions; reads of all samples interleaved, header 'S<s>.<r> ...'."""
+    rng = random.Random(seed)
+    anc = [rng.choice("ACGT") for _ in range(8000)]
+    recs = []
+    for s_ in range(n_samples):
+        g = list(anc)
+        for i in range(len(g)):
+            if rng.random() < 0.02:
+                g[i] = rng.choice("ACGT")
+        for r in range(reads_per_sample):
+            p = rng.randrange(0, len(g) - L)
+            read = "".join(g[p:p + L])
+            if rng.random() < 0.5:
+                read = clean_spec.revcomp(read)
+            if rng.random() < 0.1:
+                q = rng.randrange(L)
+                read = read[:q] + "N" + read[q + 1:]
+            recs.append((rng.random(), ">S%d.%d len=%d\n%s\n" % (s_, r, L, read)))
+    recs.sort()
+    return "".join(t for _, t in recs)
+
+
+def _multiseq_expected(oracle, fasta, k, m, B):
+    import re
+    texts, order = {}, []
+    for rec in re.split(r"(?m)^(?=>)", fasta):
+        if not rec:
+            continue
+        tag = re.match(r">\W*(\w+)", rec).group(1)
+        if tag not in texts:
+            texts[tag] = []
+            order.append(tag)
+        texts[tag].append(rec)
+    counts = []
+    for tag in order:
+        res = oracle.count("".join(texts[tag]).encode(), k, m, 3, B, 1, threads=8)
+        counts.append({(int(b), int(h), int(l)): int(c) for b, h, l, c in zip(res["bin"], res["hi"], res["lo"], res["cnt"])})
+    S = len(order)
+    keys = set().union(*[set(c) for c in counts]) if counts else set()
+    dist = np.zeros((S, S))
+    for a in range(S):
+        for b in range(a + 1, S):
+            d = sum((counts[a].get(key, 0) - counts[b].get(key, 0)) ** 2 for key in keys)   # SquaredEuclidean.java:19-27
+            dist[a, b] = dist[b, a] = d
+    return order, dist
+
+
+@pytest.mark.parametrize("k,m", [(28, 10), (55, 13), (12, 5)])
+def test_multisequence_distances(ctx, oracle, tmp_path, k, m):
+    fasta = _multiseq_input(5, 300, 100, 4242 + k)
+    c = cfg(k, m, 3, 2048, 0)
+    names, dist, res, st = ctx.multiseq_fasta(c, fasta.encode(), want_result=True)
+    want_names, want_dist = _multiseq_expected(oracle, fasta, k, m, 2048)
+    assert names == want_names
+    assert np.array_equal(dist, want_dist) and dist.max() > 0          # integer-valued doubles: exact
+    whole = oracle.count(fasta.encode(), k, m, 3, 2048, 0, threads=8)    # the files hold kmer<TAB>sum of the per-sample counts
+    assert_same(res.arrays(), whole, "merged counts")
+    res.write(str(tmp_path / "ms"))
+    some = sorted(os.listdir(tmp_path / "ms"))[0]
+    body = (tmp_path / "ms" / some).read_bytes()
+    assert body.endswith(b"\n") and not body.endswith(b"EOF")             # no trailer in this writer (MSKC:524-526)
+
+
+def test_multisequence_mirror(ctx, tmp_path):
+    from fastkmer_b200.multisequence import MultisequenceTestConfiguration, SparkMultiSequenceKmerCounter
+    fasta = _multiseq_input(3, 100, 80, 99)
+    inp = tmp_path / "samples.fasta"
+    inp.write_text(fasta)
+    tc = MultisequenceTestConfiguration(str(inp), str(tmp_path) + "/", 20, 6, 3, max_b=100, write=True)
+    names, dist = SparkMultiSequenceKmerCounter.executeJob(ctx, tc)
+    assert names == ["S%d" % i for i in sorted(range(3), key=lambda s_: fasta.index(">S%d." % s_))]
+    assert dist.shape == (3, 3) and (dist == dist.T).all() and (np.diag(dist) == 0).all()
+    assert (tmp_path / "k20_m6_x3_b100_s0").is_dir()                      # multisequence/package.scala:29
