@@ -89,10 +89,10 @@ class Workload:
         """bounded sample of the same workload for the CPU oracle -> (fasta uint8 array, description)"""
         c = self.c
         if self.kind == "reads":
-            reads = min(c["reads"], 500_000)
+            reads = min(c["reads"], 5_000_000)            # ~10 s of work for 16 host threads
             sp = dict(seeds=c["seeds"], genome_len=reads * c["L"] // c["cov"], n_reads=reads, read_len=c["L"])
             return fk.synth_fasta(sp), "%d reads x %d bp of the same generator" % (reads, c["L"])
-        n = min(c["n_bases"], 40_000_000)
+        n = min(c["n_bases"], 100_000_000)
         return fk.synth_long_fasta(dict(seeds=c["seeds"], n_bases=n)), "first %d bp of the same synthetic genome" % n
 
 
