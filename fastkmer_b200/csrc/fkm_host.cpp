@@ -1,6 +1,6 @@
-// fkm_host.cpp — host side of the path: FASTA record split + 2-bit packing (replaces
-// the FASTdoop record readers, SBKC:62-65,1009-1012), the per-bin text writer
-// (SBKC:550-606 sort path, SBKC:715-734 HT path) and the synthetic FASTA generator.
+// fkm_host.cpp — host-side helpers: FASTA record split + 2-bit packing (the host twin of the
+// device ingest; replaces the FASTdoop record readers, SBKC:62-65,1009-1012), directory
+// creation for the bin files, and the synthetic FASTA generators of SURVEY §8(d).
 #include "fkm_host.h"
 #include "fkm_common.h"
 #include "../../include/fastkmer_b200.h"
@@ -14,20 +14,6 @@
 #include <sys/stat.h>
 #include <thread>
 #include <vector>
-
-int fkm_read_file(const char* path, std::vector<uint8_t>& out) {
-    FILE* f = fopen(path, "rb");
-    if (!f) return fkm_set_error(FKM_EIO, "cannot open %s: %s", path, strerror(errno));
-    fseek(f, 0, SEEK_END);
-    long n = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    if (n < 0) { fclose(f); return fkm_set_error(FKM_EIO, "cannot size %s", path); }
-    out.resize((size_t)n);
-    size_t got = n ? fread(out.data(), 1, (size_t)n, f) : 0;
-    fclose(f);
-    if (got != (size_t)n) return fkm_set_error(FKM_EIO, "short read on %s", path);
-    return FKM_OK;
-}
 
 // Record split: a record starts at a '>' that begins a line; its
 // header runs to the end of that line; the value is every following byte up to
@@ -90,42 +76,6 @@ static int mkdir_p(const std::string& dir) {
 
 int fkm_make_dirs(const char* dir) {
     if (mkdir_p(dir) != 0) return fkm_set_error(FKM_EIO, "cannot create %s: %s", dir, strerror(errno));
-    return FKM_OK;
-}
-
-// host-side formatter (kept for reference / small results; fkm_result_write formats on the device)
-int fkm_write_bins(const char* out_dir, int32_t B, int32_t k, int sorted, const uint64_t* out_base,
-                   const uint64_t* hi, const uint64_t* lo, const uint32_t* cnt) {
-    if (mkdir_p(out_dir) != 0) return fkm_set_error(FKM_EIO, "cannot create %s: %s", out_dir, strerror(errno));
-    std::atomic<int> next(0); std::atomic<int> failed(0);
-    unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    auto work = [&]() {
-        std::string buf;
-        for (;;) {
-            int b = next.fetch_add(1);
-            if (b >= B) break;
-            uint64_t a = out_base[b], e = out_base[b + 1];
-            if (a == e) continue;                                        // only non-empty bins get a file (SBKC:548,711)
-            buf.clear(); buf.reserve((size_t)(e - a) * (size_t)(k + 12) + 4);
-            char line[96];
-            for (uint64_t i = a; i < e; i++) {
-                unsigned __int128 v = ((unsigned __int128)hi[i] << 64) | lo[i];
-                for (int j = 0; j < k; j++) line[j] = "ACGT"[(unsigned)(v >> (2 * (k - 1 - j))) & 3u];   // UTIL:416-454
-                int len = k + snprintf(line + k, sizeof line - (size_t)k, "\t%u\n", cnt[i]);             // SBKC:581,729
-                buf.append(line, (size_t)len);
-            }
-            if (sorted) buf += "EOF";                                    // SBKC:606, no newline
-            std::string path = std::string(out_dir) + "/bin" + std::to_string(b);
-            FILE* f = fopen(path.c_str(), "wb");
-            if (!f || fwrite(buf.data(), 1, buf.size(), f) != buf.size()) failed = 1;
-            if (f) fclose(f);
-        }
-    };
-    std::vector<std::thread> th;
-    for (unsigned t = 1; t < nt; t++) th.emplace_back(work);
-    work();
-    for (auto& q : th) q.join();
-    if (failed) return fkm_set_error(FKM_EIO, "failed writing bin files under %s", out_dir);
     return FKM_OK;
 }
 
