@@ -37,23 +37,23 @@ def test_literal_helpers_match_oracle(oracle):
                 assert rc.toByteArray() == comp
 
 
-@pytest.mark.parametrize("gid", ["G4", "G1"])
+@pytest.mark.parametrize("gid", sorted(GOLD))
 @pytest.mark.parametrize("use_ht", [0, 1])
 def test_literal_reproduces_golden_digests(oracle, gid, use_ht):
+    """The Scala, transliterated line by line, gives the SHA-256 digests of SURVEY App. C.4 on both reduce paths —
+    and, entry for entry, what the fast C++ oracle gives."""
     (seed, G, R, L), (k, m, x, B), nk, dist, nbins, maxc, nsk, skb, sha = GOLD[gid]
-    if gid == "G1":
-        R = 60                                                # pure Python: a prefix of G1 against the C++ oracle instead of the digest
     fasta = oracle.gen_lcg_fasta(seed, G, R, L)
     triples, per_bin = literal.count(fasta, k, m, x, B, use_ht)
-    want = _oracle_triples(oracle.count(fasta, k, m, x, B, use_ht), k)
-    assert triples == want
-    if gid == "G4":
-        lines = sorted(b"%d\t%s\t%d\n" % (b, s.encode(), c) for b, s, c in triples)
-        assert hashlib.sha256(b"".join(lines)).hexdigest() == sha
-        assert per_bin[0][:5] == [("CTGAC", 3), ("CTGCA", 10), ("CTGGA", 13), ("CTGTC", 18), ("GGAAC", 16)] if not use_ht else True
+    assert triples == _oracle_triples(oracle.count(fasta, k, m, x, B, use_ht), k)
+    lines = sorted(b"%d\t%s\t%d\n" % (b, s.encode(), c) for b, s, c in triples)
+    assert hashlib.sha256(b"".join(lines)).hexdigest() == sha
+    assert (sum(c for _, _, c in triples), len(triples), len(per_bin), max(c for _, _, c in triples)) == (nk, dist, nbins, maxc)
+    if gid == "G4" and not use_ht:
+        assert per_bin[0][:5] == [("CTGAC", 3), ("CTGCA", 10), ("CTGGA", 13), ("CTGTC", 18), ("GGAAC", 16)]
     if not use_ht:                                            # the sort path writes ascending k-mers (SBKC:566-597)
-        for lines in per_bin.values():
-            assert [s for s, _ in lines] == sorted(s for s, _ in lines)
+        for lines_ in per_bin.values():
+            assert [s for s, _ in lines_] == sorted(s for s, _ in lines_)
 
 
 @pytest.mark.parametrize("k,m,x", [(5, 3, 1), (12, 4, 2), (28, 10, 3), (31, 11, 3), (32, 7, 2), (33, 8, 3), (55, 13, 3),
