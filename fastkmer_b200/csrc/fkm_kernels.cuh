@@ -367,10 +367,27 @@ __global__ void __launch_bounds__(256) k_scatter_events(const ScatterParams P) {
     const ulonglong2 ev = __ldcs(P.events + i);
     const unsigned long long rs = ev.x;
     const uint32_t n = (uint32_t)ev.y, v = (uint32_t)(ev.y >> 32);
+    // the bases of the first (usually only) piece are requested before the cursor atomic, so the two round trips overlap
+    constexpr int NW = WIDE ? 5 : 3;
+    const unsigned long long a0 = rs - (unsigned long long)(P.k - 1);
+    const unsigned long long j0 = a0 >> 5; const uint32_t sh = 2u * (uint32_t)(a0 & 31ull);
+    uint64_t w[NW];
+#pragma unroll
+    for (int q = 0; q < NW; q++) w[q] = (j0 + q < P.n_words) ? P.bases[j0 + q] : 0ull;
     const uint32_t bin = hash_to_bucket(v, P.B);
     const uint32_t pieces = (n + (uint32_t)P.cap - 1) / (uint32_t)P.cap;
     const unsigned long long slot0 = P.bin_base[bin] + atomicAdd(&P.cursor[bin], (unsigned long long)pieces);
-    for (uint32_t pc = 0, off = 0; off < n; off += (uint32_t)P.cap, pc++) {
+    {
+        const uint32_t nn = min((uint32_t)P.cap, n);
+        uint64_t r[NW - 1];
+#pragma unroll
+        for (int q = 0; q < NW - 1; q++) r[q] = sh ? ((w[q] << sh) | (w[q + 1] >> (64 - sh))) : w[q];
+        r[NW - 2] = (r[NW - 2] & ~0xFFull) | (uint64_t)nn;
+        ulonglong2* dst = reinterpret_cast<ulonglong2*>(P.records) + (WIDE ? 2 : 1) * slot0;
+        dst[0] = make_ulonglong2(r[0], r[1]);
+        if constexpr (WIDE) dst[1] = make_ulonglong2(r[2], r[3]);
+    }
+    for (uint32_t pc = 1, off = (uint32_t)P.cap; off < n; off += (uint32_t)P.cap, pc++) {
         const uint32_t nn = min((uint32_t)P.cap, n - off);
         write_record<WIDE>(P.records, slot0 + pc, P.bases, P.n_words, rs + off - (unsigned long long)(P.k - 1), nn);
     }
@@ -489,7 +506,7 @@ __device__ __forceinline__ int ht_insert(SlotN* tbl, unsigned long long size, ui
         int claimed = 0;
         if (cur == ~0ull) {
             cur = atomicCAS((unsigned long long*)&s->key, ~0ull, (unsigned long long)key);
-            if (cur == ~0ull) { cur = key; claimed = 1; }
+            if (cur == ~0ull) return 1;                        // claimed: the slot's count of 0 already means "seen once"
         }
         if (cur == key) { atomicAdd(&s->cnt, 1u); return claimed; }
         if (++slot == size) slot = 0;
@@ -507,7 +524,7 @@ __device__ __forceinline__ int ht_insert(SlotW* tbl, unsigned long long size, ke
         // a half equal to all-ones may be a torn read of a slot being claimed: let the CAS decide
         if (cur.lo == ~0ull || cur.hi == ~0ull) {
             cur = cas128(&s->key, empty, key);
-            if (key_eq(cur, empty)) { cur = key; claimed = 1; }
+            if (key_eq(cur, empty)) return 1;                  // claimed: count 0 == seen once
         }
         if (key_eq(cur, key)) { atomicAdd(&s->cnt, 1u); return claimed; }
         if (++slot == size) slot = 0;
@@ -541,8 +558,8 @@ __device__ __forceinline__ key128 kmer_at_wide(const uint64_t* rec, int j, int k
 // bitmask of record starts inside the current block of 32 slots (one redux.or),
 // record(t) = #starts before the block + popc(M & lanes<=t) - 1.  Every lane then cuts
 // its own k-mer out of the record, canonicalises it and inserts it — no lane idles
-// because its record is shorter than its neighbour's.  Table counts start at
-// 0xFFFFFFFF (the table is cleared with an all-ones memset): real = cnt + 1.
+// because its record is shorter than its neighbour's.  An empty slot is {key = all ones,
+// count = 0}; claiming it needs no increment, so the stored count is occurrences - 1.
 template <bool WIDE>
 __global__ void __launch_bounds__(256) k_count_ht(const CountParams P) {
     typedef typename Traits<WIDE>::Slot Slot;
@@ -635,7 +652,7 @@ __global__ void __launch_bounds__(256) k_count_ht(const CountParams P) {
                     uint32_t* cp;
                     if constexpr (!WIDE) cp = &(reinterpret_cast<SlotN*>(tbl) + slot[u])->cnt;
                     else cp = &(reinterpret_cast<SlotW*>(tbl) + slot[u])->cnt;
-                    if (state[u] == 1 && is_empty) { claims++; atomicAdd(cp, 1u); state[u] = 2; }
+                    if (state[u] == 1 && is_empty) { claims++; state[u] = 2; }        // claimed: count 0 == seen once, no RED
                     else if (key_eq(got[u], key[u])) { atomicAdd(cp, 1u); state[u] = 2; }
                     else if (state[u] == 0 && maybe_empty) { state[u] = 1; more = true; }
                     else { if (++slot[u] == size) slot[u] = 0; state[u] = 0; more = true; }
@@ -660,6 +677,17 @@ __global__ void __launch_bounds__(256) k_count_ht(const CountParams P) {
         if (claims) atomicAdd(&P.bin_distinct[bin], (unsigned long long)claims);
     }
     if (ovf) *P.overflow = 1;
+}
+
+// empty table: key = all ones, count = 0
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_fill_table(void* table, unsigned long long n_slots) {
+    ulonglong2* t = reinterpret_cast<ulonglong2*>(table);
+    const unsigned long long n16 = n_slots * (WIDE ? 2ull : 1ull);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (unsigned long long)gridDim.x * blockDim.x) {
+        if constexpr (!WIDE) t[i] = make_ulonglong2(~0ull, 0ull);
+        else t[i] = (i & 1ull) ? make_ulonglong2(0ull, 0ull) : make_ulonglong2(~0ull, ~0ull);
+    }
 }
 
 struct CompactParams {
@@ -694,12 +722,12 @@ __global__ void __launch_bounds__(256) k_compact_ht(const CompactParams P) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const unsigned long long sl = tile0 + (unsigned long long)j * 256ull + threadIdx.x;
-            cnts[j] = 0xFFFFFFFFu;
+            cnts[j] = 0u;
             if (sl < P.n_slots) {
                 if constexpr (!WIDE) {
                     ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&tbl[sl]);
                     keys[j] = v.x; cnts[j] = (uint32_t)v.y;
-                    if (v.x != ~0ull) { have |= 1u << j; if (P.clear) *reinterpret_cast<ulonglong2*>(&tbl[sl]) = make_ulonglong2(~0ull, ~0ull); }
+                    if (v.x != ~0ull) { have |= 1u << j; if (P.clear) *reinterpret_cast<ulonglong2*>(&tbl[sl]) = make_ulonglong2(~0ull, 0ull); }
                 } else {
                     ulonglong2* p = reinterpret_cast<ulonglong2*>(&tbl[sl]);
                     ulonglong2 kv = p[0]; ulonglong2 cv = p[1];
@@ -707,7 +735,7 @@ __global__ void __launch_bounds__(256) k_compact_ht(const CompactParams P) {
                     keys[j] = kk; cnts[j] = (uint32_t)cv.x;
                     if (!(kv.x == ~0ull && kv.y == ~0ull)) {
                         have |= 1u << j;
-                        if (P.clear) { p[0] = make_ulonglong2(~0ull, ~0ull); p[1] = make_ulonglong2(~0ull, ~0ull); }
+                        if (P.clear) { p[0] = make_ulonglong2(~0ull, ~0ull); p[1] = make_ulonglong2(0ull, 0ull); }
                     }
                 }
             }

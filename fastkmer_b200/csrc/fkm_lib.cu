@@ -485,7 +485,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
                     }
                     if (slots > table_cap) { CKC(dmalloc(ctx, &d_table, (size_t)slots * sizeof(Slot))); table_cap = slots; }
                     CKC(cudaEventRecord(ctx->ev[6], s));
-                    CKC(cudaMemsetAsync(d_table, 0xFF, (size_t)slots * sizeof(Slot), s));
+                    if (slots) { k_fill_table<WIDE><<<ctx->n_sm * 8, 256, 0, s>>>(d_table, slots); CKLC(); }
                     CKC(cudaMemsetAsync(d_ovf, 0, 8, s));
                     CKC(cudaMemcpyAsync(d_tbl_base, tb.data(), tb.size() * 8, cudaMemcpyHostToDevice, s));
                     st->h2d_bytes += tb.size() * 8;
@@ -572,7 +572,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
             CKC(dmalloc(ctx, &ch.cnt, (size_t)std::max<uint64_t>(out_cap, 1) * 4));
             CKC(cudaMemcpyAsync(d_tb_all, tb_all.data(), tb_all.size() * 8, cudaMemcpyHostToDevice, s));
             st->h2d_bytes += tb_all.size() * 8;
-            CKC(cudaMemsetAsync(d_tab, 0xFF, (size_t)std::max<uint64_t>(max_slots, 1024) * sizeof(Slot), s));
+            k_fill_table<WIDE><<<ctx->n_sm * 8, 256, 0, s>>>(d_tab, std::max<uint64_t>(max_slots, 1024)); CKLC();
             CKC(cudaMemsetAsync(d_ovf, 0, 8, s));
             CKC(cudaMemsetAsync(d_cursor + lo0, 0, (size_t)(B - lo0) * 8, s));
             CKC(cudaEventRecord(ctx->ev[6], s));
