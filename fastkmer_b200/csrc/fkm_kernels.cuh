@@ -712,11 +712,18 @@ __global__ void __launch_bounds__(256) k_compact_ht(const CompactParams P) {
     __shared__ unsigned int s_warp[8];
     __shared__ unsigned long long s_base;
     __shared__ int s_bin;
+    __shared__ unsigned long long s_lo, s_hi;              // slot range of the bin the previous tile belonged to
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     Slot* tbl = reinterpret_cast<Slot*>(P.table);
     const unsigned long long n_tiles = (P.n_slots + 1023) / 1024;
+    // every CTA owns a contiguous range of tiles: consecutive tiles are nearly always in the same bin, so the
+    // serial part of a tile (which bin? reserve output space) is one compare and one atomic
+    const unsigned long long per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const unsigned long long tile_begin = (unsigned long long)blockIdx.x * per_cta;
+    const unsigned long long tile_end = min(n_tiles, tile_begin + per_cta);
+    if (threadIdx.x == 0) { s_lo = 1; s_hi = 0; s_bin = 0; }
     unsigned long long dsum = 0, dxor = 0, dcnt = 0;
-    for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (unsigned long long tile = tile_begin; tile < tile_end; tile++) {
         const unsigned long long tile0 = tile * 1024ull;
         Key keys[4]; uint32_t cnts[4]; unsigned int have = 0;
 #pragma unroll
@@ -752,9 +759,11 @@ __global__ void __launch_bounds__(256) k_compact_ht(const CompactParams P) {
         for (int i = 0; i < 8; i++) { unsigned int t = s_warp[i]; if (i < warp) wbase += t; total += t; }
         if (total == 0) continue;                          // block-uniform
         if (threadIdx.x == 0) {
-            const int bin = P.bin_lo + find_bin(P.tbl_base, 0, P.n_bins, tile0);
-            s_bin = bin;
-            s_base = P.out_base[bin] - P.out_origin + atomicAdd(&P.out_cursor[bin], (unsigned long long)total);
+            if (!(tile0 >= s_lo && tile0 < s_hi)) {
+                const int bl = find_bin(P.tbl_base, 0, P.n_bins, tile0);
+                s_bin = P.bin_lo + bl; s_lo = P.tbl_base[bl]; s_hi = P.tbl_base[bl + 1];
+            }
+            s_base = P.out_base[s_bin] - P.out_origin + atomicAdd(&P.out_cursor[s_bin], (unsigned long long)total);
         }
         __syncthreads();
         const unsigned long long base = s_base; const uint32_t bin = (uint32_t)s_bin;
