@@ -598,68 +598,58 @@ __global__ void __launch_bounds__(256) k_count_ht(const CountParams P) {
         const unsigned long long tb0 = P.tbl_base[bin0 - P.bin_lo];
         const unsigned long long size = P.tbl_base[bin0 - P.bin_lo + 1] - tb0;
         Slot* tbl = reinterpret_cast<Slot*>(P.table) + tb0;
-        const uint32_t le_mask = (2u << lane) - 1u;
-        uint32_t cb = 0;
-        // U independent k-mers per lane and iteration; the probe loop is a per-key state
-        // machine (0 = read the slot, 1 = CAS the empty slot, 2 = done), so U memory
-        // operations per lane are in flight during every round trip to L2 / HBM.
-        constexpr int U = 4;
-        for (uint32_t tb = 0; tb < T; tb += 32 * U) {
-            Key key[U]; unsigned long long slot[U]; int state[U];
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                state[u] = 2; slot[u] = 0; key[u] = Key();
-                const uint32_t bb = tb + 32u * u;
-                if (bb < T) {                                                       // warp-uniform
-                    const uint32_t p = excl - bb;
-                    const uint32_t M = __reduce_or_sync(FULL, (n > 0 && p < 32u) ? (1u << p) : 0u);
-                    const uint32_t t = bb + lane;
+        // Lane refill: the warp's T k-mers form a pool; a lane whose k-mer is done takes the next unassigned
+        // one at once (ballot + popc, no atomics), so every round trip to L2 / HBM carries one probe per
+        // lane — the warp never waits for its longest probe chain.  Per-lane state machine:
+        // 0 = read the slot, 1 = CAS the empty slot, 2 = done (wants a refill), 3 = idle (pool exhausted).
+        const uint32_t lt_mask = (1u << lane) - 1u;
+        uint32_t next = 0;                                   // first unassigned k-mer of the pool (warp-uniform)
+        Key key = Key(); unsigned long long slot = 0; int state = 2;
+        for (int round = 0;; round++) {
+            const uint32_t want = __ballot_sync(FULL, state == 2);
+            if (want) {
+                if (state == 2) {
+                    const uint32_t t = next + __popc(want & lt_mask);
                     if (t < T) {
-                        const int ri = (int)(cb + __popc(M & le_mask)) - 1;
-                        const int j = (int)(t - s_off[warp][ri]);
-                        if constexpr (!WIDE) key[u] = kmer_at_narrow(&s_rec[warp][ri * RW], j, P.k);
-                        else key[u] = kmer_at_wide(&s_rec[warp][ri * RW], j, P.k);
-                        slot[u] = slot_of(key_hash(key[u]), size);
-                        state[u] = 0;
-                    }
-                    cb += __popc(M);
-                }
-            }
-            for (int round = 0;; round++) {
-                Key got[U];
+                        int lo_ = 0, hi_ = 32;               // record ri with s_off[ri] <= t < s_off[ri+1]
 #pragma unroll
-                for (int u = 0; u < U; u++) {
-                    if constexpr (!WIDE) {
-                        SlotN* sp = reinterpret_cast<SlotN*>(tbl) + slot[u];
-                        if (state[u] == 0) got[u] = __ldcg(&sp->key);
-                        else if (state[u] == 1) got[u] = atomicCAS((unsigned long long*)&sp->key, ~0ull, (unsigned long long)key[u]);
-                    } else {
-                        SlotW* sp = reinterpret_cast<SlotW*>(tbl) + slot[u];
-                        if (state[u] == 0) { got[u].lo = __ldcg(&sp->key.lo); got[u].hi = __ldcg(&sp->key.hi); }
-                        else if (state[u] == 1) { const key128 empty = {~0ull, ~0ull}; got[u] = cas128(&sp->key, empty, key[u]); }
-                    }
+                        for (int it = 0; it < 5; it++) { const int mid = (lo_ + hi_) >> 1; if (s_off[warp][mid] <= t) lo_ = mid; else hi_ = mid; }
+                        const int j = (int)(t - s_off[warp][lo_]);
+                        if constexpr (!WIDE) key = kmer_at_narrow(&s_rec[warp][lo_ * RW], j, P.k);
+                        else key = kmer_at_wide(&s_rec[warp][lo_ * RW], j, P.k);
+                        slot = slot_of(key_hash(key), size);
+                        state = 0;
+                    } else state = 3;
                 }
-                bool more = false;
-#pragma unroll
-                for (int u = 0; u < U; u++) {
-                    if (state[u] == 2) continue;
-                    bool is_empty, maybe_empty;
-                    if constexpr (!WIDE) { is_empty = got[u] == ~0ull; maybe_empty = is_empty; }
-                    else {      // a half equal to all-ones may be a torn read of a slot being claimed: the CAS decides
-                        is_empty = got[u].lo == ~0ull && got[u].hi == ~0ull;
-                        maybe_empty = got[u].lo == ~0ull || got[u].hi == ~0ull;
-                    }
-                    uint32_t* cp;
-                    if constexpr (!WIDE) cp = &(reinterpret_cast<SlotN*>(tbl) + slot[u])->cnt;
-                    else cp = &(reinterpret_cast<SlotW*>(tbl) + slot[u])->cnt;
-                    if (state[u] == 1 && is_empty) { claims++; state[u] = 2; }        // claimed: count 0 == seen once, no RED
-                    else if (key_eq(got[u], key[u])) { atomicAdd(cp, 1u); state[u] = 2; }
-                    else if (state[u] == 0 && maybe_empty) { state[u] = 1; more = true; }
-                    else { if (++slot[u] == size) slot[u] = 0; state[u] = 0; more = true; }
-                }
-                if (!more) break;
-                if (round > 2 * P.max_probe) { ovf = true; break; }
+                next += __popc(want);
             }
+            if (__all_sync(FULL, state == 3)) break;
+            Key got = Key();
+            if constexpr (!WIDE) {
+                SlotN* sp = reinterpret_cast<SlotN*>(tbl) + slot;
+                if (state == 0) got = __ldcg(&sp->key);
+                else if (state == 1) got = atomicCAS((unsigned long long*)&sp->key, ~0ull, (unsigned long long)key);
+            } else {
+                SlotW* sp = reinterpret_cast<SlotW*>(tbl) + slot;
+                if (state == 0) { got.lo = __ldcg(&sp->key.lo); got.hi = __ldcg(&sp->key.hi); }
+                else if (state == 1) { const key128 empty = {~0ull, ~0ull}; got = cas128(&sp->key, empty, key); }
+            }
+            if (state < 2) {
+                bool is_empty, maybe_empty;
+                if constexpr (!WIDE) { is_empty = got == ~0ull; maybe_empty = is_empty; }
+                else {      // a half equal to all-ones may be a torn read of a slot being claimed: the CAS decides
+                    is_empty = got.lo == ~0ull && got.hi == ~0ull;
+                    maybe_empty = got.lo == ~0ull || got.hi == ~0ull;
+                }
+                uint32_t* cp;
+                if constexpr (!WIDE) cp = &(reinterpret_cast<SlotN*>(tbl) + slot)->cnt;
+                else cp = &(reinterpret_cast<SlotW*>(tbl) + slot)->cnt;
+                if (state == 1 && is_empty) { claims++; state = 2; }                 // claimed: count 0 == seen once, no RED
+                else if (key_eq(got, key)) { atomicAdd(cp, 1u); state = 2; }
+                else if (state == 0 && maybe_empty) state = 1;
+                else { if (++slot == size) slot = 0; state = 0; }
+            }
+            if (round > (int)T + 2 * P.max_probe) { ovf = true; break; }            // warp-uniform bound on the rounds
         }
         const unsigned int tot = __reduce_add_sync(FULL, claims);
         if (lane == 0 && tot) atomicAdd(&P.bin_distinct[bin0], (unsigned long long)tot);
