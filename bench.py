@@ -330,7 +330,7 @@ def main():
     count_ms = stage[3]
     traffic = None
     try:                                              # measured DRAM bytes per record of k_count_ht (one ncu --set full capture)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1c_count_ht_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1d_count_ht_traffic.json")))
         traffic = tj["dram_bytes_per_record"] * (st["n_superkmers"] / n_count_launches)
     except Exception:
         pass
