@@ -53,6 +53,31 @@ def main():
             ok &= bool(good)
         ctx.free_device(d_b)
         ctx.free_device(d_i)
+    # long-sequence mode (BASELINE config 3): one genome split by position range with a (k-1)-base halo per shard
+    for (k, m, ht) in ((31, 11, 0), (31, 11, 1)):
+        n_bases = 3_000_000
+        seeds = (3001, 3002, 3003)
+        per = n_bases // world
+        first = rank * per
+        n = (per if rank < world - 1 else n_bases - first) + (k - 1 if rank < world - 1 else 0)
+        cfg = fk.TestConfiguration("", "", k, m, 3, max_b=4096, useHT=bool(ht), write=False, sequenceType=1)
+        job = multigpu.ShardedJob(ctx, cfg, dist, rank, world)
+        d_b, d_i, n_pos = ctx.synth_long_packed_device(dict(seeds=seeds, first_pos=first, n_bases=n))
+        res, st = job.count_packed_device(d_b, d_i, n_pos, want_result=True)
+        a = res.arrays()
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object({k_: v for k_, v in a.items()}, gathered, dst=0)
+        if rank == 0:
+            import oracle_lib
+            oracle = oracle_lib.load()
+            want = oracle.count(fk.synth_long_fasta(dict(seeds=seeds, n_bases=n_bases)).tobytes(), k, m, 3, 4096, ht, threads=os.cpu_count())
+            got = {k_: np.concatenate([g[k_] for g in gathered]) for k_ in ("bin", "hi", "lo", "cnt")}
+            order = np.lexsort((got["lo"], got["hi"], got["bin"]))
+            good = all(np.array_equal(got[k_][order], want[k_]) for k_ in got) and st["n_kmers_global"] == want["stats"]["n_kmers"]
+            print("mg_check world=%d long sequence k=%d useHT=%d: %s (%d k-mers)" % (world, k, ht, "OK" if good else "MISMATCH", want["stats"]["n_kmers"]))
+            ok &= bool(good)
+        ctx.free_device(d_b)
+        ctx.free_device(d_i)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     ctx.close()
