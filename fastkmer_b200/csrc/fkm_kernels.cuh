@@ -158,9 +158,9 @@ __device__ __forceinline__ void write_record(void* records, unsigned long long s
 //   * the m-mer ending at e is cut out of two broadcast 64-bit words (funnel shift),
 //     its reverse complement comes from brev, norm() is the closed form of UTIL:46-100;
 //   * the minimum over the window's w = 2^L + d m-mers is built by doubling with warp
-//     shuffles: x_{j+1}[e] = min(x_j[e], x_j[e - 2^j]); values that fall before lane 0
-//     come from the previous group's registers (prev[j]); L is a template parameter so
-//     the level loop is straight-line code;
+//     shuffles: x_{j+1}[e] = min(x_j[e], x_j[e - 2^j]), one shuffle per level (the source
+//     lane sends its value of the previous group when its reader wrapped below lane 0);
+//     L is a template parameter so the level loop is straight-line code;
 //   * a window is valid iff the last invalid position at or before e is >= k behind;
 //   * run boundaries (signature value changes / validity changes) are found with one
 //     shuffle and two ballots; every lane that sees a run END pushes (start, length,
@@ -263,26 +263,21 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams P) {
                 const uint32_t v = __funnelshift_r(lo, hi, fsh) & mmask;
                 uint32_t x = mmer_norm(v, revcomp32(v, m), m, mmask);
                 Wprev = W;
-                // ---- minimum over the last w m-mers (doubling, straight-line)
+                // ---- minimum over the last w m-mers (doubling, straight-line).  One shuffle per level: lane l reads
+                // from lane (l - s) & 31, and that source lane knows what its reader needs — its value of the
+                // current group if the reader is s lanes above it, of the previous group if the reader wrapped.
 #pragma unroll
                 for (int j = 0; j < L; j++) {
                     const int s = 1 << j;
                     const uint32_t cur = x;
-                    uint32_t partner;
-                    if (s == 32) partner = prev[j];
-                    else {
-                        const uint32_t t = __shfl_up_sync(FULL, cur, s);
-                        const uint32_t u = __shfl_sync(FULL, prev[j], (lane - s) & 31);
-                        partner = lane >= s ? t : u;
-                    }
-                    x = min(cur, partner);
+                    const uint32_t send = (lane < 32 - s) ? cur : prev[j];
+                    x = min(cur, __shfl_sync(FULL, send, (lane - s) & 31));
                     prev[j] = cur;
                 }
                 {   // w = 2^L + d: one more step with offset d (d == 0 degenerates to min(x, x))
                     const uint32_t cur = x;
-                    const uint32_t t = __shfl_up_sync(FULL, cur, d);
-                    const uint32_t u = __shfl_sync(FULL, prev[L], (lane - d) & 31);
-                    x = min(cur, lane >= d ? t : u);
+                    const uint32_t send = (lane < 32 - d) ? cur : prev[L];
+                    x = min(cur, __shfl_sync(FULL, send, (lane - d) & 31));
                     prev[L] = cur;
                 }
                 // ---- validity: last invalid position <= e must be at least k behind
