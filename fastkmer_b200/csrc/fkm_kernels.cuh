@@ -862,9 +862,18 @@ __global__ void __launch_bounds__(256) k_radix_scan(const SortParams P) {
     __shared__ unsigned int s_base[kMaxDigits];
     const int seg = blockIdx.x;
     const unsigned int t0 = P.seg_tile0[seg], t1 = P.seg_tile0[seg + 1];
+    constexpr int UB = 8;                          // tiles whose counters are loaded together (independent loads in flight)
     for (int d = threadIdx.x; d < P.nd; d += 256) {
         unsigned int tot = 0;
-        for (unsigned int t = t0; t < t1; t++) tot += P.tile_hist[(size_t)t * P.nd + d];
+        unsigned int t = t0;
+        for (; t + UB <= t1; t += UB) {
+            unsigned int c[UB];
+#pragma unroll
+            for (int u = 0; u < UB; u++) c[u] = P.tile_hist[(size_t)(t + u) * P.nd + d];
+#pragma unroll
+            for (int u = 0; u < UB; u++) tot += c[u];
+        }
+        for (; t < t1; t++) tot += P.tile_hist[(size_t)t * P.nd + d];
         s_tot[d] = tot;
         if (P.seg_digit_tot) P.seg_digit_tot[(size_t)seg * P.nd + d] = tot;
     }
@@ -883,7 +892,15 @@ __global__ void __launch_bounds__(256) k_radix_scan(const SortParams P) {
     __syncthreads();
     for (int d = threadIdx.x; d < P.nd; d += 256) {
         unsigned int run = s_base[d];
-        for (unsigned int t = t0; t < t1; t++) {
+        unsigned int t = t0;
+        for (; t + UB <= t1; t += UB) {
+            unsigned int c[UB];
+#pragma unroll
+            for (int u = 0; u < UB; u++) c[u] = P.tile_hist[(size_t)(t + u) * P.nd + d];
+#pragma unroll
+            for (int u = 0; u < UB; u++) { P.tile_hist[(size_t)(t + u) * P.nd + d] = run; run += c[u]; }
+        }
+        for (; t < t1; t++) {
             unsigned int c = P.tile_hist[(size_t)t * P.nd + d];
             P.tile_hist[(size_t)t * P.nd + d] = run;
             run += c;
