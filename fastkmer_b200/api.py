@@ -82,6 +82,8 @@ def load_library():
         "fkm_result_copy": (C.c_int, [vp, vp, vp, vp, vp]),
         "fkm_result_write": (C.c_int, [vp, C.c_char_p]),
         "fkm_result_free": (None, [vp]),
+        "fkm_result_clone": (C.c_int, [vp, C.POINTER(vp)]),
+        "fkm_result_dot": (C.c_int, [vp, vp, vp, C.POINTER(u64)]),
         "fkm_synth_fasta_host": (C.c_int, [C.POINTER(fkm_synth), vp, u64, C.POINTER(u64)]),
         "fkm_synth_packed_device": (C.c_int, [vp, C.POINTER(fkm_synth), C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]),
         "fkm_synth_long_fasta_host": (C.c_int, [C.POINTER(fkm_synth_long), vp, u64, C.POINTER(u64)]),
@@ -248,6 +250,18 @@ class CountResult:
 
     def write(self, out_dir: str):
         _check(load_library().fkm_result_write(self._h, out_dir.encode()))
+
+    def clone(self):
+        """A copy in plain device memory that survives later jobs on the context."""
+        h = C.c_void_p()
+        _check(load_library().fkm_result_clone(self._h, C.byref(h)))
+        return CountResult(h, self.k, self._ctx)
+
+    def dot(self, other):
+        """sum over common (bin, k-mer) of count * other's count — both must be clones of sorted results."""
+        v = C.c_uint64()
+        _check(load_library().fkm_result_dot(self._ctx._h, self._h, other._h, C.byref(v)))
+        return v.value
 
     def free(self):
         if self._h:

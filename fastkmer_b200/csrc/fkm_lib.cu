@@ -111,6 +111,8 @@ static inline void dfree(fkm_ctx*, void*) {}
 
 struct Chunk { void* keys = nullptr; uint32_t* cnt = nullptr; uint64_t n = 0; };
 struct fkm_result {
+    bool owned = false;                           // clone: arrays in plain device memory, valid until fkm_result_free
+    unsigned long long* d_base = nullptr;         // clone: device copy of out_base (for k_sparse_dot)
     bool eof_trailer = true;                      // sorted files end with "EOF" (SBKC:606); the multisequence writer has none (MSKC:524-526)
     fkm_ctx* ctx = nullptr; uint64_t gen = 0;     // arrays live in ctx's arena until its next job
     int device = 0;
@@ -1139,8 +1141,6 @@ extern "C" int fkm_mg_count(fkm_ctx* ctx, const fkm_config* cfg, const void* d_r
 // semantics are the intended ones of SURVEY App. A.7: the sample of a read is the leading \w+ of its header.
 // Here: reads are split by sample on the host, every sample is counted with the sorted pipeline, and
 // k_sparse_dot gives sum_k c_a(k) c_b(k) for every pair, all in 64-bit integers.
-struct SampleCounts { void* keys = nullptr; uint32_t* cnt = nullptr; unsigned long long* base = nullptr; uint64_t n = 0; };
-
 extern "C" int fkm_multiseq_fasta(fkm_ctx* ctx, const fkm_config* cfg, const uint8_t* fasta, uint64_t n_bytes, int32_t max_samples,
                                   int32_t* n_samples, char* names, double* dist, fkm_result** merged, fkm_stats* stats) {
     if (!ctx || !n_samples || !dist || max_samples < 1) return fkm_set_error(FKM_EINVAL, "bad argument");
@@ -1175,57 +1175,28 @@ extern "C" int fkm_multiseq_fasta(fkm_ctx* ctx, const fkm_config* cfg, const uin
     *n_samples = S;
     if (names) for (int a = 0; a < S; a++) { memset(names + 64 * a, 0, 64); strncpy(names + 64 * a, tags[a].c_str(), 63); }
     for (int a = 0; a < max_samples * max_samples; a++) dist[a] = 0.0;
-    // ---- count every sample (sorted per bin), keep the results in plain device memory
+    // ---- count every sample (sorted per bin) and keep a clone of each result
     fkm_config c2 = *cfg; c2.use_ht = 0; if (c2.x < 1) c2.x = 1;
-    const bool wide = cfg->k > 32;
-    const size_t ksz = wide ? 16 : 8;
-    std::vector<SampleCounts> sc((size_t)S);
-    auto release = [&]() { for (auto& q : sc) { cudaFree(q.keys); cudaFree(q.cnt); cudaFree(q.base); } };
+    std::vector<fkm_result*> sc((size_t)S, nullptr);
+    auto release = [&]() { for (auto* q : sc) fkm_result_free(q); };
     fkm_stats total; memset(&total, 0, sizeof total);
     for (int a = 0; a < S && !rc; a++) {
         fkm_result* r = nullptr; fkm_stats st;
         rc = fkm_count_fasta(ctx, &c2, texts[(size_t)a].data(), texts[(size_t)a].size(), &r, &st);
         if (rc) break;
-        SampleCounts& q = sc[(size_t)a];
-        q.n = r->total;
-        cudaError_t e = cudaMalloc(&q.keys, std::max<uint64_t>(q.n, 1) * ksz);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&q.cnt, std::max<uint64_t>(q.n, 1) * 4);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&q.base, ((size_t)B + 1) * 8);
-        uint64_t o = 0;
-        for (const Chunk& ch : r->chunks) {
-            if (e != cudaSuccess || !ch.n) continue;
-            e = cudaMemcpyAsync((char*)q.keys + o * ksz, ch.keys, ch.n * ksz, cudaMemcpyDeviceToDevice, ctx->stream);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(q.cnt + o, ch.cnt, ch.n * 4, cudaMemcpyDeviceToDevice, ctx->stream);
-            o += ch.n;
-        }
-        if (e == cudaSuccess) e = cudaMemcpyAsync(q.base, r->out_base.data(), ((size_t)B + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        rc = fkm_result_clone(r, &sc[(size_t)a]);
         fkm_result_free(r);
-        if (e != cudaSuccess) rc = fkm_set_error(FKM_ECUDA, "multiseq copy: %s", cudaGetErrorString(e));
         total.n_bases += st.n_bases; total.n_kmers += st.n_kmers; total.n_distinct += st.n_distinct; total.total_count += st.total_count;
         total.gpu_launches += st.gpu_launches; total.h2d_bytes += st.h2d_bytes; total.d2h_bytes += st.d2h_bytes; total.ms_total += st.ms_total;
     }
     // ---- pairwise sparse dot products
     std::vector<unsigned long long> dot((size_t)S * S, 0);
-    if (!rc && S) {
-        unsigned long long* d_acc = nullptr;
-        cudaError_t e = cudaMalloc((void**)&d_acc, (size_t)S * S * 8);
-        if (e == cudaSuccess) e = cudaMemsetAsync(d_acc, 0, (size_t)S * S * 8, ctx->stream);
-        for (int a = 0; a < S && e == cudaSuccess; a++)
-            for (int b = a; b < S; b++) {
-                if (!sc[(size_t)a].n || !sc[(size_t)b].n) continue;
-                DotParams P;
-                P.keysA = sc[(size_t)a].keys; P.cntA = sc[(size_t)a].cnt; P.baseA = sc[(size_t)a].base; P.nA = sc[(size_t)a].n;
-                P.keysB = sc[(size_t)b].keys; P.cntB = sc[(size_t)b].cnt; P.baseB = sc[(size_t)b].base; P.B = B; P.acc = d_acc + (size_t)a * S + b;
-                const int grid = (int)std::min<uint64_t>((P.nA + 255) / 256, (uint64_t)ctx->n_sm * 8);
-                if (wide) k_sparse_dot<true><<<grid, 256, 0, ctx->stream>>>(P); else k_sparse_dot<false><<<grid, 256, 0, ctx->stream>>>(P);
-                g_launches++; total.gpu_launches++;
-            }
-        if (e == cudaSuccess) e = cudaMemcpyAsync(dot.data(), d_acc, (size_t)S * S * 8, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        cudaFree(d_acc);
-        if (e != cudaSuccess) rc = fkm_set_error(FKM_ECUDA, "multiseq distances: %s", cudaGetErrorString(e));
-    }
+    for (int a = 0; a < S && !rc; a++)
+        for (int b = a; b < S && !rc; b++) {
+            uint64_t v = 0;
+            rc = fkm_result_dot(ctx, sc[(size_t)a], sc[(size_t)b], &v);
+            dot[(size_t)a * S + b] = v; total.gpu_launches++;
+        }
     release();
     if (rc) return rc;
     for (int a = 0; a < S; a++)
@@ -1258,7 +1229,7 @@ extern "C" int fkm_result_bin_offsets(const fkm_result* r, uint64_t* offsets) {
 }
 extern "C" int fkm_result_copy(const fkm_result* r, int32_t* bin, uint64_t* key_hi, uint64_t* key_lo, uint32_t* count) {
     if (!r) return fkm_set_error(FKM_EINVAL, "null result");
-    if (r->total && r->gen != r->ctx->gen)
+    if (!r->owned && r->total && r->gen != r->ctx->gen)
         return fkm_set_error(FKM_EINVAL, "result was invalidated by a later job on the same context (copy it out first)");
     CK(cudaSetDevice(r->device));
     uint64_t o = 0;
@@ -1358,12 +1329,76 @@ static int write_result_device(fkm_ctx* ctx, const fkm_result* r, const char* ou
 
 extern "C" int fkm_result_write(const fkm_result* r, const char* out_dir) {
     if (!r || !out_dir) return fkm_set_error(FKM_EINVAL, "null argument");
-    if (r->total && r->gen != r->ctx->gen)
+    if (!r->owned && r->total && r->gen != r->ctx->gen)
         return fkm_set_error(FKM_EINVAL, "result was invalidated by a later job on the same context (write it first)");
     CK(cudaSetDevice(r->device));
     return r->wide ? write_result_device<true>(r->ctx, r, out_dir) : write_result_device<false>(r->ctx, r, out_dir);
 }
-extern "C" void fkm_result_free(fkm_result* r) { delete r; }   // device arrays belong to the context arena
+extern "C" void fkm_result_free(fkm_result* r) {
+    if (!r) return;
+    if (r->owned) {                                // a clone owns its arrays; everything else lives in the context arena
+        cudaSetDevice(r->device);
+        for (Chunk& ch : r->chunks) { cudaFree(ch.keys); cudaFree(ch.cnt); }
+        cudaFree(r->d_base);
+    }
+    delete r;
+}
+
+// A copy of a result in plain device memory (one chunk): it stays valid when later jobs reuse the context's arena.
+extern "C" int fkm_result_clone(const fkm_result* r, fkm_result** out) {
+    if (!r || !out) return fkm_set_error(FKM_EINVAL, "null argument");
+    if (!r->owned && r->total && r->gen != r->ctx->gen) return fkm_set_error(FKM_EINVAL, "result was invalidated by a later job on the same context");
+    CK(cudaSetDevice(r->device));
+    const size_t ksz = r->wide ? 16 : 8;
+    fkm_result* c = new fkm_result();
+    c->owned = true; c->eof_trailer = r->eof_trailer; c->ctx = r->ctx; c->gen = 0; c->device = r->device;
+    c->B = r->B; c->k = r->k; c->wide = r->wide; c->sorted = r->sorted; c->out_base = r->out_base; c->total = r->total;
+    Chunk ch; ch.n = r->total;
+    cudaError_t e = cudaMalloc(&ch.keys, std::max<uint64_t>(r->total, 1) * ksz);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ch.cnt, std::max<uint64_t>(r->total, 1) * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_base, ((size_t)r->B + 1) * 8);
+    c->chunks.push_back(ch);
+    uint64_t o = 0;
+    cudaStream_t s = r->ctx->stream;
+    for (const Chunk& src : r->chunks) {
+        if (e != cudaSuccess || !src.n) continue;
+        e = cudaMemcpyAsync((char*)ch.keys + o * ksz, src.keys, src.n * ksz, cudaMemcpyDeviceToDevice, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ch.cnt + o, src.cnt, src.n * 4, cudaMemcpyDeviceToDevice, s);
+        o += src.n;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_base, c->out_base.data(), ((size_t)r->B + 1) * 8, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { fkm_result_free(c); return fkm_set_error(e == cudaErrorMemoryAllocation ? FKM_ENOMEM : FKM_ECUDA, "clone: %s", cudaGetErrorString(e)); }
+    *out = c;
+    return FKM_OK;
+}
+
+// sum over the (bin, k-mer) pairs present in both results of count_a * count_b.  Both must be clones of sorted
+// (use_ht=0) results of the same configuration.  (MSKC:474-482: the cross term of the squared euclidean distance.)
+extern "C" int fkm_result_dot(fkm_ctx* ctx, const fkm_result* a, const fkm_result* b, uint64_t* dot) {
+    if (!ctx || !a || !b || !dot) return fkm_set_error(FKM_EINVAL, "null argument");
+    if (!a->owned || !b->owned || !a->sorted || !b->sorted || a->B != b->B || a->k != b->k)
+        return fkm_set_error(FKM_EINVAL, "fkm_result_dot needs two clones of sorted results of one configuration");
+    CK(cudaSetDevice(ctx->device));
+    *dot = 0;
+    if (!a->total || !b->total) return FKM_OK;
+    unsigned long long* d_acc = nullptr;
+    CK(cudaMalloc((void**)&d_acc, 8));
+    CK(cudaMemsetAsync(d_acc, 0, 8, ctx->stream));
+    DotParams P;
+    P.keysA = a->chunks[0].keys; P.cntA = a->chunks[0].cnt; P.baseA = a->d_base; P.nA = a->total;
+    P.keysB = b->chunks[0].keys; P.cntB = b->chunks[0].cnt; P.baseB = b->d_base; P.B = a->B; P.acc = d_acc;
+    const int grid = (int)std::min<uint64_t>((P.nA + 255) / 256, (uint64_t)ctx->n_sm * 8);
+    if (a->wide) k_sparse_dot<true><<<grid, 256, 0, ctx->stream>>>(P); else k_sparse_dot<false><<<grid, 256, 0, ctx->stream>>>(P);
+    g_launches++;
+    unsigned long long v = 0;
+    cudaError_t e = cudaMemcpyAsync(&v, d_acc, 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_acc);
+    if (e != cudaSuccess) return fkm_set_error(FKM_ECUDA, "dot: %s", cudaGetErrorString(e));
+    *dot = v;
+    return FKM_OK;
+}
 
 // ------------------------------------------------------------------ synthetic data, test hooks
 extern "C" int fkm_synth_packed_device(fkm_ctx* ctx, const fkm_synth* sy, void** d_bases, void** d_inv, uint64_t* n_positions) {

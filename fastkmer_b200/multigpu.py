@@ -33,13 +33,14 @@ def assign_owners(bin_kmers, world):
     return owner
 
 
-def plan_exchange(H_rec, H_kmer, rank, world):
-    """H_rec, H_kmer: [world, B] records / k-mers every rank puts into every bin.
+def plan_exchange(H_rec, H_kmer, rank, world, owner=None):
+    """H_rec, H_kmer: [world, B] records / k-mers every rank puts into every bin.  owner: a fixed bin -> GPU map
+    (jobs that must agree on the ownership, e.g. the samples of a distance job); default LPT on this job's histogram.
     -> dict with everything rank `rank` needs for steps 4-7."""
     H_rec = np.asarray(H_rec, dtype=np.uint64)
     H_kmer = np.asarray(H_kmer, dtype=np.uint64)
     B = H_rec.shape[1]
-    owner = assign_owners(H_kmer.sum(axis=0), world)
+    owner = assign_owners(H_kmer.sum(axis=0), world) if owner is None else np.asarray(owner, dtype=np.int32)
     # send buffer: bins ordered by (owner, bin)
     order = np.lexsort((np.arange(B), owner))
     send_base = np.zeros(B + 1, dtype=np.uint64)
@@ -99,6 +100,7 @@ class ShardedJob:
         self.torch, self.ctx, self.cfg, self.dist, self.rank, self.world = torch, ctx, configuration, dist, rank, world
         from . import api
         self.rec_bytes = api.record_bytes(configuration)
+        self.fixed_owner = None           # set to a bin -> GPU map to override the per-job LPT assignment
         self.last_plan = None
         self.last_exchange_ms = 0.0
 
@@ -122,7 +124,7 @@ class ShardedJob:
         allh = torch.empty(self.world * 2 * B, dtype=torch.int64, device="cuda")
         dist.all_gather_into_tensor(allh, mine)
         allh = allh.cpu().numpy().reshape(self.world, 2, B).astype(np.uint64)
-        plan = plan_exchange(allh[:, 0, :], allh[:, 1, :], self.rank, self.world)
+        plan = plan_exchange(allh[:, 0, :], allh[:, 1, :], self.rank, self.world, owner=self.fixed_owner)
         self.last_plan = plan
         send = torch.empty((max(plan["n_send"], 1), self.rec_bytes), dtype=torch.uint8, device="cuda")
         self.ctx.mg_scatter(plan["send_base"], send.data_ptr())
@@ -152,6 +154,62 @@ class ShardedJob:
         if want_result:
             return res, st
         return st
+
+
+def split_by_sample(fasta: bytes):
+    """FASTA text -> ordered {sample tag: text of its records}; the tag is the leading \\w+ of the header
+    (SparkMultiSequenceKmerCounter.scala:61-62)."""
+    import re
+    out = {}
+    for rec in re.split(rb"(?m)^(?=>)", fasta):
+        if not rec.startswith(b">"):
+            continue
+        m_ = re.match(rb">\W*(\w+)", rec)
+        tag = m_.group(1).decode() if m_ else ""
+        out.setdefault(tag, []).append(rec if rec.endswith(b"\n") else rec + b"\n")
+    return {t: b"".join(v) for t, v in out.items()}
+
+
+def multiseq_sharded(ctx, configuration, dist, rank, world, fasta_shard: bytes):
+    """Multi-sample squared-euclidean distances over `world` GPUs (BASELINE config 5): every rank holds a shard of
+    the reads; per sample the bins are exchanged and counted as in ShardedJob, every rank computes the partial
+    sums over the bins it owns (fkm_result_dot), and ONE all-reduce of the S x S matrix finishes the job
+    (SparkMultiSequenceKmerCounter.scala:458-520, multiseq/SquaredEuclidean.java:19-32).
+    -> (sample names, S x S float64 matrix), identical on every rank."""
+    import torch
+    from dataclasses import replace
+    cfg = replace(configuration, useHT=False, write=False)
+    mine = split_by_sample(fasta_shard)
+    tags_all = [None] * world
+    dist.all_gather_object(tags_all, list(mine))
+    names = sorted(set(t for tl in tags_all for t in tl))
+    job = ShardedJob(ctx, cfg, dist, rank, world)
+    # all samples must agree on who owns a bin (the partial sums pair bin b of sample a with bin b of sample b):
+    # bins are hash buckets of the signature, so a static round-robin map is balanced enough
+    job.fixed_owner = np.arange(cfg.b, dtype=np.int32) % world
+    clones = []
+    for t in names:                                               # every rank runs every sample's job (possibly on no reads)
+        text = np.frombuffer(mine.get(t, b""), dtype=np.uint8)
+        res, _ = job.count_fasta(text, want_result=True)
+        clones.append(res.clone())
+    S = len(names)
+    part = np.zeros((S, S), dtype=np.uint64)
+    for a in range(S):
+        for b in range(a, S):
+            part[a, b] = clones[a].dot(clones[b])
+    for c in clones:
+        c.free()
+    # uint64 sums through two int64 halves (NCCL has no uint64 sum)
+    lo = torch.from_numpy((part & np.uint64(0xFFFFFFFF)).astype(np.int64)).cuda()
+    hi = torch.from_numpy((part >> np.uint64(32)).astype(np.int64)).cuda()
+    dist.all_reduce(lo)
+    dist.all_reduce(hi)
+    dot = [[(int(hi[a, b]) << 32) + int(lo[a, b]) for b in range(S)] for a in range(S)]
+    out = np.zeros((S, S), dtype=np.float64)
+    for a in range(S):
+        for b in range(a + 1, S):
+            out[a, b] = out[b, a] = float(dot[a][a] + dot[b][b] - 2 * dot[a][b])
+    return names, out
 
 
 def emulate_ranks(ctx, configuration, shards, world):

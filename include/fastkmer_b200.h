@@ -140,6 +140,11 @@ int  fkm_result_copy(const fkm_result* r, int32_t* bin, uint64_t* key_hi, uint64
 /* writes <out_dir>/bin<id> for every non-empty bin (SBKC:550-606 / 715-734)    */
 int  fkm_result_write(const fkm_result* r, const char* out_dir);
 void fkm_result_free(fkm_result* r);
+/* A copy in plain device memory that stays valid across later jobs (free it with fkm_result_free).           */
+int  fkm_result_clone(const fkm_result* r, fkm_result** out);
+/* sum over the (bin, k-mer) pairs present in both of count_a * count_b; a and b are clones of sorted
+ * (use_ht = 0) results of one configuration.  Building block of the multi-sample distances.                  */
+int  fkm_result_dot(fkm_ctx* ctx, const fkm_result* a, const fkm_result* b, uint64_t* dot);
 
 /* ---- synthetic inputs of SURVEY §8(d) (counter-based splitmix64) -------------- */
 typedef struct fkm_synth {

@@ -503,3 +503,25 @@ def test_multisequence_mirror(ctx, tmp_path):
     assert names == ["S%d" % i for i in sorted(range(3), key=lambda s_: fasta.index(">S%d." % s_))]
     assert dist.shape == (3, 3) and (dist == dist.T).all() and (np.diag(dist) == 0).all()
     assert (tmp_path / "k20_m6_x3_b100_s0").is_dir()                      # multisequence/package.scala:29
+
+
+def test_result_clone_survives_later_jobs_and_dot(ctx, oracle):
+    fa = _multiseq_input(1, 400, 100, 7).encode()
+    fb = _multiseq_input(1, 400, 100, 8).encode()
+    c = cfg(28, 10, 3, 2048, 0)
+    ra, _ = ctx.count_fasta(c, fa)
+    ca = ra.clone()
+    rb, _ = ctx.count_fasta(c, fb)                      # a later job on the same context: ra is stale, its clone is not
+    cb = rb.clone()
+    with pytest.raises(fk.FkmError):
+        ra._cache = None
+        ra.arrays()
+    wa = oracle.count(fa, 28, 10, 3, 2048, 0)
+    wb = oracle.count(fb, 28, 10, 3, 2048, 0)
+    assert_same(ca.arrays(), wa, "clone a")
+    da = {(int(b), int(l)): int(n) for b, l, n in zip(wa["bin"], wa["lo"], wa["cnt"])}
+    db = {(int(b), int(l)): int(n) for b, l, n in zip(wb["bin"], wb["lo"], wb["cnt"])}
+    assert ca.dot(cb) == sum(n * db.get(key, 0) for key, n in da.items()) == cb.dot(ca)
+    assert ca.dot(ca) == sum(n * n for n in da.values())
+    ca.free()
+    cb.free()

@@ -41,6 +41,18 @@ def test_plan_is_consistent_across_ranks():
         assert sum(int(p["bin_kmer"].sum()) for p in plans) == Hk.sum()
 
 
+def test_fixed_owner_map_is_respected():
+    rng = np.random.default_rng(5)
+    Hr = rng.integers(0, 40, (3, 50))
+    Hk = Hr * 7
+    owner = np.arange(50) % 3
+    plans = [mg.plan_exchange(Hr, Hk, r, 3, owner=owner) for r in range(3)]
+    for r, p in enumerate(plans):
+        assert (p["owner"] == owner).all()
+        assert p["bin_rec"][owner != r].sum() == 0 and p["bin_rec"][owner == r].sum() == Hr[:, owner == r].sum()
+        assert p["recv_splits"] == [plans[s]["send_splits"][r] for s in range(3)]
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
