@@ -911,7 +911,7 @@ __global__ void __launch_bounds__(256) k_radix_scan(const SortParams P) {
 // stable scatter of one tile: warp `wi` owns keys [wi*256, wi*256+256) of the tile
 // in 8 rounds of 32; ranks come from match.any peer masks and per-warp digit counters.
 template <bool WIDE>
-__global__ void __launch_bounds__(256) k_radix_scatter(const SortParams P) {
+__global__ void __launch_bounds__(256, 5) k_radix_scatter(const SortParams P) {
     typedef typename Traits<WIDE>::Key Key;
     __shared__ unsigned int s_wc[8][kMaxDigits];
     __shared__ unsigned int s_off[kMaxDigits];
