@@ -93,7 +93,7 @@ struct fkm_ctx {
     double debug_event_scale = 1.0;   // test hook: scales the run-event list capacity (forces the second-scan fallback)
     double debug_force_lsd = 0.0;     // sort path: 0 = auto (MSD + shared-memory chunk sort for 64-bit keys, LSD passes for 128-bit), 1 = LSD, 2 = MSD
     double debug_rho_scale = 1.0;     // test hook: scales the learnt distinct/k-mer ratio (forces the overflow fallback)
-    double l2_table_bytes = 1024.0 * (1 << 20); // tables of one asynchronous batch; 0 disables the asynchronous phase (measured: 0.25-16 GB all within 8%, profiles/r1_table_sweep.txt)
+    double async_table_bytes = 1024.0 * (1 << 20); // tables of one asynchronous batch; 0 disables the asynchronous phase (0.25-16 GB all within 8 %, profiles/r1_table_sweep.txt)
     uint64_t job_launches = 0;
     uint64_t gen = 0;                 // job generation: results of older jobs are invalid
     Arena arena;
@@ -169,7 +169,7 @@ extern "C" int fkm_ctx_set(fkm_ctx* c, const char* name, double v) {
     if (!strcmp(name, "table_budget_bytes")) c->table_budget_bytes = v;
     else if (!strcmp(name, "sort_budget_keys")) c->sort_budget_keys = v;
     else if (!strcmp(name, "load_factor")) c->load_factor = v;
-    else if (!strcmp(name, "l2_table_bytes")) c->l2_table_bytes = v;
+    else if (!strcmp(name, "async_table_bytes") || !strcmp(name, "l2_table_bytes")) c->async_table_bytes = v;
     else if (!strcmp(name, "debug_rho_scale")) c->debug_rho_scale = v;
     else if (!strcmp(name, "debug_force_lsd")) c->debug_force_lsd = v;
     else if (!strcmp(name, "debug_event_scale")) c->debug_event_scale = v;
@@ -541,14 +541,14 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
             return FKM_OK;
         };
 
-        // ---- asynchronous batches with L2-resident tables: all launches are queued without a
+        // ---- asynchronous batches: all launches are queued without a
         // host sync; tables are sized from rho, the output arrays from rho_obs; the compaction
-        // kernel clears the slots it reads, so one memset serves every batch.  Any overflow
+        // kernel clears the slots it reads, so one fill serves every batch.  Any overflow
         // (table or output) is caught by flags read once at the end; the caller then redoes
         // the bins with safe_batches.
         auto fast_batches = [&](const int lo0, bool* ok) -> int {
             *ok = false;
-            const uint64_t budget_slots = std::max<uint64_t>(1024, (uint64_t)(ctx->l2_table_bytes / sizeof(Slot)));
+            const uint64_t budget_slots = std::max<uint64_t>(1024, (uint64_t)(ctx->async_table_bytes / sizeof(Slot)));
             struct Batch { int lo, hi; size_t tb_idx; uint64_t slots; };
             std::vector<Batch> batches; std::vector<unsigned long long> tb_all;
             uint64_t max_slots = 0, nk_rest = 0;
@@ -636,7 +636,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
         bool fast_ok = false;
         const double rho_keep = rho, rho_obs_keep = rho_obs;
         rho *= ctx->debug_rho_scale; rho_obs *= ctx->debug_rho_scale;
-        if (lo < B && ctx->l2_table_bytes >= 1.0) {
+        if (lo < B && ctx->async_table_bytes >= 1.0) {
             // the fast path folds its digest into the accumulators: keep a copy to roll back on fallback
             unsigned long long* d_acc_keep = nullptr;
             CKC(dmalloc(ctx, &d_acc_keep, 192 * 8));

@@ -192,7 +192,7 @@ def test_small_table_budget_batches_and_retry(ctx, oracle):
     c2 = fk.Context(0)
     try:
         c2.set("table_budget_bytes", 1 << 20)
-        c2.set("l2_table_bytes", 0)                        # synchronous batches only
+        c2.set("async_table_bytes", 0)                        # synchronous batches only
         res, st = c2.count_fasta(cfg(28, 10, 3, 2048, 1), fasta)
         assert st["n_batches"] > 4
         assert_same(res.sorted_arrays(), want, "tiny budget")
@@ -227,7 +227,7 @@ def test_async_phase_overflow_falls_back(oracle):
             assert st["n_fallbacks"] == 1
             assert_same(res.sorted_arrays(), want, "event overflow ht%d" % ht)
         c2.set("debug_event_scale", 1.0)
-        c2.set("l2_table_bytes", 1 << 16)                  # many tiny asynchronous batches
+        c2.set("async_table_bytes", 1 << 16)                  # many tiny asynchronous batches
         res, st = c2.count_fasta(cfg(28, 10, 3, 2048, 1), fasta)
         assert st["n_fallbacks"] == 0 and st["n_batches"] > 100
         assert_same(res.sorted_arrays(), want, "tiny async batches")
