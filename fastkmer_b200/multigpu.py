@@ -157,14 +157,15 @@ class ShardedJob:
 
 
 def split_by_sample(fasta: bytes):
-    """FASTA text -> ordered {sample tag: text of its records}; the tag is the leading \\w+ of the header
-    (SparkMultiSequenceKmerCounter.scala:61-62)."""
+    """FASTA text -> ordered {sample tag: text of its records}; the tag is the leading \\w+ of the header LINE
+    (SparkMultiSequenceKmerCounter.scala:61-62; the reference's `(\\w+).` full match also keeps
+    the one character after the word -- a label difference only).  Same rule as fkm_multiseq_fasta."""
     import re
     out = {}
     for rec in re.split(rb"(?m)^(?=>)", fasta):
         if not rec.startswith(b">"):
             continue
-        m_ = re.match(rb">\W*(\w+)", rec)
+        m_ = re.match(rb">[^\w\n]*(\w+)", rec)
         tag = m_.group(1).decode() if m_ else ""
         out.setdefault(tag, []).append(rec if rec.endswith(b"\n") else rec + b"\n")
     return {t: b"".join(v) for t, v in out.items()}

@@ -123,3 +123,48 @@ def test_exchange_over_gloo(world):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res)
+
+
+def test_split_by_sample_uses_the_leading_word_of_the_header():
+    fasta = (b"junk\n>SRR1.1 HW len=3\nACG\nTTT\n>SRR2.1 x\nGGG\n>SRR1.2\nCCC\n>  odd_tag-7 z\nAAA\n>\nTT\n")
+    parts = mg.split_by_sample(fasta)
+    assert list(parts) == ["SRR1", "SRR2", "odd_tag", ""]                      # order of first appearance
+    assert parts["SRR1"] == b">SRR1.1 HW len=3\nACG\nTTT\n>SRR1.2\nCCC\n"
+    assert parts["SRR2"] == b">SRR2.1 x\nGGG\n"
+    assert parts["odd_tag"] == b">  odd_tag-7 z\nAAA\n"
+    assert sum(len(v) for v in parts.values()) == len(fasta) - len(b"junk\n")
+
+
+def test_multisequence_configuration_mirror():
+    from fastkmer_b200.multisequence import MultisequenceTestConfiguration
+    tc = MultisequenceTestConfiguration("in.fa", "/out/", 28, 10, 3, max_b=2048, sequenceType=1)
+    assert tc.b == 2048 and tc.outputDir == "/out/k28_m10_x3_b2048_s1"       # multisequence/package.scala:28-29 (no prefix)
+    cc = tc.counting_configuration()
+    assert (cc.k, cc.m, cc.x, cc.max_b, cc.useHT, cc.sequenceType) == (28, 10, 3, 2048, False, 1)
+
+
+def test_bench_workload_shards_cover_the_input_once():
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    wl = bench.Workload(3)                                                      # long sequence: position ranges + (k-1) halo
+    k = wl.c["k"]
+    for world in (1, 2, 4, 8):
+        shards = [wl.spec(r, world) for r in range(world)]
+        assert shards[0]["first_pos"] == 0
+        starts = 0
+        for r, sh in enumerate(shards):
+            halo = k - 1 if r < world - 1 else 0
+            starts += sh["n_bases"] - halo                                      # window starts owned by the shard
+            if r + 1 < world:
+                assert shards[r + 1]["first_pos"] == sh["first_pos"] + sh["n_bases"] - halo
+        assert starts == wl.c["n_bases"]
+        assert wl.n_bases_total(world) == wl.c["n_bases"] and wl.scaling == "strong"
+    w2 = bench.Workload(2)
+    for world in (1, 8):
+        sh = [w2.spec(r, world) for r in range(world)]
+        assert [s_["first_read"] for s_ in sh] == [r * w2.c["reads"] for r in range(world)]
+        assert len({s_["genome_len"] for s_ in sh}) == 1 and w2.scaling == "weak"
+        assert w2.n_bases_total(world) == world * w2.c["reads"] * w2.c["L"]
