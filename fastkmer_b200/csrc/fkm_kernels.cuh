@@ -694,6 +694,8 @@ template <bool WIDE>
 __global__ void __launch_bounds__(256) k_compact_ht(const CompactParams P) {
     typedef typename Traits<WIDE>::Slot Slot;
     typedef typename Traits<WIDE>::Key Key;
+    __shared__ Key s_keys[1024];                           // the tile's entries, dense (thread-major slot order)
+    __shared__ uint32_t s_cnts[1024];
     __shared__ unsigned int s_warp[8];
     __shared__ unsigned long long s_base;
     __shared__ int s_bin;
@@ -736,34 +738,38 @@ __global__ void __launch_bounds__(256) k_compact_ht(const CompactParams P) {
         unsigned int incl = c;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { unsigned int t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
-        __syncthreads();                                   // previous tile's s_warp / s_base fully consumed
         if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
+        __syncthreads();                                   // also: the previous tile's reads of s_keys / s_cnts / s_base are done
         unsigned int wbase = 0, total = 0;
 #pragma unroll
         for (int i = 0; i < 8; i++) { unsigned int t = s_warp[i]; if (i < warp) wbase += t; total += t; }
-        if (total == 0) continue;                          // block-uniform
-        if (threadIdx.x == 0) {
-            if (!(tile0 >= s_lo && tile0 < s_hi)) {
-                const int bl = find_bin(P.tbl_base, 0, P.n_bins, tile0);
-                s_bin = P.bin_lo + bl; s_lo = P.tbl_base[bl]; s_hi = P.tbl_base[bl + 1];
+        if (total) {                                       // block-uniform
+            if (threadIdx.x == 0) {
+                if (!(tile0 >= s_lo && tile0 < s_hi)) {
+                    const int bl = find_bin(P.tbl_base, 0, P.n_bins, tile0);
+                    s_bin = P.bin_lo + bl; s_lo = P.tbl_base[bl]; s_hi = P.tbl_base[bl + 1];
+                }
+                s_base = P.out_base[s_bin] - P.out_origin + atomicAdd(&P.out_cursor[s_bin], (unsigned long long)total);
             }
-            s_base = P.out_base[s_bin] - P.out_origin + atomicAdd(&P.out_cursor[s_bin], (unsigned long long)total);
+            unsigned int o = wbase + (incl - c);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (have & (1u << j)) { s_keys[o] = keys[j]; s_cnts[o] = cnts[j] + 1u; o++; }
         }
         __syncthreads();
+        if (total == 0) continue;
         const unsigned long long base = s_base; const uint32_t bin = (uint32_t)s_bin;
         if (base + total > P.out_cap) { if (threadIdx.x == 0) *P.cap_overflow = 1; continue; }
-        unsigned long long o = base + wbase + (incl - c);
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (have & (1u << j)) {
-                const uint32_t n = cnts[j] + 1u;
-                reinterpret_cast<Key*>(P.out_keys)[o] = keys[j];
-                P.out_cnt[o] = n;
-                o++;
-                uint64_t hi, lo;
-                if constexpr (!WIDE) { hi = 0; lo = keys[j]; } else { hi = keys[j].hi; lo = keys[j].lo; }
-                const uint64_t h = entry_hash(bin, hi, lo);
+        // dense part: coalesced stores, every lane busy in the digest
+        const uint64_t hbin = mix64((uint64_t)bin);
+        const uint64_t hpre = mix64(hbin);                 // entry_hash's inner term when hi == 0 (narrow keys)
+        for (unsigned int i = threadIdx.x; i < total; i += 256u) {
+            const Key kk = s_keys[i]; const uint32_t n = s_cnts[i];
+            reinterpret_cast<Key*>(P.out_keys)[base + i] = kk;
+            P.out_cnt[base + i] = n;
+            if (P.acc) {
+                uint64_t h;                                // == entry_hash(bin, hi, lo)
+                if constexpr (!WIDE) h = mix64(kk ^ hpre); else h = mix64(kk.lo ^ mix64(kk.hi ^ hbin));
                 dsum += h * (uint64_t)n; dxor ^= mix64(h + n); dcnt += n;
             }
         }

@@ -348,6 +348,17 @@ static int scan_end(fkm_ctx* ctx, ScanState* S, fkm_stats* st) {
     return FKM_OK;
 }
 
+// k_compact_ht gives every CTA an equal, contiguous share of the tiles: whole waves only (4 per launch), so
+// no SM idles behind a partial last wave
+template <bool WIDE>
+static uint64_t compact_grid(fkm_ctx* ctx) {
+    static int per_sm = 0;
+    if (!per_sm) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_compact_ht<WIDE>, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    }
+    return (uint64_t)ctx->n_sm * (uint64_t)per_sm * 4ull;
+}
+
 // stage 1 on input that is already resident: one chunk
 static int stage_scan(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const void* d_bases, const void* d_inv, uint64_t n_pos,
                       ScanState* S, fkm_stats* st) {
@@ -524,7 +535,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
                         Q.out_keys = ch.keys; Q.out_cnt = ch.cnt; Q.clear = 0; Q.cap_overflow = d_ovf + 1; Q.acc = d_acc;
                         CKC(cudaMemsetAsync(d_cursor + lo, 0, (size_t)(hi - lo) * 8, s));
                         CKC(cudaEventRecord(ctx->ev[6], s));
-                        const unsigned grid = (unsigned)std::min<uint64_t>((slots + 1023) / 1024, (uint64_t)ctx->n_sm * 8);
+                        const unsigned grid = (unsigned)std::min<uint64_t>((slots + 1023) / 1024, compact_grid<WIDE>(ctx));
                         k_compact_ht<WIDE><<<grid, 256, 0, s>>>(Q); CKLC();
                         CKC(cudaEventRecord(ctx->ev[7], s));
                         CKC(cudaStreamSynchronize(s));
@@ -597,7 +608,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
                     Q.table = d_tab; Q.n_slots = bt.slots; Q.tbl_base = d_tb_all + bt.tb_idx; Q.n_bins = bt.hi - bt.lo; Q.bin_lo = bt.lo;
                     Q.out_base = d_out_base; Q.out_cursor = d_cursor; Q.out_origin = out_total; Q.out_cap = out_cap;
                     Q.out_keys = ch.keys; Q.out_cnt = ch.cnt; Q.clear = 1; Q.cap_overflow = d_ovf + 1; Q.acc = d_acc;
-                    const unsigned grid = (unsigned)std::min<uint64_t>((bt.slots + 1023) / 1024, (uint64_t)ctx->n_sm * 8);
+                    const unsigned grid = (unsigned)std::min<uint64_t>((bt.slots + 1023) / 1024, compact_grid<WIDE>(ctx));
                     k_compact_ht<WIDE><<<grid, 256, 0, s>>>(Q); CKLC();
                 }
                 if (sample) { CKC(cudaEventRecord(ctx->evs[3 * sampled + 2], s)); sampled++; }
