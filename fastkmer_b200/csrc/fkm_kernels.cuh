@@ -473,6 +473,7 @@ struct CountParams {
     unsigned long long* bin_distinct;           // [B] distinct k-mers per bin (claims)
     int* overflow;                              // set when a probe sequence exceeds max_probe
     int k; int max_probe;
+    int first_state;                            // 0: read the slot, CAS only when it looks empty; 1: CAS straight away (every probe is ONE atomic at the slot's home L2 slice)
 };
 
 // 32-bit table hash (murmur3 finaliser over the folded key); the slot is mulhi(hash, size)
@@ -599,6 +600,7 @@ __global__ void __launch_bounds__(256) k_count_ht(const CountParams P) {
         // 0 = read the slot, 1 = CAS the empty slot, 2 = done (wants a refill), 3 = idle (pool exhausted).
         const uint32_t lt_mask = (1u << lane) - 1u;
         uint32_t next = 0;                                   // first unassigned k-mer of the pool (warp-uniform)
+        const int first_state = P.first_state;
         Key key = Key(); unsigned long long slot = 0; int state = 2;
         for (int round = 0;; round++) {
             const uint32_t want = __ballot_sync(FULL, state == 2);
@@ -613,7 +615,7 @@ __global__ void __launch_bounds__(256) k_count_ht(const CountParams P) {
                         if constexpr (!WIDE) key = kmer_at_narrow(&s_rec[warp][lo_ * RW], j, P.k);
                         else key = kmer_at_wide(&s_rec[warp][lo_ * RW], j, P.k);
                         slot = slot_of(key_hash(key), size);
-                        state = 0;
+                        state = first_state;
                     } else state = 3;
                 }
                 next += __popc(want);
@@ -642,7 +644,7 @@ __global__ void __launch_bounds__(256) k_count_ht(const CountParams P) {
                 if (state == 1 && is_empty) { claims++; state = 2; }                 // claimed: count 0 == seen once, no RED
                 else if (key_eq(got, key)) { atomicAdd(cp, 1u); state = 2; }
                 else if (state == 0 && maybe_empty) state = 1;
-                else { if (++slot == size) slot = 0; state = 0; }
+                else { if (++slot == size) slot = 0; state = first_state; }
             }
             if (round > (int)T + 2 * P.max_probe) { ovf = true; break; }            // warp-uniform bound on the rounds
         }

@@ -91,6 +91,7 @@ struct fkm_ctx {
     double load_factor = 0.6;
     double ingest_chunk_bytes = 256.0 * (1 << 20);   // FASTA text is streamed to the GPU in chunks of about this size
     double debug_event_scale = 1.0;   // test hook: scales the run-event list capacity (forces the second-scan fallback)
+    double cas_first = 0.0;           // hash path: 1 = probe with the CAS itself instead of a read followed by a CAS
     double debug_force_lsd = 0.0;     // sort path: 0 = auto (MSD + shared-memory chunk sort for 64-bit keys, LSD passes for 128-bit), 1 = LSD, 2 = MSD
     double debug_rho_scale = 1.0;     // test hook: scales the learnt distinct/k-mer ratio (forces the overflow fallback)
     double async_table_bytes = 1024.0 * (1 << 20); // tables of one asynchronous batch; 0 disables the asynchronous phase (0.25-16 GB all within 8 %, profiles/r1_table_sweep.txt)
@@ -171,6 +172,7 @@ extern "C" int fkm_ctx_set(fkm_ctx* c, const char* name, double v) {
     else if (!strcmp(name, "load_factor")) c->load_factor = v;
     else if (!strcmp(name, "async_table_bytes") || !strcmp(name, "l2_table_bytes")) c->async_table_bytes = v;
     else if (!strcmp(name, "debug_rho_scale")) c->debug_rho_scale = v;
+    else if (!strcmp(name, "cas_first")) c->cas_first = v;
     else if (!strcmp(name, "debug_force_lsd")) c->debug_force_lsd = v;
     else if (!strcmp(name, "debug_event_scale")) c->debug_event_scale = v;
     else if (!strcmp(name, "ingest_chunk_bytes")) c->ingest_chunk_bytes = v;
@@ -505,7 +507,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
                     CountParams C;
                     C.records = d_records; C.rec_lo = h_base[(size_t)lo]; C.rec_hi = h_base[(size_t)hi];
                     C.bin_base = d_bin_base; C.bin_lo = lo; C.bin_hi = hi; C.table = d_table; C.tbl_base = d_tbl_base;
-                    C.bin_distinct = d_distinct; C.overflow = d_ovf; C.k = cfg->k; C.max_probe = 512;
+                    C.bin_distinct = d_distinct; C.overflow = d_ovf; C.k = cfg->k; C.max_probe = 512; C.first_state = ctx->cas_first >= 1.0 ? 1 : 0;
                     const uint64_t nr = C.rec_hi - C.rec_lo;
                     if (nr) { k_count_ht<WIDE><<<(unsigned)((nr + 255) / 256), 256, 0, s>>>(C); CKLC(); }
                     k_bin_offsets<<<1, 256, 0, s>>>(d_distinct, d_out_base, lo, hi, d_small); CKLC();
@@ -597,7 +599,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
                 CountParams C;
                 C.records = d_records; C.rec_lo = h_base[(size_t)bt.lo]; C.rec_hi = h_base[(size_t)bt.hi];
                 C.bin_base = d_bin_base; C.bin_lo = bt.lo; C.bin_hi = bt.hi; C.table = d_tab; C.tbl_base = d_tb_all + bt.tb_idx;
-                C.bin_distinct = d_distinct; C.overflow = d_ovf; C.k = cfg->k; C.max_probe = 512;
+                C.bin_distinct = d_distinct; C.overflow = d_ovf; C.k = cfg->k; C.max_probe = 512; C.first_state = ctx->cas_first >= 1.0 ? 1 : 0;
                 const uint64_t nr = C.rec_hi - C.rec_lo;
                 if (sample) CKC(cudaEventRecord(ctx->evs[3 * sampled], s));
                 if (nr) { k_count_ht<WIDE><<<(unsigned)((nr + 255) / 256), 256, 0, s>>>(C); CKLC(); }

@@ -86,7 +86,8 @@ const char* fkm_last_error(void);
 int  fkm_ctx_create(int device, void* stream, fkm_ctx** out);
 void fkm_ctx_destroy(fkm_ctx* ctx);
 int  fkm_ctx_sync(fkm_ctx* ctx);
-/* tuning knobs (optional): name in {"table_budget_bytes","async_table_bytes","sort_budget_keys","load_factor","ingest_chunk_bytes"} */
+/* tuning knobs (optional): name in {"table_budget_bytes","async_table_bytes","sort_budget_keys","load_factor","ingest_chunk_bytes",
+ * "cas_first" (experiment: probe with the CAS itself; slower, see profiles/README.md)} */
 int  fkm_ctx_set(fkm_ctx* ctx, const char* name, double value);
 
 /* b = min(4^m, max_b) and outputDir = outputDirectory + prefix + "k"+k+"_m"+m+"_x"+x+"_b"+b+"_s"+sequenceType
