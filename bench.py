@@ -254,11 +254,13 @@ def main():
     launches0 = api.load_library().fkm_total_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage = [0.0] * 8
+    ms_fold = 0.0
     e0.record(stream)
     for _ in range(args.steps):
         st = step_resident()
         for i in range(8):
             stage[i] += st["ms_stage"][i]
+        ms_fold += st["ms_fold"]
     e1.record(stream)
     barrier()
     launches = api.load_library().fkm_total_launches() - launches0
@@ -270,6 +272,7 @@ def main():
         ms = float(t.item())
     ms_step = ms / args.steps
     stage = [s / args.steps for s in stage]
+    ms_fold /= args.steps
     n_bases_total = wl.n_bases_total(world)
     n_kmers_total = st["n_kmers_global"] if "n_kmers_global" in st else st["n_kmers"]
     n_distinct_total = st["n_distinct_global"] if "n_distinct_global" in st else st["n_distinct"]
@@ -327,11 +330,15 @@ def main():
     # the super-k-mer stream once (L_s/4 algorithmic bytes); the distinct (k-mer,count) pairs leave through stage 4.
     n_count_launches = max(1, int(st["n_batches"]))
     count_bytes = (L_s / 4) / world
-    count_ms = stage[3]
+    count_ms = stage[3] + ms_fold                   # folding identical records (when on) is part of the count stage
     traffic = None
     try:                                              # measured DRAM bytes per record of k_count_ht (one ncu --set full capture)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1d_count_ht_traffic.json")))
-        traffic = tj["dram_bytes_per_record"] * (st["n_superkmers"] / n_count_launches)
+        if st["n_folded_records"]:                    # the kernel reads folded (weighted) records: its own capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1f_count_ht_traffic.json")))
+            traffic = tj["dram_bytes_per_record"] * (st["n_folded_records"] / n_count_launches)
+        else:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1d_count_ht_traffic.json")))
+            traffic = tj["dram_bytes_per_record"] * (st["n_superkmers"] / n_count_launches)
     except Exception:
         pass
     if not wl.c["ht"] or wl.c["k"] > 32:
@@ -355,8 +362,9 @@ def main():
             "config": {"workload": wl.c["name"] + (" (per GPU; 1% substitutions, 0.1% N)" if wl.kind == "reads" else ""),
                        "reads_per_gpu": wl.c.get("reads"), "n_bases": n_bases_total,
                        "n_kmers": int(n_kmers_total), "n_distinct": int(n_distinct_total),
+                       "n_superkmers": int(st["n_superkmers"]), "n_folded_records": int(st["n_folded_records"]),
                        "l2": "inputs (%.1f GB packed) larger than L2, no flush" % (n_pos * 3 / 8 / 1e9)},
-            "stage_ms": {"histogram": stage[1], "scatter": stage[2], "count": stage[3], "compact": stage[4], "digest": stage[5],
+            "stage_ms": {"histogram": stage[1], "scatter": stage[2], "fold": ms_fold, "count": stage[3], "compact": stage[4], "digest": stage[5],
                          "device_pipeline": stage[7]},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "shuffle": shuffle}

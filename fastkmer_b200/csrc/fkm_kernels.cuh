@@ -124,17 +124,36 @@ __device__ __forceinline__ uint32_t revcomp32(uint32_t v, int len) {       // le
     return x >> (32 - 2 * len);
 }
 
+// Record folding (hash path, NARROW records): a record and its reverse complement hold the same canonical
+// k-mers, and so do two records that differ only behind their n+k-1 bases.  Zero the unused tail and keep the
+// smaller of the string and its reverse complement (left-aligned, so the order is lexicographic): identical
+// super-k-mers of different reads, either strand, become bit-identical records.  w1's n byte must be clear.
+__device__ __forceinline__ void canon_record_narrow(uint64_t& w0, uint64_t& w1, int len) {
+    const int bits = 2 * len;                                               // 2..120
+    w0 &= bits >= 64 ? ~0ull : ~0ull << (64 - bits);
+    w1 &= bits <= 64 ? 0ull : ~0ull << (128 - bits);
+    // complement, reverse all 64 base positions: the string's reverse complement lands in the low `bits` bits
+    const uint64_t c_hi = swap_pairs(__brevll(~w1)), c_lo = swap_pairs(__brevll(~w0));
+    const int sft = 128 - bits;                                             // 8..126: shift it back to the top
+    uint64_t r0, r1;
+    if (sft >= 64) { r0 = c_lo << (sft - 64); r1 = 0ull; }
+    else { r0 = (c_hi << sft) | (c_lo >> (64 - sft)); r1 = c_lo << sft; }
+    if (r0 < w0 || (r0 == w0 && r1 < w1)) { w0 = r0; w1 = r1; }
+}
+
 // bases [a, a+n+k-1) -> one super-k-mer record at `slot`
 template <bool WIDE>
 __device__ __forceinline__ void write_record(void* records, unsigned long long slot, const uint64_t* bases, uint64_t n_words,
-                                             unsigned long long a, uint32_t nn) {
+                                             unsigned long long a, uint32_t nn, int canon_len = 0) {
     auto ld = [&](unsigned long long gw) -> uint64_t { return gw < n_words ? bases[gw] : 0ull; };
     const unsigned long long j = a >> 5; const uint32_t sh = 2u * (uint32_t)(a & 31ull);
     if constexpr (!WIDE) {
         uint64_t w0 = ld(j), w1 = ld(j + 1), w2 = ld(j + 2);
         uint64_t r0 = sh ? ((w0 << sh) | (w1 >> (64 - sh))) : w0;
         uint64_t r1 = sh ? ((w1 << sh) | (w2 >> (64 - sh))) : w1;
-        r1 = (r1 & ~0xFFull) | (uint64_t)nn;
+        r1 &= ~0xFFull;
+        if (canon_len) canon_record_narrow(r0, r1, canon_len);
+        r1 |= (uint64_t)nn;
         reinterpret_cast<ulonglong2*>(records)[slot] = make_ulonglong2(r0, r1);
     } else {
         uint64_t x0 = ld(j), x1 = ld(j + 1), x2 = ld(j + 2), x3 = ld(j + 3), x4 = ld(j + 4);
@@ -354,6 +373,7 @@ struct ScatterParams {
     const uint64_t* bases; uint64_t n_words;
     uint32_t B; int cap; int k;
     const unsigned long long* bin_base; unsigned long long* cursor; void* records;
+    int canon;                                  // NARROW only: write canonical, tail-zeroed records (they are going to be folded)
 };
 template <bool WIDE>
 __global__ void __launch_bounds__(256) k_scatter_events(const ScatterParams P) {
@@ -377,14 +397,17 @@ __global__ void __launch_bounds__(256) k_scatter_events(const ScatterParams P) {
         uint64_t r[NW - 1];
 #pragma unroll
         for (int q = 0; q < NW - 1; q++) r[q] = sh ? ((w[q] << sh) | (w[q + 1] >> (64 - sh))) : w[q];
-        r[NW - 2] = (r[NW - 2] & ~0xFFull) | (uint64_t)nn;
+        r[NW - 2] &= ~0xFFull;
+        if constexpr (!WIDE) { if (P.canon) canon_record_narrow(r[0], r[1], (int)nn + P.k - 1); }
+        r[NW - 2] |= (uint64_t)nn;
         ulonglong2* dst = reinterpret_cast<ulonglong2*>(P.records) + (WIDE ? 2 : 1) * slot0;
         dst[0] = make_ulonglong2(r[0], r[1]);
         if constexpr (WIDE) dst[1] = make_ulonglong2(r[2], r[3]);
     }
     for (uint32_t pc = 1, off = (uint32_t)P.cap; off < n; off += (uint32_t)P.cap, pc++) {
         const uint32_t nn = min((uint32_t)P.cap, n - off);
-        write_record<WIDE>(P.records, slot0 + pc, P.bases, P.n_words, rs + off - (unsigned long long)(P.k - 1), nn);
+        write_record<WIDE>(P.records, slot0 + pc, P.bases, P.n_words, rs + off - (unsigned long long)(P.k - 1), nn,
+                           (!WIDE && P.canon) ? (int)nn + P.k - 1 : 0);
     }
 }
 
@@ -473,6 +496,7 @@ struct CountParams {
     unsigned long long* bin_distinct;           // [B] distinct k-mers per bin (claims)
     int* overflow;                              // set when a probe sequence exceeds max_probe
     int k; int max_probe;
+    const uint32_t* weights;                    // [records] multiplicity of a folded record, or NULL (every record counts once)
     int first_state;                            // 0: read the slot, CAS only when it looks empty; 1: CAS straight away (every probe is ONE atomic at the slot's home L2 slice)
 };
 
@@ -494,7 +518,7 @@ __device__ __forceinline__ unsigned long long slot_of(uint32_t h, unsigned long 
 }
 
 // returns 1 if this call claimed a new slot, 0 if the key was present, -1 on overflow
-__device__ __forceinline__ int ht_insert(SlotN* tbl, unsigned long long size, uint64_t key, int max_probe) {
+__device__ __forceinline__ int ht_insert(SlotN* tbl, unsigned long long size, uint64_t key, int max_probe, uint32_t weight = 1u) {
     unsigned long long slot = slot_of(key_hash(key), size);
     for (int probe = 0; probe < max_probe; probe++) {
         SlotN* s = tbl + slot;
@@ -502,14 +526,14 @@ __device__ __forceinline__ int ht_insert(SlotN* tbl, unsigned long long size, ui
         int claimed = 0;
         if (cur == ~0ull) {
             cur = atomicCAS((unsigned long long*)&s->key, ~0ull, (unsigned long long)key);
-            if (cur == ~0ull) return 1;                        // claimed: the slot's count of 0 already means "seen once"
+            if (cur == ~0ull) { if (weight > 1u) atomicAdd(&s->cnt, weight - 1u); return 1; }   // claimed: the slot's count of 0 already means "seen once"
         }
-        if (cur == key) { atomicAdd(&s->cnt, 1u); return claimed; }
+        if (cur == key) { atomicAdd(&s->cnt, weight); return claimed; }
         if (++slot == size) slot = 0;
     }
     return -1;
 }
-__device__ __forceinline__ int ht_insert(SlotW* tbl, unsigned long long size, key128 key, int max_probe) {
+__device__ __forceinline__ int ht_insert(SlotW* tbl, unsigned long long size, key128 key, int max_probe, uint32_t weight = 1u) {
     unsigned long long slot = slot_of(key_hash(key), size);
     const key128 empty = {~0ull, ~0ull};
     for (int probe = 0; probe < max_probe; probe++) {
@@ -520,9 +544,9 @@ __device__ __forceinline__ int ht_insert(SlotW* tbl, unsigned long long size, ke
         // a half equal to all-ones may be a torn read of a slot being claimed: let the CAS decide
         if (cur.lo == ~0ull || cur.hi == ~0ull) {
             cur = cas128(&s->key, empty, key);
-            if (key_eq(cur, empty)) return 1;                  // claimed: count 0 == seen once
+            if (key_eq(cur, empty)) { if (weight > 1u) atomicAdd(&s->cnt, weight - 1u); return 1; }   // claimed: count 0 == seen once
         }
-        if (key_eq(cur, key)) { atomicAdd(&s->cnt, 1u); return claimed; }
+        if (key_eq(cur, key)) { atomicAdd(&s->cnt, weight); return claimed; }
         if (++slot == size) slot = 0;
     }
     return -1;
@@ -563,13 +587,15 @@ __global__ void __launch_bounds__(256) k_count_ht(const CountParams P) {
     constexpr int RW = Traits<WIDE>::kRecWords;
     __shared__ uint64_t s_rec[8][32 * RW];
     __shared__ uint32_t s_off[8][32];
+    __shared__ uint32_t s_wt[WIDE ? 1 : 8][32];
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned long long r = P.rec_lo + ((unsigned long long)blockIdx.x * 8 + warp) * 32 + lane;
     const bool in = r < P.rec_hi;
     uint64_t w[RW];
-    uint32_t n = 0; int bin = -1;
+    uint32_t n = 0; int bin = -1; uint32_t wt = 1u;
     if (in) {
+        if constexpr (!WIDE) { if (P.weights) wt = P.weights[r]; }          // only 16-byte records are ever folded
         const ulonglong2* src = reinterpret_cast<const ulonglong2*>(P.records) + (RW / 2) * r;
 #pragma unroll
         for (int i = 0; i < RW / 2; i++) { ulonglong2 v = __ldcs(src + i); w[2 * i] = v.x; w[2 * i + 1] = v.y; }   // read once: keep L2 for the tables
@@ -586,6 +612,7 @@ __global__ void __launch_bounds__(256) k_count_ht(const CountParams P) {
     const uint32_t T = __shfl_sync(FULL, incl, 31);
     if (T == 0) return;
     s_off[warp][lane] = excl;
+    if constexpr (!WIDE) s_wt[warp][lane] = wt;
     __syncwarp();
     const int bin0 = __shfl_sync(FULL, bin, 0);
     const bool uniform = __all_sync(FULL, bin == bin0 || bin < 0);
@@ -601,7 +628,7 @@ __global__ void __launch_bounds__(256) k_count_ht(const CountParams P) {
         const uint32_t lt_mask = (1u << lane) - 1u;
         uint32_t next = 0;                                   // first unassigned k-mer of the pool (warp-uniform)
         const int first_state = P.first_state;
-        Key key = Key(); unsigned long long slot = 0; int state = 2;
+        Key key = Key(); unsigned long long slot = 0; int state = 2; uint32_t kw = 1u;   // kw: weight of the k-mer's record
         for (int round = 0;; round++) {
             const uint32_t want = __ballot_sync(FULL, state == 2);
             if (want) {
@@ -615,6 +642,7 @@ __global__ void __launch_bounds__(256) k_count_ht(const CountParams P) {
                         if constexpr (!WIDE) key = kmer_at_narrow(&s_rec[warp][lo_ * RW], j, P.k);
                         else key = kmer_at_wide(&s_rec[warp][lo_ * RW], j, P.k);
                         slot = slot_of(key_hash(key), size);
+                        if constexpr (!WIDE) kw = s_wt[warp][lo_];
                         state = first_state;
                     } else state = 3;
                 }
@@ -641,8 +669,8 @@ __global__ void __launch_bounds__(256) k_count_ht(const CountParams P) {
                 uint32_t* cp;
                 if constexpr (!WIDE) cp = &(reinterpret_cast<SlotN*>(tbl) + slot)->cnt;
                 else cp = &(reinterpret_cast<SlotW*>(tbl) + slot)->cnt;
-                if (state == 1 && is_empty) { claims++; state = 2; }                 // claimed: count 0 == seen once, no RED
-                else if (key_eq(got, key)) { atomicAdd(cp, 1u); state = 2; }
+                if (state == 1 && is_empty) { claims++; if (kw > 1u) atomicAdd(cp, kw - 1u); state = 2; }   // claimed: count 0 == seen once, no RED
+                else if (key_eq(got, key)) { atomicAdd(cp, kw); state = 2; }
                 else if (state == 0 && maybe_empty) state = 1;
                 else { if (++slot == size) slot = 0; state = first_state; }
             }
@@ -657,11 +685,94 @@ __global__ void __launch_bounds__(256) k_count_ht(const CountParams P) {
         Slot* tbl = reinterpret_cast<Slot*>(P.table) + tb0;
         for (int j = 0; j < (int)n; j++) {
             int c;
-            if constexpr (!WIDE) c = ht_insert(reinterpret_cast<SlotN*>(tbl), size, kmer_at_narrow(&s_rec[warp][lane * RW], j, P.k), P.max_probe);
-            else c = ht_insert(reinterpret_cast<SlotW*>(tbl), size, kmer_at_wide(&s_rec[warp][lane * RW], j, P.k), P.max_probe);
+            if constexpr (!WIDE) c = ht_insert(reinterpret_cast<SlotN*>(tbl), size, kmer_at_narrow(&s_rec[warp][lane * RW], j, P.k), P.max_probe, wt);
+            else c = ht_insert(reinterpret_cast<SlotW*>(tbl), size, kmer_at_wide(&s_rec[warp][lane * RW], j, P.k), P.max_probe, wt);
             if (c < 0) ovf = true; else claims += (unsigned)c;
         }
         if (claims) atomicAdd(&P.bin_distinct[bin], (unsigned long long)claims);
+    }
+    if (ovf) *P.overflow = 1;
+}
+
+// Record folding: every NARROW record (16 bytes, canonical orientation, see canon_record_narrow) is inserted
+// as a 128-bit key into its bin's table of SlotW; the slot count becomes its multiplicity - 1.  The tables are
+// then compacted by k_compact_ht<true> into dense (record, multiplicity) arrays, bin-major like the input.  A
+// record is never all ones (its low byte is n <= 60), so the table's EMPTY key cannot collide.
+struct FoldParams {
+    const void* records; unsigned long long rec_lo, rec_hi;
+    const unsigned long long* bin_base; int bin_lo, bin_hi;
+    void* table; const unsigned long long* tbl_base;
+    unsigned long long* bin_distinct;           // [B] distinct records per bin
+    int* overflow; int max_probe;
+};
+static constexpr int kFoldPerWarp = 256;
+// One warp per 256 consecutive records, staged in shared memory; the lanes then run k_count_ht's refill state
+// machine over that pool (0 = read the slot, 1 = CAS the empty slot, 2 = done, take the next record, 3 = pool
+// exhausted), so every round trip carries one probe per lane whatever the lengths of the probe chains.
+__global__ void __launch_bounds__(256) k_fold_insert(const FoldParams P) {
+    __shared__ ulonglong2 s_rec[8][kFoldPerWarp];
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long r0 = P.rec_lo + ((unsigned long long)blockIdx.x * 8 + warp) * kFoldPerWarp;
+    if (r0 >= P.rec_hi) return;                              // warp-uniform
+    const uint32_t T = (uint32_t)min((unsigned long long)kFoldPerWarp, P.rec_hi - r0);
+    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(P.records) + r0;
+    for (uint32_t i = lane; i < T; i += 32) s_rec[warp][i] = __ldcs(src + i);
+    __syncwarp();
+    const int bin_first = find_bin(P.bin_base, P.bin_lo, P.bin_hi, r0);
+    const int bin_last = find_bin(P.bin_base, P.bin_lo, P.bin_hi, r0 + T - 1);
+    bool ovf = false;
+    if (bin_first == bin_last) {
+        const unsigned long long tb0 = P.tbl_base[bin_first - P.bin_lo];
+        const unsigned long long size = P.tbl_base[bin_first - P.bin_lo + 1] - tb0;
+        SlotW* tbl = reinterpret_cast<SlotW*>(P.table) + tb0;
+        const uint32_t lt_mask = (1u << lane) - 1u;
+        const key128 empty = {~0ull, ~0ull};
+        uint32_t next = 0; unsigned int claims = 0;
+        key128 key = empty; unsigned long long slot = 0; int state = 2;
+        for (int round = 0;; round++) {
+            const uint32_t want = __ballot_sync(FULL, state == 2);
+            if (want) {
+                if (state == 2) {
+                    const uint32_t t = next + __popc(want & lt_mask);
+                    if (t < T) {
+                        const ulonglong2 v = s_rec[warp][t];
+                        key.lo = v.x; key.hi = v.y;          // the memory image of the record
+                        slot = slot_of(key_hash(key), size);
+                        state = 0;
+                    } else state = 3;
+                }
+                next += __popc(want);
+            }
+            if (__all_sync(FULL, state == 3)) break;
+            SlotW* sp = tbl + slot;
+            key128 got = empty;
+            if (state == 0) { const ulonglong2 kv = __ldcg(reinterpret_cast<const ulonglong2*>(&sp->key)); got.lo = kv.x; got.hi = kv.y; }
+            else if (state == 1) got = cas128(&sp->key, empty, key);
+            if (state < 2) {
+                // a half equal to all-ones may be a torn read of a slot being claimed: the CAS decides
+                const bool is_empty = got.lo == ~0ull && got.hi == ~0ull;
+                const bool maybe_empty = got.lo == ~0ull || got.hi == ~0ull;
+                if (state == 1 && is_empty) { claims++; state = 2; }              // count 0 == seen once
+                else if (key_eq(got, key)) { atomicAdd(&sp->cnt, 1u); state = 2; }
+                else if (state == 0 && maybe_empty) state = 1;
+                else { if (++slot == size) slot = 0; state = 0; }
+            }
+            if (round > (int)T + 2 * P.max_probe) { ovf = true; break; }           // warp-uniform bound on the rounds
+        }
+        const unsigned int tot = __reduce_add_sync(FULL, claims);
+        if (lane == 0 && tot) atomicAdd(&P.bin_distinct[bin_first], (unsigned long long)tot);
+    } else {
+        // the warp's records straddle a bin boundary (rare): one lane per record
+        for (uint32_t i = lane; i < T; i += 32) {
+            const int bin = find_bin(P.bin_base, bin_first, bin_last + 1, r0 + i);
+            const unsigned long long tb0 = P.tbl_base[bin - P.bin_lo];
+            const unsigned long long size = P.tbl_base[bin - P.bin_lo + 1] - tb0;
+            const ulonglong2 v = s_rec[warp][i];
+            key128 key; key.lo = v.x; key.hi = v.y;
+            const int c = ht_insert(reinterpret_cast<SlotW*>(P.table) + tb0, size, key, P.max_probe);
+            if (c < 0) ovf = true; else if (c) atomicAdd(&P.bin_distinct[bin], 1ull);
+        }
     }
     if (ovf) *P.overflow = 1;
 }

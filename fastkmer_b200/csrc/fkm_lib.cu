@@ -91,6 +91,9 @@ struct fkm_ctx {
     double load_factor = 0.6;
     double ingest_chunk_bytes = 256.0 * (1 << 20);   // FASTA text is streamed to the GPU in chunks of about this size
     double debug_event_scale = 1.0;   // test hook: scales the run-event list capacity (forces the second-scan fallback)
+    double fold_records = 1.0;        // hash path, k <= 32: 1 = fold identical super-k-mer records into one weighted record before counting
+    double fold_table_bytes = 1024.0 * 1048576.0;   // ... in batches of bins whose record tables (32-byte slots) fit this
+    double fold_max_ratio = 0.6;      // ... unless the first batch shows that more than this share of the records is distinct
     double cas_first = 0.0;           // hash path: 1 = probe with the CAS itself instead of a read followed by a CAS
     double debug_force_lsd = 0.0;     // sort path: 0 = auto (MSD + shared-memory chunk sort for 64-bit keys, LSD passes for 128-bit), 1 = LSD, 2 = MSD
     double debug_rho_scale = 1.0;     // test hook: scales the learnt distinct/k-mer ratio (forces the overflow fallback)
@@ -172,6 +175,9 @@ extern "C" int fkm_ctx_set(fkm_ctx* c, const char* name, double v) {
     else if (!strcmp(name, "load_factor")) c->load_factor = v;
     else if (!strcmp(name, "async_table_bytes") || !strcmp(name, "l2_table_bytes")) c->async_table_bytes = v;
     else if (!strcmp(name, "debug_rho_scale")) c->debug_rho_scale = v;
+    else if (!strcmp(name, "fold_records")) c->fold_records = v;
+    else if (!strcmp(name, "fold_max_ratio")) c->fold_max_ratio = v;
+    else if (!strcmp(name, "fold_table_bytes")) c->fold_table_bytes = v;
     else if (!strcmp(name, "cas_first")) c->cas_first = v;
     else if (!strcmp(name, "debug_force_lsd")) c->debug_force_lsd = v;
     else if (!strcmp(name, "debug_event_scale")) c->debug_event_scale = v;
@@ -376,7 +382,7 @@ static int stage_scan(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const void
 // stage 2: run events -> super-k-mer records at d_records[bin_base[bin] + ...] (the "shuffle").  bin_base is any
 // per-bin record offset table: bin-major on one GPU, owner-major for the multi-GPU send buffer.
 static int stage_scatter(fkm_ctx* ctx, ScanState* S, const unsigned long long* d_bin_base, unsigned long long* d_cursor,
-                         void* d_records, uint64_t n_rec, fkm_stats* st) {
+                         void* d_records, uint64_t n_rec, fkm_stats* st, bool canon = false) {
     cudaStream_t s = ctx->stream;
     const fkm_config* cfg = &S->cfg;
     const bool wide = cfg->k > 32;
@@ -386,7 +392,7 @@ static int stage_scatter(fkm_ctx* ctx, ScanState* S, const unsigned long long* d
             ScatterParams Q;
             Q.events = C.d_events; Q.n_events = C.n_events; Q.bases = (const uint64_t*)C.d_bases; Q.n_words = (C.n_pos + 31) / 32;
             Q.B = (uint32_t)S->B; Q.cap = wide ? (125 - cfg->k) : (61 - cfg->k); Q.k = cfg->k;
-            Q.bin_base = d_bin_base; Q.cursor = d_cursor; Q.records = d_records;
+            Q.bin_base = d_bin_base; Q.cursor = d_cursor; Q.records = d_records; Q.canon = (canon && !wide) ? 1 : 0;
             if (C.n_events) {
                 const unsigned grid = (unsigned)((C.n_events + 255) / 256);
                 if (wide) k_scatter_events<true><<<grid, 256, 0, s>>>(Q); else k_scatter_events<false><<<grid, 256, 0, s>>>(Q);
@@ -462,14 +468,128 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
     st->n_kmers = n_kmers; st->n_superkmers = n_rec; st->superkmer_bytes = n_rec * rec_bytes; st->n_nonempty_bins = nonempty;
     CKC(cudaMemcpyAsync(d_bin_base, h_base.data(), bB + 8, cudaMemcpyHostToDevice, s));
     st->h2d_bytes += bB + 8;
+    const bool want_fold = !WIDE && cfg->use_ht && ctx->fold_records >= 1.0 && n_rec >= 4096;
     if (!pre) {
         CKC(dmalloc(ctx, &d_records, std::max<size_t>(16, (size_t)n_rec * rec_bytes)));
         tr.mark("records allocated", (long long)n_rec);
-        rc = stage_scatter(ctx, &scan, d_bin_base, d_cursor, d_records, n_rec, st); if (rc) return rc;
+        rc = stage_scatter(ctx, &scan, d_bin_base, d_cursor, d_records, n_rec, st, want_fold); if (rc) return rc;
     } else {
         d_records = const_cast<void*>(pre->d_records);
         CKC(cudaEventRecord(ctx->ev[2], s));
     }
+
+    // ---- stage 2b (hash path, 64-bit k-mers, optional): fold identical records.  Reads of a deeply sequenced
+    // genome repeat its super-k-mers once per covering read (either strand); every k-mer of a repeated record costs
+    // one atomic in k_count_ht.  Folding costs one 128-bit insertion per RECORD and lets the count stage add the
+    // multiplicity with one atomic per k-mer of a DISTINCT record.  Batches of bins like the count stage; the first
+    // batch is synchronous and decides whether the input repeats enough for the rest to pay.
+    const void* d_count_records = d_records;      // what the count stage reads
+    const uint32_t* d_weights = nullptr;
+    float ms_fold = 0;
+    if constexpr (!WIDE) {
+        if (want_fold) {
+            const uint64_t budget_slots = std::max<uint64_t>(1024, (uint64_t)(ctx->fold_table_bytes / sizeof(SlotW)));
+            struct FoldBatch { int lo, hi; size_t tb_idx; uint64_t slots; };
+            std::vector<FoldBatch> fbs; std::vector<unsigned long long> ftb;
+            // bins [lo0, B) -> batches; a bin's table holds share * records / 0.6 slots.  The sampled first batch is
+            // small and sized for all-distinct records (share 1); the rest is sized from the share it observed.
+            auto plan = [&](int lo0, double share, bool sample_only) -> uint64_t {
+                uint64_t max_slots = 1024;
+                for (int lo = lo0; lo < B;) {
+                    FoldBatch fb; fb.lo = lo; fb.tb_idx = ftb.size(); ftb.push_back(0);
+                    int hi = lo; uint64_t slots = 0;
+                    while (hi < B) {
+                        const uint64_t c = h_rec[(size_t)hi];
+                        const uint64_t sz = c ? round_up(std::max<uint64_t>((uint64_t)((double)c * share / 0.6) + 1, 1024), 1024) : 0;
+                        if (hi > lo && slots + sz > budget_slots) break;
+                        slots += sz; ftb.push_back(slots); hi++;
+                        if (sample_only && hi - lo >= std::max(1, B / 64) && slots >= budget_slots / 32) break;
+                    }
+                    fb.hi = hi; fb.slots = slots; fbs.push_back(fb); max_slots = std::max(max_slots, slots); lo = hi;
+                    if (sample_only) break;
+                }
+                return max_slots;
+            };
+            unsigned long long *d_ftb = nullptr, *d_fdistinct = nullptr, *d_fbase = nullptr, *d_fcursor = nullptr;
+            void* d_frec = nullptr; uint32_t* d_fwt = nullptr;
+            CKC(dmalloc(ctx, &d_ftb, ((size_t)2 * B + 8) * 8)); CKC(dmalloc(ctx, &d_fdistinct, bB)); CKC(dmalloc(ctx, &d_fbase, bB + 8)); CKC(dmalloc(ctx, &d_fcursor, bB));
+            CKC(dmalloc(ctx, &d_frec, (size_t)n_rec * 16)); CKC(dmalloc(ctx, &d_fwt, (size_t)n_rec * 4));
+            CKC(cudaMemsetAsync(d_fdistinct, 0, bB, s)); CKC(cudaMemsetAsync(d_fbase, 0, bB + 8, s)); CKC(cudaMemsetAsync(d_fcursor, 0, bB, s));
+            CKC(cudaMemsetAsync(d_ovf, 0, 8, s));
+            CKC(cudaEventRecord(ctx->ev[6], s));
+            bool keep = true;
+            size_t done = 0;                               // batches already queued
+            auto run_batches = [&](void* d_ftab) -> int {
+                for (; done < fbs.size(); done++) {
+                    const FoldBatch& fb = fbs[done];
+                    FoldParams F;
+                    F.records = d_records; F.rec_lo = h_base[(size_t)fb.lo]; F.rec_hi = h_base[(size_t)fb.hi];
+                    F.bin_base = d_bin_base; F.bin_lo = fb.lo; F.bin_hi = fb.hi; F.table = d_ftab; F.tbl_base = d_ftb + fb.tb_idx;
+                    F.bin_distinct = d_fdistinct; F.overflow = d_ovf; F.max_probe = 512;
+                    const uint64_t nr = F.rec_hi - F.rec_lo;
+                    if (nr) { k_fold_insert<<<(unsigned)((nr + 8 * kFoldPerWarp - 1) / (8 * kFoldPerWarp)), 256, 0, s>>>(F); CKLC(); }
+                    k_bin_offsets<<<1, 256, 0, s>>>(d_fdistinct, d_fbase, fb.lo, fb.hi, d_small); CKLC();
+                    if (fb.slots) {
+                        CompactParams Q;
+                        Q.table = d_ftab; Q.n_slots = fb.slots; Q.tbl_base = d_ftb + fb.tb_idx; Q.n_bins = fb.hi - fb.lo; Q.bin_lo = fb.lo;
+                        Q.out_base = d_fbase; Q.out_cursor = d_fcursor; Q.out_origin = 0; Q.out_cap = n_rec;
+                        Q.out_keys = d_frec; Q.out_cnt = d_fwt; Q.clear = 1; Q.cap_overflow = d_ovf + 1; Q.acc = nullptr;
+                        const unsigned grid = (unsigned)std::min<uint64_t>((fb.slots + 1023) / 1024, compact_grid<true>(ctx));
+                        k_compact_ht<true><<<grid, 256, 0, s>>>(Q); CKLC();
+                    }
+                }
+                return FKM_OK;
+            };
+            {   // the sample
+                const uint64_t slots0 = plan(0, 1.0, true);
+                void* d_ftab0 = nullptr;
+                CKC(dmalloc(ctx, &d_ftab0, (size_t)slots0 * sizeof(SlotW)));
+                CKC(cudaMemcpyAsync(d_ftb, ftb.data(), ftb.size() * 8, cudaMemcpyHostToDevice, s));
+                st->h2d_bytes += ftb.size() * 8;
+                k_fill_table<true><<<ctx->n_sm * 8, 256, 0, s>>>(d_ftab0, slots0); CKLC();
+                rc = run_batches(d_ftab0); if (rc) { cleanup(); return rc; }
+            }
+            const int lo1 = fbs[0].hi;
+            if (lo1 < B) {
+                unsigned long long folded = 0;
+                CKC(cudaMemcpyAsync(&folded, d_small, 8, cudaMemcpyDeviceToHost, s));
+                CKC(cudaStreamSynchronize(s));
+                st->d2h_bytes += 8;
+                const uint64_t nr0 = h_base[(size_t)lo1] - h_base[0];
+                const double share0 = nr0 ? (double)folded / (double)nr0 : 1.0;
+                if (share0 > ctx->fold_max_ratio) keep = false;
+                else {
+                    const size_t first_new = ftb.size();
+                    const uint64_t slots1 = plan(lo1, std::min(1.0, share0 * 1.3 + 0.03), false);
+                    void* d_ftab1 = nullptr;
+                    CKC(dmalloc(ctx, &d_ftab1, (size_t)slots1 * sizeof(SlotW)));
+                    CKC(cudaMemcpyAsync(d_ftb + first_new, ftb.data() + first_new, (ftb.size() - first_new) * 8, cudaMemcpyHostToDevice, s));
+                    st->h2d_bytes += (ftb.size() - first_new) * 8;
+                    k_fill_table<true><<<ctx->n_sm * 8, 256, 0, s>>>(d_ftab1, slots1); CKLC();
+                    rc = run_batches(d_ftab1); if (rc) { cleanup(); return rc; }
+                }
+            }
+            std::vector<unsigned long long> h_fbase((size_t)B + 1);
+            int flags[2] = {0, 0};
+            if (keep) {
+                CKC(cudaMemcpyAsync(h_fbase.data(), d_fbase, bB + 8, cudaMemcpyDeviceToHost, s));
+                CKC(cudaMemcpyAsync(flags, d_ovf, 8, cudaMemcpyDeviceToHost, s));
+            }
+            CKC(cudaEventRecord(ctx->ev[7], s));
+            CKC(cudaStreamSynchronize(s));
+            cudaEventElapsedTime(&ms_fold, ctx->ev[6], ctx->ev[7]);
+            if (keep && !flags[0] && !flags[1]) {
+                st->d2h_bytes += bB + 16;
+                h_base = h_fbase;                          // the count stage now sees the folded records
+                CKC(cudaMemcpyAsync(d_bin_base, d_fbase, bB + 8, cudaMemcpyDeviceToDevice, s));
+                d_count_records = d_frec; d_weights = d_fwt;
+                st->n_folded_records = h_fbase[(size_t)B];
+            }
+            CKC(cudaMemsetAsync(d_ovf, 0, 8, s));
+            CKC(cudaMemsetAsync(d_small, 0, 64, s));
+        }
+    }
+    st->ms_fold = ms_fold;
 
     // ---- stage 3/4: per-bin exact count, batches of consecutive bins
     uint64_t out_total = 0;
@@ -505,7 +625,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
                     CKC(cudaMemcpyAsync(d_tbl_base, tb.data(), tb.size() * 8, cudaMemcpyHostToDevice, s));
                     st->h2d_bytes += tb.size() * 8;
                     CountParams C;
-                    C.records = d_records; C.rec_lo = h_base[(size_t)lo]; C.rec_hi = h_base[(size_t)hi];
+                    C.records = d_count_records; C.weights = d_weights; C.rec_lo = h_base[(size_t)lo]; C.rec_hi = h_base[(size_t)hi];
                     C.bin_base = d_bin_base; C.bin_lo = lo; C.bin_hi = hi; C.table = d_table; C.tbl_base = d_tbl_base;
                     C.bin_distinct = d_distinct; C.overflow = d_ovf; C.k = cfg->k; C.max_probe = 512; C.first_state = ctx->cas_first >= 1.0 ? 1 : 0;
                     const uint64_t nr = C.rec_hi - C.rec_lo;
@@ -597,7 +717,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
                 const Batch& bt = batches[bi];
                 const bool sample = (bi % stride == stride / 2) && sampled < n_samples;
                 CountParams C;
-                C.records = d_records; C.rec_lo = h_base[(size_t)bt.lo]; C.rec_hi = h_base[(size_t)bt.hi];
+                C.records = d_count_records; C.weights = d_weights; C.rec_lo = h_base[(size_t)bt.lo]; C.rec_hi = h_base[(size_t)bt.hi];
                 C.bin_base = d_bin_base; C.bin_lo = bt.lo; C.bin_hi = bt.hi; C.table = d_tab; C.tbl_base = d_tb_all + bt.tb_idx;
                 C.bin_distinct = d_distinct; C.overflow = d_ovf; C.k = cfg->k; C.max_probe = 512; C.first_state = ctx->cas_first >= 1.0 ? 1 : 0;
                 const uint64_t nr = C.rec_hi - C.rec_lo;
@@ -1115,7 +1235,9 @@ extern "C" int fkm_mg_scatter(fkm_ctx* ctx, const uint64_t* bin_base, void* d_se
     CK(cudaMemsetAsync(d_cursor, 0, bB, ctx->stream));
     uint64_t n_rec = 0; for (int b = 0; b < S->B; b++) n_rec += S->h_rec[(size_t)b];
     fkm_stats st; memset(&st, 0, sizeof st);
-    int rc = stage_scatter(ctx, S, d_bin_base, d_cursor, d_send, n_rec, &st); if (rc) return rc;
+    // canonical, tail-zeroed records when the receiving side is going to fold them (hash path, 16-byte records)
+    const bool canon = S->cfg.use_ht && S->cfg.k <= 32 && ctx->fold_records >= 1.0;
+    int rc = stage_scatter(ctx, S, d_bin_base, d_cursor, d_send, n_rec, &st, canon); if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     return FKM_OK;
 }

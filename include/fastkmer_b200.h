@@ -76,7 +76,9 @@ typedef struct fkm_stats {
     uint64_t n_batches;
     uint64_t n_fallbacks;        /* times the asynchronous count phase had to be redone synchronously */
     double   ms_total;           /* host wall time of the call                               */
-    double   ms_stage[8];        /* 0 parse/pack+H2D 1 histogram 2 scatter 3 count 4 compact/reduce 5 digest 6 D2H/write 7 spare (device, CUDA events) */
+    double   ms_stage[8];        /* 0 parse/pack+H2D 1 histogram 2 scatter 3 count 4 compact/reduce 5 digest 6 D2H/write 7 whole device pipeline (CUDA events) */
+    uint64_t n_folded_records;   /* records left after folding identical ones (knob fold_records); 0 = not folded */
+    double   ms_fold;            /* device time of the folding stage (between scatter and count)       */
 } fkm_stats;
 
 const char* fkm_last_error(void);
@@ -87,6 +89,8 @@ int  fkm_ctx_create(int device, void* stream, fkm_ctx** out);
 void fkm_ctx_destroy(fkm_ctx* ctx);
 int  fkm_ctx_sync(fkm_ctx* ctx);
 /* tuning knobs (optional): name in {"table_budget_bytes","async_table_bytes","sort_budget_keys","load_factor","ingest_chunk_bytes",
+ * "fold_records" (default 1: hash path with k <= 32 folds identical super-k-mer records into one weighted record before
+ * counting, unless the sampled first bins show more than "fold_max_ratio" (0.6) distinct records; 0 = never), "fold_table_bytes",
  * "cas_first" (experiment: probe with the CAS itself; slower, see profiles/README.md)} */
 int  fkm_ctx_set(fkm_ctx* ctx, const char* name, double value);
 

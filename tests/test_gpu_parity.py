@@ -240,6 +240,44 @@ def test_async_phase_overflow_falls_back(oracle):
 
 
 # ---------------------------------------------------------------- the drop-in call and its files
+def test_record_folding_gives_identical_counts(oracle):
+    """fold_records=1 (hash path, k <= 32): identical super-k-mer records, either strand, are folded into one
+    weighted record before counting.  Same (bin, k-mer, count) as the oracle; deep coverage folds a lot, an input
+    without repeats is left alone after the sampled first batch; 128-bit k-mers and the sort path ignore the knob."""
+    rng = random.Random(99)
+    deep = fk.synth_fasta(dict(seeds=(71, 72, 73), genome_len=30000, n_reads=60000, read_len=100)).tobytes()     # 200x coverage
+    flat = fk.synth_fasta(dict(seeds=(74, 75, 76), genome_len=40000000, n_reads=60000, read_len=100)).tobytes()  # 0.15x: no repeats
+    poly = (">a\n" + "A" * 5000 + "\n>t\n" + "T" * 5000 + "\n>ac\n" + "AC" * 3000 + "\n>r\n" +
+            "".join(rng.choice("ACGT") for _ in range(3000)) * 3 + "\n").encode()
+    c2 = fk.Context(0)
+    try:
+        c2.set("fold_records", 1)
+        for text, label in ((deep, "deep"), (poly, "poly"), (flat, "flat")):
+            for k, m, B in ((28, 10, 2048), (31, 11, 64), (12, 4, 100), (32, 7, 1)):
+                want = oracle.count(text, k, m, 3, B, 1, threads=8)
+                for tbl in (1 << 30, 1 << 16):                     # one fold batch / many small ones (sample + asynchronous rest)
+                    c2.set("fold_table_bytes", tbl)
+                    res, st = c2.count_fasta(cfg(k, m, 3, B, 1), text)
+                    assert_same(res.sorted_arrays(), want, "fold %s k=%d tbl=%d" % (label, k, tbl))
+                    assert (st["digest_sum"], st["digest_xor"]) == (want["stats"]["digest_sum"], want["stats"]["digest_xor"])
+                    if st["n_superkmers"] >= 4096:
+                        if label == "deep" and tbl == 1 << 30:          # (small tables: sized from a one-bin sample, may give up)
+                            assert 0 < st["n_folded_records"] < 0.6 * st["n_superkmers"]
+                        if label == "flat" and tbl == 1 << 16 and B > 64:
+                            assert st["n_folded_records"] == 0      # the sample said: not worth it
+        c2.set("fold_table_bytes", 1 << 30)
+        want = oracle.count(deep, 55, 13, 3, 2048, 1, threads=8)
+        res, st = c2.count_fasta(cfg(55, 13, 3, 2048, 1), deep)
+        assert_same(res.sorted_arrays(), want, "fold knob, 128-bit k-mers")
+        assert st["n_folded_records"] == 0
+        want = oracle.count(deep, 28, 10, 3, 2048, 0, threads=8)
+        res, st = c2.count_fasta(cfg(28, 10, 3, 2048, 0), deep)
+        assert_same(res.arrays(), want, "fold knob, sort path")
+        assert st["n_folded_records"] == 0
+    finally:
+        c2.close()
+
+
 @pytest.mark.parametrize("ht", [0, 1])
 def test_execute_job_writes_reference_layout(ctx, oracle, tmp_path, ht):
     fasta = oracle.gen_lcg_fasta(42, 2000, 200, 100)
