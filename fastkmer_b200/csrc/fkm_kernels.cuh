@@ -705,10 +705,10 @@ struct FoldParams {
     unsigned long long* bin_distinct;           // [B] distinct records per bin
     int* overflow; int max_probe;
 };
-static constexpr int kFoldPerWarp = 256;
 // One warp per 256 consecutive records, staged in shared memory; the lanes then run k_count_ht's refill state
 // machine over that pool (0 = read the slot, 1 = CAS the empty slot, 2 = done, take the next record, 3 = pool
 // exhausted), so every round trip carries one probe per lane whatever the lengths of the probe chains.
+template <int kFoldPerWarp>
 __global__ void __launch_bounds__(256) k_fold_insert(const FoldParams P) {
     __shared__ ulonglong2 s_rec[8][kFoldPerWarp];
     const unsigned FULL = 0xFFFFFFFFu;

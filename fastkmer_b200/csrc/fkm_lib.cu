@@ -93,6 +93,7 @@ struct fkm_ctx {
     double debug_event_scale = 1.0;   // test hook: scales the run-event list capacity (forces the second-scan fallback)
     double fold_records = 1.0;        // hash path, k <= 32: 1 = fold identical super-k-mer records into one weighted record before counting
     double fold_table_bytes = 1024.0 * 1048576.0;   // ... in batches of bins whose record tables (32-byte slots) fit this
+    double fold_pool = 256.0;         // ... records per warp in k_fold_insert (64, 128 or 256)
     double fold_max_ratio = 0.6;      // ... unless the first batch shows that more than this share of the records is distinct
     double cas_first = 0.0;           // hash path: 1 = probe with the CAS itself instead of a read followed by a CAS
     double debug_force_lsd = 0.0;     // sort path: 0 = auto (MSD + shared-memory chunk sort for 64-bit keys, LSD passes for 128-bit), 1 = LSD, 2 = MSD
@@ -177,6 +178,7 @@ extern "C" int fkm_ctx_set(fkm_ctx* c, const char* name, double v) {
     else if (!strcmp(name, "debug_rho_scale")) c->debug_rho_scale = v;
     else if (!strcmp(name, "fold_records")) c->fold_records = v;
     else if (!strcmp(name, "fold_max_ratio")) c->fold_max_ratio = v;
+    else if (!strcmp(name, "fold_pool")) c->fold_pool = v;
     else if (!strcmp(name, "fold_table_bytes")) c->fold_table_bytes = v;
     else if (!strcmp(name, "cas_first")) c->cas_first = v;
     else if (!strcmp(name, "debug_force_lsd")) c->debug_force_lsd = v;
@@ -527,7 +529,14 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
                     F.bin_base = d_bin_base; F.bin_lo = fb.lo; F.bin_hi = fb.hi; F.table = d_ftab; F.tbl_base = d_ftb + fb.tb_idx;
                     F.bin_distinct = d_fdistinct; F.overflow = d_ovf; F.max_probe = 512;
                     const uint64_t nr = F.rec_hi - F.rec_lo;
-                    if (nr) { k_fold_insert<<<(unsigned)((nr + 8 * kFoldPerWarp - 1) / (8 * kFoldPerWarp)), 256, 0, s>>>(F); CKLC(); }
+                    if (nr) {
+                        const int pool = ctx->fold_pool >= 256.0 ? 256 : ctx->fold_pool >= 128.0 ? 128 : 64;   // records per warp
+                        const unsigned grid = (unsigned)((nr + 8 * (uint64_t)pool - 1) / (8 * (uint64_t)pool));
+                        if (pool == 256) k_fold_insert<256><<<grid, 256, 0, s>>>(F);
+                        else if (pool == 128) k_fold_insert<128><<<grid, 256, 0, s>>>(F);
+                        else k_fold_insert<64><<<grid, 256, 0, s>>>(F);
+                        CKLC();
+                    }
                     k_bin_offsets<<<1, 256, 0, s>>>(d_fdistinct, d_fbase, fb.lo, fb.hi, d_small); CKLC();
                     if (fb.slots) {
                         CompactParams Q;
