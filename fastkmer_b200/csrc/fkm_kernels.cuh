@@ -144,16 +144,14 @@ __device__ __forceinline__ void canon_record_narrow(uint64_t& w0, uint64_t& w1, 
 // bases [a, a+n+k-1) -> one super-k-mer record at `slot`
 template <bool WIDE>
 __device__ __forceinline__ void write_record(void* records, unsigned long long slot, const uint64_t* bases, uint64_t n_words,
-                                             unsigned long long a, uint32_t nn, int canon_len = 0) {
+                                             unsigned long long a, uint32_t nn) {
     auto ld = [&](unsigned long long gw) -> uint64_t { return gw < n_words ? bases[gw] : 0ull; };
     const unsigned long long j = a >> 5; const uint32_t sh = 2u * (uint32_t)(a & 31ull);
     if constexpr (!WIDE) {
         uint64_t w0 = ld(j), w1 = ld(j + 1), w2 = ld(j + 2);
         uint64_t r0 = sh ? ((w0 << sh) | (w1 >> (64 - sh))) : w0;
         uint64_t r1 = sh ? ((w1 << sh) | (w2 >> (64 - sh))) : w1;
-        r1 &= ~0xFFull;
-        if (canon_len) canon_record_narrow(r0, r1, canon_len);
-        r1 |= (uint64_t)nn;
+        r1 = (r1 & ~0xFFull) | (uint64_t)nn;
         reinterpret_cast<ulonglong2*>(records)[slot] = make_ulonglong2(r0, r1);
     } else {
         uint64_t x0 = ld(j), x1 = ld(j + 1), x2 = ld(j + 2), x3 = ld(j + 3), x4 = ld(j + 4);
@@ -373,7 +371,6 @@ struct ScatterParams {
     const uint64_t* bases; uint64_t n_words;
     uint32_t B; int cap; int k;
     const unsigned long long* bin_base; unsigned long long* cursor; void* records;
-    int canon;                                  // NARROW only: write canonical, tail-zeroed records (they are going to be folded)
 };
 template <bool WIDE>
 __global__ void __launch_bounds__(256) k_scatter_events(const ScatterParams P) {
@@ -397,17 +394,14 @@ __global__ void __launch_bounds__(256) k_scatter_events(const ScatterParams P) {
         uint64_t r[NW - 1];
 #pragma unroll
         for (int q = 0; q < NW - 1; q++) r[q] = sh ? ((w[q] << sh) | (w[q + 1] >> (64 - sh))) : w[q];
-        r[NW - 2] &= ~0xFFull;
-        if constexpr (!WIDE) { if (P.canon) canon_record_narrow(r[0], r[1], (int)nn + P.k - 1); }
-        r[NW - 2] |= (uint64_t)nn;
+        r[NW - 2] = (r[NW - 2] & ~0xFFull) | (uint64_t)nn;
         ulonglong2* dst = reinterpret_cast<ulonglong2*>(P.records) + (WIDE ? 2 : 1) * slot0;
         dst[0] = make_ulonglong2(r[0], r[1]);
         if constexpr (WIDE) dst[1] = make_ulonglong2(r[2], r[3]);
     }
     for (uint32_t pc = 1, off = (uint32_t)P.cap; off < n; off += (uint32_t)P.cap, pc++) {
         const uint32_t nn = min((uint32_t)P.cap, n - off);
-        write_record<WIDE>(P.records, slot0 + pc, P.bases, P.n_words, rs + off - (unsigned long long)(P.k - 1), nn,
-                           (!WIDE && P.canon) ? (int)nn + P.k - 1 : 0);
+        write_record<WIDE>(P.records, slot0 + pc, P.bases, P.n_words, rs + off - (unsigned long long)(P.k - 1), nn);
     }
 }
 
@@ -694,7 +688,7 @@ __global__ void __launch_bounds__(256) k_count_ht(const CountParams P) {
     if (ovf) *P.overflow = 1;
 }
 
-// Record folding: every NARROW record (16 bytes, canonical orientation, see canon_record_narrow) is inserted
+// Record folding: every NARROW record (16 bytes, brought into canonical form first, see canon_record_narrow) is inserted
 // as a 128-bit key into its bin's table of SlotW; the slot count becomes its multiplicity - 1.  The tables are
 // then compacted by k_compact_ht<true> into dense (record, multiplicity) arrays, bin-major like the input.  A
 // record is never all ones (its low byte is n <= 60), so the table's EMPTY key cannot collide.
@@ -703,9 +697,9 @@ struct FoldParams {
     const unsigned long long* bin_base; int bin_lo, bin_hi;
     void* table; const unsigned long long* tbl_base;
     unsigned long long* bin_distinct;           // [B] distinct records per bin
-    int* overflow; int max_probe;
+    int* overflow; int max_probe; int k;
 };
-// One warp per 256 consecutive records, staged in shared memory; the lanes then run k_count_ht's refill state
+// One warp per kFoldPerWarp consecutive records, staged in shared memory; the lanes then run k_count_ht's refill state
 // machine over that pool (0 = read the slot, 1 = CAS the empty slot, 2 = done, take the next record, 3 = pool
 // exhausted), so every round trip carries one probe per lane whatever the lengths of the probe chains.
 template <int kFoldPerWarp>
@@ -717,7 +711,12 @@ __global__ void __launch_bounds__(256) k_fold_insert(const FoldParams P) {
     if (r0 >= P.rec_hi) return;                              // warp-uniform
     const uint32_t T = (uint32_t)min((unsigned long long)kFoldPerWarp, P.rec_hi - r0);
     const ulonglong2* src = reinterpret_cast<const ulonglong2*>(P.records) + r0;
-    for (uint32_t i = lane; i < T; i += 32) s_rec[warp][i] = __ldcs(src + i);
+    for (uint32_t i = lane; i < T; i += 32) {                // stage the records in canonical form (see canon_record_narrow)
+        const ulonglong2 v = __ldcs(src + i);
+        uint64_t w0 = v.x, w1 = v.y & ~0xFFull; const int n = (int)(v.y & 0xFFull);
+        canon_record_narrow(w0, w1, n + P.k - 1);
+        s_rec[warp][i] = make_ulonglong2(w0, w1 | (uint64_t)n);
+    }
     __syncwarp();
     const int bin_first = find_bin(P.bin_base, P.bin_lo, P.bin_hi, r0);
     const int bin_last = find_bin(P.bin_base, P.bin_lo, P.bin_hi, r0 + T - 1);

@@ -93,7 +93,7 @@ struct fkm_ctx {
     double debug_event_scale = 1.0;   // test hook: scales the run-event list capacity (forces the second-scan fallback)
     double fold_records = 1.0;        // hash path, k <= 32: 1 = fold identical super-k-mer records into one weighted record before counting
     double fold_table_bytes = 1024.0 * 1048576.0;   // ... in batches of bins whose record tables (32-byte slots) fit this
-    double fold_pool = 256.0;         // ... records per warp in k_fold_insert (64, 128 or 256)
+    double fold_pool = 128.0;         // ... records per warp in k_fold_insert (64, 128 or 256)
     double fold_max_ratio = 0.6;      // ... unless the first batch shows that more than this share of the records is distinct
     double cas_first = 0.0;           // hash path: 1 = probe with the CAS itself instead of a read followed by a CAS
     double debug_force_lsd = 0.0;     // sort path: 0 = auto (MSD + shared-memory chunk sort for 64-bit keys, LSD passes for 128-bit), 1 = LSD, 2 = MSD
@@ -384,7 +384,7 @@ static int stage_scan(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const void
 // stage 2: run events -> super-k-mer records at d_records[bin_base[bin] + ...] (the "shuffle").  bin_base is any
 // per-bin record offset table: bin-major on one GPU, owner-major for the multi-GPU send buffer.
 static int stage_scatter(fkm_ctx* ctx, ScanState* S, const unsigned long long* d_bin_base, unsigned long long* d_cursor,
-                         void* d_records, uint64_t n_rec, fkm_stats* st, bool canon = false) {
+                         void* d_records, uint64_t n_rec, fkm_stats* st) {
     cudaStream_t s = ctx->stream;
     const fkm_config* cfg = &S->cfg;
     const bool wide = cfg->k > 32;
@@ -394,7 +394,7 @@ static int stage_scatter(fkm_ctx* ctx, ScanState* S, const unsigned long long* d
             ScatterParams Q;
             Q.events = C.d_events; Q.n_events = C.n_events; Q.bases = (const uint64_t*)C.d_bases; Q.n_words = (C.n_pos + 31) / 32;
             Q.B = (uint32_t)S->B; Q.cap = wide ? (125 - cfg->k) : (61 - cfg->k); Q.k = cfg->k;
-            Q.bin_base = d_bin_base; Q.cursor = d_cursor; Q.records = d_records; Q.canon = (canon && !wide) ? 1 : 0;
+            Q.bin_base = d_bin_base; Q.cursor = d_cursor; Q.records = d_records;
             if (C.n_events) {
                 const unsigned grid = (unsigned)((C.n_events + 255) / 256);
                 if (wide) k_scatter_events<true><<<grid, 256, 0, s>>>(Q); else k_scatter_events<false><<<grid, 256, 0, s>>>(Q);
@@ -474,7 +474,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
     if (!pre) {
         CKC(dmalloc(ctx, &d_records, std::max<size_t>(16, (size_t)n_rec * rec_bytes)));
         tr.mark("records allocated", (long long)n_rec);
-        rc = stage_scatter(ctx, &scan, d_bin_base, d_cursor, d_records, n_rec, st, want_fold); if (rc) return rc;
+        rc = stage_scatter(ctx, &scan, d_bin_base, d_cursor, d_records, n_rec, st); if (rc) return rc;
     } else {
         d_records = const_cast<void*>(pre->d_records);
         CKC(cudaEventRecord(ctx->ev[2], s));
@@ -527,7 +527,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
                     FoldParams F;
                     F.records = d_records; F.rec_lo = h_base[(size_t)fb.lo]; F.rec_hi = h_base[(size_t)fb.hi];
                     F.bin_base = d_bin_base; F.bin_lo = fb.lo; F.bin_hi = fb.hi; F.table = d_ftab; F.tbl_base = d_ftb + fb.tb_idx;
-                    F.bin_distinct = d_fdistinct; F.overflow = d_ovf; F.max_probe = 512;
+                    F.bin_distinct = d_fdistinct; F.overflow = d_ovf; F.max_probe = 512; F.k = cfg->k;
                     const uint64_t nr = F.rec_hi - F.rec_lo;
                     if (nr) {
                         const int pool = ctx->fold_pool >= 256.0 ? 256 : ctx->fold_pool >= 128.0 ? 128 : 64;   // records per warp
@@ -1244,9 +1244,7 @@ extern "C" int fkm_mg_scatter(fkm_ctx* ctx, const uint64_t* bin_base, void* d_se
     CK(cudaMemsetAsync(d_cursor, 0, bB, ctx->stream));
     uint64_t n_rec = 0; for (int b = 0; b < S->B; b++) n_rec += S->h_rec[(size_t)b];
     fkm_stats st; memset(&st, 0, sizeof st);
-    // canonical, tail-zeroed records when the receiving side is going to fold them (hash path, 16-byte records)
-    const bool canon = S->cfg.use_ht && S->cfg.k <= 32 && ctx->fold_records >= 1.0;
-    int rc = stage_scatter(ctx, S, d_bin_base, d_cursor, d_send, n_rec, &st, canon); if (rc) return rc;
+    int rc = stage_scatter(ctx, S, d_bin_base, d_cursor, d_send, n_rec, &st); if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     return FKM_OK;
 }
