@@ -90,7 +90,7 @@ void fkm_ctx_destroy(fkm_ctx* ctx);
 int  fkm_ctx_sync(fkm_ctx* ctx);
 /* tuning knobs (optional): name in {"table_budget_bytes","async_table_bytes","sort_budget_keys","load_factor","ingest_chunk_bytes",
  * "fold_records" (default 1: hash path with k <= 32 folds identical super-k-mer records into one weighted record before
- * counting, unless the sampled first bins show more than "fold_max_ratio" (0.6) distinct records; 0 = never), "fold_table_bytes",
+ * counting, unless the sampled first bins show more than "fold_max_ratio" (0.6) distinct records; 0 = never), "fold_table_bytes", "fold_pool" (records per warp in k_fold_insert: 64, 128, 256),
  * "cas_first" (experiment: probe with the CAS itself; slower, see profiles/README.md)} */
 int  fkm_ctx_set(fkm_ctx* ctx, const char* name, double value);
 
