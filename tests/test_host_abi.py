@@ -138,3 +138,27 @@ def test_rejected_configurations(bad):
     with pytest.raises(fk.FkmError) as e:
         api.derive(tc)
     assert e.value.code == api.FKM_EINVAL
+
+
+def test_header_is_plain_c_and_ctypes_mirrors_match(tmp_path):
+    """include/fastkmer_b200.h compiles as C (what cgo / JNI would include) and the ctypes mirrors in api.py have the
+    same size and field offsets as the C structs."""
+    import ctypes
+    import subprocess
+    from fastkmer_b200 import api
+    mirrors = {"fkm_config": api.fkm_config, "fkm_stats": api.fkm_stats, "fkm_synth": api.fkm_synth, "fkm_synth_long": api.fkm_synth_long}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "fastkmer_b200.h"', 'int main(void) {']
+    for name, cls in mirrors.items():
+        lines.append('  printf("%s.sizeof %%zu\\n", sizeof(%s));' % (name, name))
+        for field, _ in cls._fields_:
+            lines.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (name, field, name, field))
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    for name, cls in mirrors.items():
+        assert int(got[name + ".sizeof"]) == ctypes.sizeof(cls), name
+        for field, _ in cls._fields_:
+            assert int(got["%s.%s" % (name, field)]) == getattr(cls, field).offset, "%s.%s" % (name, field)
