@@ -205,7 +205,7 @@ def test_small_table_budget_batches_and_retry(ctx, oracle):
 
 
 def test_async_phase_overflow_falls_back(oracle):
-    """A wrong distinct/k-mer estimate overflows the L2-resident tables: the job must notice and redo the
+    """A wrong distinct/k-mer estimate overflows the pre-planned tables of the asynchronous batches: the job must notice and redo the
     bins synchronously with the same result."""
     spec = dict(seeds=(17, 18, 19), genome_len=400000, n_reads=40000, read_len=100)
     fasta = fk.synth_fasta(spec).tobytes()
