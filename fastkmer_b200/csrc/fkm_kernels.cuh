@@ -113,7 +113,8 @@ struct ScanParams {
     ulonglong2* events;             // run events {first window end, n | value<<32}   (MODE 0)
     unsigned long long ev_cap; unsigned long long* ev_count; int* ev_overflow;
     const unsigned long long* bin_base;   // [B+1] record offsets     (MODE 1)
-    unsigned long long* cursor;     // [B]                            (MODE 1)
+    unsigned long long* cursor;     // [B << cursor_shift], one per bin at stride 1 << cursor_shift   (MODE 1)
+    int cursor_shift;
     void* records;                  //                                (MODE 1)
     int32_t* dbg_bins;              // [n_pos]                        (MODE 2)
 };
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams P) {
             } else if (MODE == 1) {
                 for (uint32_t off = 0; off < n; off += (uint32_t)P.cap) {
                     const uint32_t nn = min((uint32_t)P.cap, n - off);
-                    const unsigned long long slot = P.bin_base[bin] + atomicAdd(&P.cursor[bin], 1ull);
+                    const unsigned long long slot = P.bin_base[bin] + atomicAdd(&P.cursor[(size_t)bin << P.cursor_shift], 1ull);
                     const unsigned long long a = rs + off - (unsigned long long)(k - 1);
                     if (P.wide) write_record<true>(P.records, slot, P.bases, P.n_words, a, nn);
                     else write_record<false>(P.records, slot, P.bases, P.n_words, a, nn);
@@ -370,7 +371,8 @@ struct ScatterParams {
     const ulonglong2* events; unsigned long long n_events;
     const uint64_t* bases; uint64_t n_words;
     uint32_t B; int cap; int k;
-    const unsigned long long* bin_base; unsigned long long* cursor; void* records;
+    const unsigned long long* bin_base; void* records;
+    unsigned long long* cursor; int cursor_shift;   // write cursor of bin b at cursor[b << cursor_shift]
 };
 template <bool WIDE>
 __global__ void __launch_bounds__(256) k_scatter_events(const ScatterParams P) {
@@ -388,7 +390,7 @@ __global__ void __launch_bounds__(256) k_scatter_events(const ScatterParams P) {
     for (int q = 0; q < NW; q++) w[q] = (j0 + q < P.n_words) ? P.bases[j0 + q] : 0ull;
     const uint32_t bin = hash_to_bucket(v, P.B);
     const uint32_t pieces = (n + (uint32_t)P.cap - 1) / (uint32_t)P.cap;
-    const unsigned long long slot0 = P.bin_base[bin] + atomicAdd(&P.cursor[bin], (unsigned long long)pieces);
+    const unsigned long long slot0 = P.bin_base[bin] + atomicAdd(&P.cursor[(size_t)bin << P.cursor_shift], (unsigned long long)pieces);
     {
         const uint32_t nn = min((uint32_t)P.cap, n);
         uint64_t r[NW - 1];
