@@ -26,6 +26,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "fkm_common.h"
+#include "fkm_math.h"
 
 namespace fkm {
 
@@ -33,7 +34,6 @@ static constexpr uint32_t kInvalidMin = 0xFFFFFFFFu;
 static constexpr int kScanThreads = 256;
 static constexpr int kSmemHistMaxB = 4096;
 
-struct __align__(16) key128 { uint64_t lo, hi; };
 struct __align__(16) SlotN { uint64_t key; uint32_t cnt; uint32_t pad; };
 struct __align__(32) SlotW { key128 key; uint32_t cnt; uint32_t pad[3]; };
 
@@ -47,40 +47,7 @@ template <> struct Traits<true> {
     static constexpr int kRecWords = 4, kRecBases = 124;
 };
 
-// ------------------------------------------------------------------ small helpers
-__device__ __forceinline__ uint64_t swap_pairs(uint64_t x) {
-    return ((x & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((x & 0x5555555555555555ull) << 1);
-}
-// reverse complement of a right-aligned len-mer (len <= 32)
-__device__ __forceinline__ uint64_t revcomp64(uint64_t x, int len) {
-    return swap_pairs(__brevll(~x)) >> (64 - 2 * len);
-}
-__device__ __forceinline__ key128 revcomp128(key128 x, int len) {          // 32 < len <= 64
-    uint64_t rh = swap_pairs(__brevll(~x.lo)), rl = swap_pairs(__brevll(~x.hi));
-    int s = 128 - 2 * len;                                                  // 0..62
-    key128 r;
-    r.lo = s ? ((rl >> s) | (rh << (64 - s))) : rl;
-    r.hi = rh >> s;
-    return r;
-}
-__device__ __forceinline__ bool key_less(key128 a, key128 b) { return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo); }
-__device__ __forceinline__ bool key_eq(key128 a, key128 b) { return a.hi == b.hi && a.lo == b.lo; }
-__device__ __forceinline__ bool key_eq(uint64_t a, uint64_t b) { return a == b; }
-
-// norm of an m-mer given the value v and its reverse complement r (UTIL:46-100,
-// closed form of SURVEY App. A.5: allowed <=> no "AA" inside and prefix != "ACA").
-__device__ __forceinline__ bool mmer_allowed(uint32_t v, int m, uint32_t mmask) {
-    uint32_t nz = (v | (v >> 1)) & 0x55555555u;
-    uint32_t a = ~nz & 0x55555555u & mmask;
-    return ((a & (a >> 2)) == 0u) && ((v >> (2 * m - 6)) != 4u);
-}
-__device__ __forceinline__ uint32_t mmer_norm(uint32_t v, uint32_t r, int m, uint32_t mmask) {
-    uint32_t dflt = mmask + 1u;
-    uint32_t a = mmer_allowed(v, m, mmask) ? v : dflt;
-    uint32_t b = mmer_allowed(r, m, mmask) ? r : dflt;
-    return min(a, b);
-}
-
+// ------------------------------------------------------------------ small helpers (the pure arithmetic ones live in fkm_math.h)
 // 64 bits starting at bit position `pos` of an MSB-first u32 bit array
 __device__ __forceinline__ uint64_t bits64_at(const uint32_t* a, uint32_t pos) {
     uint32_t wi = pos >> 5, sh = pos & 31;
@@ -118,29 +85,6 @@ struct ScanParams {
     void* records;                  //                                (MODE 1)
     int32_t* dbg_bins;              // [n_pos]                        (MODE 2)
 };
-
-__device__ __forceinline__ uint32_t revcomp32(uint32_t v, int len) {       // len <= 15
-    uint32_t x = __brev(~v);
-    x = ((x & 0xAAAAAAAAu) >> 1) | ((x & 0x55555555u) << 1);
-    return x >> (32 - 2 * len);
-}
-
-// Record folding (hash path, NARROW records): a record and its reverse complement hold the same canonical
-// k-mers, and so do two records that differ only behind their n+k-1 bases.  Zero the unused tail and keep the
-// smaller of the string and its reverse complement (left-aligned, so the order is lexicographic): identical
-// super-k-mers of different reads, either strand, become bit-identical records.  w1's n byte must be clear.
-__device__ __forceinline__ void canon_record_narrow(uint64_t& w0, uint64_t& w1, int len) {
-    const int bits = 2 * len;                                               // 2..120
-    w0 &= bits >= 64 ? ~0ull : ~0ull << (64 - bits);
-    w1 &= bits <= 64 ? 0ull : ~0ull << (128 - bits);
-    // complement, reverse all 64 base positions: the string's reverse complement lands in the low `bits` bits
-    const uint64_t c_hi = swap_pairs(__brevll(~w1)), c_lo = swap_pairs(__brevll(~w0));
-    const int sft = 128 - bits;                                             // 8..126: shift it back to the top
-    uint64_t r0, r1;
-    if (sft >= 64) { r0 = c_lo << (sft - 64); r1 = 0ull; }
-    else { r0 = (c_hi << sft) | (c_lo >> (64 - sft)); r1 = c_lo << sft; }
-    if (r0 < w0 || (r0 == w0 && r1 < w1)) { w0 = r0; w1 = r1; }
-}
 
 // bases [a, a+n+k-1) -> one super-k-mer record at `slot`
 template <bool WIDE>
@@ -496,23 +440,6 @@ struct CountParams {
     int first_state;                            // 0: read the slot, CAS only when it looks empty; 1: CAS straight away (every probe is ONE atomic at the slot's home L2 slice)
 };
 
-// 32-bit table hash (murmur3 finaliser over the folded key); the slot is mulhi(hash, size)
-__device__ __forceinline__ uint32_t fmix32(uint32_t x) {
-    x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
-    return x;
-}
-__device__ __forceinline__ uint32_t key_hash(uint64_t key) {
-    return fmix32((uint32_t)key * 0x9E3779B1u ^ (uint32_t)(key >> 32) * 0x85EBCA77u);
-}
-__device__ __forceinline__ uint32_t key_hash(key128 key) {
-    return fmix32(((uint32_t)key.lo * 0x9E3779B1u ^ (uint32_t)(key.lo >> 32) * 0x85EBCA77u) +
-                  ((uint32_t)key.hi * 0xC2B2AE3Du ^ (uint32_t)(key.hi >> 32) * 0x27D4EB2Fu));
-}
-__device__ __forceinline__ unsigned long long slot_of(uint32_t h, unsigned long long size) {
-    return (size <= 0xFFFFFFFFull) ? (unsigned long long)__umulhi(h, (uint32_t)size)
-                                   : __umul64hi(((unsigned long long)h << 32) | fmix32(h), size);
-}
-
 // returns 1 if this call claimed a new slot, 0 if the key was present, -1 on overflow
 __device__ __forceinline__ int ht_insert(SlotN* tbl, unsigned long long size, uint64_t key, int max_probe, uint32_t weight = 1u) {
     unsigned long long slot = slot_of(key_hash(key), size);
@@ -546,27 +473,6 @@ __device__ __forceinline__ int ht_insert(SlotW* tbl, unsigned long long size, ke
         if (++slot == size) slot = 0;
     }
     return -1;
-}
-
-// canonical k-mer number j of a record whose words sit in shared memory (n byte already cleared)
-__device__ __forceinline__ uint64_t kmer_at_narrow(const uint64_t* rec, int j, int k) {
-    const int q = j >> 5, sh = 2 * (j & 31);
-    const uint64_t a0 = rec[q], a1 = q ? 0ull : rec[1];
-    const uint64_t hi = sh ? ((a0 << sh) | (a1 >> (64 - sh))) : a0;
-    const uint64_t fwd = hi >> (64 - 2 * k);
-    const uint64_t rc = revcomp64(fwd, k);
-    return min(fwd, rc);
-}
-__device__ __forceinline__ key128 kmer_at_wide(const uint64_t* rec, int j, int k) {
-    const int q = j >> 5, sh = 2 * (j & 31);
-    const uint64_t a0 = rec[q], a1 = (q + 1 < 4) ? rec[q + 1] : 0ull, a2 = (q + 2 < 4) ? rec[q + 2] : 0ull;
-    const uint64_t h0 = sh ? ((a0 << sh) | (a1 >> (64 - sh))) : a0;
-    const uint64_t h1 = sh ? ((a1 << sh) | (a2 >> (64 - sh))) : a1;
-    const int s = 128 - 2 * k;
-    key128 fwd;
-    fwd.hi = h0 >> s; fwd.lo = s ? ((h0 << (64 - s)) | (h1 >> s)) : h1;
-    const key128 rc = revcomp128(fwd, k);
-    return key_less(rc, fwd) ? rc : fwd;
 }
 
 // One warp per 32 super-k-mer records.  The records go to shared memory, an exclusive
