@@ -162,3 +162,18 @@ def test_header_is_plain_c_and_ctypes_mirrors_match(tmp_path):
         assert int(got[name + ".sizeof"]) == ctypes.sizeof(cls), name
         for field, _ in cls._fields_:
             assert int(got["%s.%s" % (name, field)]) == getattr(cls, field).offset, "%s.%s" % (name, field)
+
+
+def test_jni_shim_builds_and_reports_errors(tmp_path):
+    """integration/fkm_jni.c (the reference-side binding of INTEGRATION.md) compiles against a minimal stand-in for
+    <jni.h>, links the C-ABI library and, driven through a fake JNIEnv, returns the library's error code and message
+    (no CUDA device here; on a GPU box the missing dataset is the error) and releases every string it took."""
+    import subprocess
+    exe = tmp_path / "jni_harness"
+    libdir = os.path.join(ROOT, "fastkmer_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "stubs"), "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "integration", "fkm_jni.c"), os.path.join(ROOT, "tests", "jni_harness.c"),
+                           "-L", libdir, "-lfastkmer_b200", "-Wl,-rpath," + libdir, "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120).stdout.strip()
+    rc = int(out.split()[0].split("=")[1])
+    assert rc != 0 and "live=0" in out and len(out.split("err=", 1)[1]) > 0, out
