@@ -26,7 +26,8 @@ class fkm_stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("n_positions", "n_bases", "n_kmers", "n_superkmers", "superkmer_bytes",
                                           "n_distinct", "total_count", "digest_sum", "digest_xor", "n_nonempty_bins",
                                           "h2d_bytes", "d2h_bytes", "gpu_launches", "n_batches", "n_fallbacks")] + \
-               [("ms_total", C.c_double), ("ms_stage", C.c_double * 8), ("n_folded_records", C.c_uint64), ("ms_fold", C.c_double)]
+               [("ms_total", C.c_double), ("ms_stage", C.c_double * 8), ("n_folded_records", C.c_uint64), ("ms_fold", C.c_double),
+                ("n_mid_bins", C.c_uint64), ("n_slow_bins", C.c_uint64)]
 
 
 class fkm_synth(C.Structure):

@@ -70,20 +70,30 @@ struct ScanParams {
     uint64_t e_total;               // window-end positions to visit
     uint64_t n_seg; uint32_t seg_len;   // segments of seg_len window ends (multiple of 32), one warp each
     int k, m, w;                    // w = k-m+1 m-mers per window
-    int L, d;                       // w = 2^L + d, 0 <= d < 2^L
+    int sh1[6];                     // shifts of the doubling levels of the signature window: w = 1 + sum(sh1), 0 = unused level
     uint32_t B;
     int cap;                        // max k-mers per record
     int wide;                       // record format (MODE 1 only)
     int smem_hist;                  // 1: per-CTA histogram in shared memory (B <= 4096)
     unsigned long long* hist_rec;   // [B] records per bin            (MODE 0)
     unsigned long long* hist_kmer;  // [B] k-mers per bin             (MODE 0)
-    ulonglong2* events;             // run events {first window end, n | value<<32}   (MODE 0)
+    ulonglong2* events;             // run events {first window end, n | value<<32}   (MODE 0, !DUAL)
     unsigned long long ev_cap; unsigned long long* ev_count; int* ev_overflow;
     const unsigned long long* bin_base;   // [B+1] record offsets     (MODE 1)
     unsigned long long* cursor;     // [B << cursor_shift], one per bin at stride 1 << cursor_shift   (MODE 1)
     int cursor_shift;
     void* records;                  //                                (MODE 1)
     int32_t* dbg_bins;              // [n_pos]                        (MODE 2)
+    // ---- DUAL (shared-memory count path): a second, hash-ordered minimizer of length m2 cuts the runs further and
+    // spreads every bin over (1 << cell_bits) cells
+    int m2; uint32_t mask2;
+    int sh2[6];                     // doubling shifts of the second window: k-m2+1 = 1 + sum(sh2)
+    int cell_bits;                  // cells per bin = 1 << cell_bits (<= 12)
+    uint32_t sample_hi;             // list 1 holds every event, list 0 (also) those of the bins < sample_hi
+    ulonglong2* events2[2];         // {first window end, n | h16 << 16 | bin << 32}
+    unsigned long long ev_cap2[2];  // ev_count[0..1] are the two list lengths
+    unsigned long long* cell_rec;   // [B << cell_bits] records per cell
+    unsigned long long* cell_kmer;  // [B << cell_bits] k-mers per cell
 };
 
 // bases [a, a+n+k-1) -> one super-k-mer record at `slot`
@@ -111,18 +121,29 @@ __device__ __forceinline__ void write_record(void* records, unsigned long long s
     }
 }
 
+// hash order of the second minimizer (any fixed bijection-like mix: only the PARTITION depends on it, never a count)
+__device__ __forceinline__ uint32_t mmer2_hash(uint32_t v2, int m2) {
+    const uint32_t r2 = revcomp32(v2, m2);
+    return fmix32((v2 < r2 ? v2 : r2) + 0x9E3779B9u);
+}
+// 16 partition bits of a run from the minimum hash of its windows (the minimum itself is biased towards small values)
+__device__ __forceinline__ uint32_t cell_hash16(uint32_t sig2) { return fmix32(sig2 ^ 0x5bd1e995u) >> 16; }
+
 // MODE 0: bin histogram (records and k-mers per bin) + the list of run events.
 // MODE 1: scatter records directly (recomputes the scan; fallback when the event list overflowed).
 // MODE 2: per-window bin ids (test hook).
+// DUAL (MODE 0 only): runs are cut where the signature OR the second minimizer changes; events carry the bin and 16 hash
+// bits of the second minimizer, and the histogram is kept per (bin, cell) in global memory as well.
 //
 // Warp-striped sliding window.  A warp owns a segment of consecutive window-END
 // positions and walks it 32 at a time, lane l <-> position e = 32 g + l:
 //   * the m-mer ending at e is cut out of two broadcast 64-bit words (funnel shift),
 //     its reverse complement comes from brev, norm() is the closed form of UTIL:46-100;
-//   * the minimum over the window's w = 2^L + d m-mers is built by doubling with warp
-//     shuffles: x_{j+1}[e] = min(x_j[e], x_j[e - 2^j]), one shuffle per level (the source
-//     lane sends its value of the previous group when its reader wrapped below lane 0);
-//     L is a template parameter so the level loop is straight-line code;
+//   * the minimum over the window's w m-mers is built by doubling with warp shuffles:
+//     x_{j+1}[e] = min(x_j[e], x_j[e - s_j]), one shuffle per level (the source lane sends its value
+//     of the previous group when its reader wrapped below lane 0); shifts 1, 2, 4, ..., then the
+//     remainder, w = 1 + sum of the shifts; NL (levels) is a template parameter, the shifts are
+//     kernel parameters (a level with shift 0 is a no-op);
 //   * a window is valid iff the last invalid position at or before e is >= k behind;
 //   * run boundaries (signature value changes / validity changes) are found with one
 //     shuffle and two ballots; every lane that sees a run END pushes (start, length,
@@ -132,23 +153,24 @@ __device__ __forceinline__ void write_record(void* records, unsigned long long s
 // groups before each segment rebuild the register state, so segments are independent;
 // runs are cut at segment boundaries (the reference's own cutting rule, SBKC:102-136,
 // is not observable: SURVEY §7).
-template <int MODE, int L>
+template <int MODE, int NL, bool DUAL>
 __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long q_rs[kScanThreads / 32][64];
     __shared__ uint32_t q_n[kScanThreads / 32][64];
     __shared__ uint32_t q_v[kScanThreads / 32][64];
+    __shared__ uint32_t q_v2[DUAL ? kScanThreads / 32 : 1][64];
     uint32_t* s_hist_rec = reinterpret_cast<uint32_t*>(smem_raw);
     uint32_t* s_hist_kmer = s_hist_rec + P.B;
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const int k = P.k, m = P.m, d = P.d;
+    const int k = P.k, m = P.m;
     const uint32_t mmask = (1u << (2 * m)) - 1u;
     const bool upper = lane >= 16;                          // m-mer lies inside W (else it reaches into Wprev)
     const uint32_t fsh = (2u * (31u - (uint32_t)lane)) & 31u;
 
-    if (MODE == 0 && P.smem_hist) {
+    if (MODE == 0 && !DUAL && P.smem_hist) {
         for (uint32_t b = threadIdx.x; b < P.B; b += kScanThreads) { s_hist_rec[b] = 0; s_hist_kmer[b] = 0; }
         __syncthreads();
     }
@@ -164,9 +186,9 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams P) {
     // drain `cnt` (<= 32) queued events: lane i takes event i
     auto drain = [&](int cnt) {
         const bool have = lane < cnt;
-        unsigned long long rs = 0; uint32_t n = 0, v = 0;
-        if (have) { rs = q_rs[warp][lane]; n = q_n[warp][lane]; v = q_v[warp][lane]; }
-        if (MODE == 0) {
+        unsigned long long rs = 0; uint32_t n = 0, v = 0, v2 = 0;
+        if (have) { rs = q_rs[warp][lane]; n = q_n[warp][lane]; v = q_v[warp][lane]; if (DUAL) v2 = q_v2[warp][lane]; }
+        if (MODE == 0 && !DUAL) {
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(P.ev_count, (unsigned long long)cnt);
             base = __shfl_sync(FULL, base, 0);
@@ -174,8 +196,35 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams P) {
                 if (have) P.events[base + lane] = make_ulonglong2(rs, (unsigned long long)n | ((unsigned long long)v << 32));
             } else if (lane == 0) *P.ev_overflow = 1;
         }
-        if (have) {
-            const uint32_t bin = hash_to_bucket(v, P.B);
+        const uint32_t bin = have ? hash_to_bucket(v, P.B) : 0u;
+        if (MODE == 0 && DUAL) {
+            // every event goes to list 1 in lane order; the events of the sample bins (few) are appended to list 0 as well
+            const uint32_t h16 = cell_hash16(v2);
+            const ulonglong2 ev = make_ulonglong2(rs, (unsigned long long)n | ((unsigned long long)h16 << 16) | ((unsigned long long)bin << 32));
+            unsigned long long b1 = 0;
+            if (lane == 0) b1 = atomicAdd(&P.ev_count[1], (unsigned long long)cnt);
+            b1 = __shfl_sync(FULL, b1, 0);
+            if (b1 + (unsigned long long)cnt <= P.ev_cap2[1]) { if (have) P.events2[1][b1 + lane] = ev; }
+            else if (lane == 0) *P.ev_overflow = 1;
+            const bool to0 = have && bin < P.sample_hi;
+            const uint32_t m0 = __ballot_sync(FULL, to0);
+            if (m0) {
+                unsigned long long b0 = 0;
+                if (lane == 0) b0 = atomicAdd(&P.ev_count[0], (unsigned long long)__popc(m0));
+                b0 = __shfl_sync(FULL, b0, 0);
+                if (to0) {
+                    const unsigned long long idx = b0 + __popc(m0 & lt_mask);
+                    if (idx < P.ev_cap2[0]) P.events2[0][idx] = ev; else *P.ev_overflow = 1;
+                }
+            }
+            if (have) {
+                const uint32_t pieces = n <= (uint32_t)P.cap ? 1u : (n + (uint32_t)P.cap - 1) / (uint32_t)P.cap;
+                const size_t cell = ((size_t)bin << P.cell_bits) | (size_t)(h16 >> (16 - P.cell_bits));
+                atomicAdd(&P.cell_rec[cell], (unsigned long long)pieces);
+                atomicAdd(&P.cell_kmer[cell], (unsigned long long)n);
+            }
+        }
+        if (have && !(MODE == 0 && DUAL)) {
             if (MODE == 0) {
                 const uint32_t pieces = (n + (uint32_t)P.cap - 1) / (uint32_t)P.cap;
                 if (P.smem_hist) { atomicAdd(&s_hist_rec[bin], pieces); atomicAdd(&s_hist_kmer[bin], n); }
@@ -202,10 +251,10 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams P) {
         const unsigned long long ws = gs << 5;                // absolute position of relative position 0
         const int n_groups = (int)(g1 - gs), n_warm = (int)(g0 - gs);
         int carry_bad = -1;                                   // last invalid relative position seen so far
-        uint32_t prev[L + 1];
+        uint32_t prev[NL], prev2[DUAL ? NL : 1];
 #pragma unroll
-        for (int j = 0; j <= L; j++) prev[j] = kInvalidMin;
-        uint32_t prev_last = kInvalidMin;                     // value of the window ending just before this group
+        for (int j = 0; j < NL; j++) { prev[j] = kInvalidMin; if (DUAL) prev2[j] = kInvalidMin; }
+        uint32_t prev_last = kInvalidMin, prev_last2 = 0;     // values of the window ending just before this group
         uint32_t run_start = 0;                               // relative END position of the first window of the open run
         uint64_t Wprev = gs > 0 ? load_bases(gs - 1) : 0ull;
 
@@ -219,28 +268,35 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams P) {
                 const int gr = gb + gi;                       // group index inside the segment
                 const uint32_t e = ((uint32_t)gr << 5) + (uint32_t)lane;
                 const bool real = gr >= n_warm;
-                // ---- m-mer ending at e: low 2m bits of (Wprev:W) >> 2*(31-lane)
+                // ---- the 16 bases ending at e: low 32 bits of (Wprev:W) >> 2*(31-lane)
                 const uint32_t lo = upper ? (uint32_t)W : (uint32_t)(W >> 32);
                 const uint32_t hi = upper ? (uint32_t)(W >> 32) : (uint32_t)Wprev;
-                const uint32_t v = __funnelshift_r(lo, hi, fsh) & mmask;
+                const uint32_t u16b = __funnelshift_r(lo, hi, fsh);
+                const uint32_t v = u16b & mmask;
                 uint32_t x = mmer_norm(v, revcomp32(v, m), m, mmask);
+                uint32_t y = 0;
+                if (DUAL) y = mmer2_hash(u16b & P.mask2, P.m2);
                 Wprev = W;
-                // ---- minimum over the last w m-mers (doubling, straight-line).  One shuffle per level: lane l reads
-                // from lane (l - s) & 31, and that source lane knows what its reader needs — its value of the
-                // current group if the reader is s lanes above it, of the previous group if the reader wrapped.
+                // ---- minimum over the last w m-mers (doubling).  One shuffle per level: lane l reads from lane
+                // (l - s) & 31, and that source lane knows what its reader needs — its value of the current group
+                // if the reader is s lanes above it, of the previous group if the reader wrapped.
 #pragma unroll
-                for (int j = 0; j < L; j++) {
-                    const int s = 1 << j;
+                for (int j = 0; j < NL; j++) {
+                    const int s = P.sh1[j];
                     const uint32_t cur = x;
                     const uint32_t send = (lane < 32 - s) ? cur : prev[j];
                     x = min(cur, __shfl_sync(FULL, send, (lane - s) & 31));
                     prev[j] = cur;
                 }
-                {   // w = 2^L + d: one more step with offset d (d == 0 degenerates to min(x, x))
-                    const uint32_t cur = x;
-                    const uint32_t send = (lane < 32 - d) ? cur : prev[L];
-                    x = min(cur, __shfl_sync(FULL, send, (lane - d) & 31));
-                    prev[L] = cur;
+                if (DUAL) {
+#pragma unroll
+                    for (int j = 0; j < NL; j++) {
+                        const int s = P.sh2[j];
+                        const uint32_t cur = y;
+                        const uint32_t send = (lane < 32 - s) ? cur : prev2[j];
+                        y = min(cur, __shfl_sync(FULL, send, (lane - s) & 31));
+                        prev2[j] = cur;
+                    }
                 }
                 // ---- validity: last invalid position <= e must be at least k behind
                 const uint32_t tb = IW >> (31 - lane);
@@ -248,6 +304,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams P) {
                 const bool valid = ((int)e - last_bad) >= k;
                 carry_bad = IW ? (gr << 5) + 31 - (__ffs((int)IW) - 1) : carry_bad;
                 const uint32_t Ev = valid ? x : kInvalidMin;
+                const uint32_t Ev2 = (DUAL && valid) ? y : 0u;
                 if (MODE == 2) {
                     const unsigned long long ea = ws + e;
                     if (real && ea + 1 >= (unsigned long long)k) {
@@ -257,18 +314,23 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams P) {
                     continue;
                 }
                 // ---- run boundaries (shuffles and votes stay outside any branch)
-                uint32_t Ep = __shfl_up_sync(FULL, Ev, 1);
-                if (lane == 0) Ep = prev_last;
-                const bool is_start = real && (Ev != kInvalidMin) && (Ev != Ep);
-                const bool is_end = real && (Ep != kInvalidMin) && (Ev != Ep);        // the run ending at e-1
+                uint32_t Ep = __shfl_up_sync(FULL, Ev, 1), Ep2 = 0;
+                if (DUAL) Ep2 = __shfl_up_sync(FULL, Ev2, 1);
+                if (lane == 0) { Ep = prev_last; Ep2 = prev_last2; }
+                const bool differs = (Ev != Ep) || (DUAL && Ev2 != Ep2);
+                const bool is_start = real && (Ev != kInvalidMin) && differs;
+                const bool is_end = real && (Ep != kInvalidMin) && differs;          // the run ending at e-1
                 const uint32_t Sm = __ballot_sync(FULL, is_start), Em = __ballot_sync(FULL, is_end);
                 const uint32_t last = __shfl_sync(FULL, Ev, 31);
+                uint32_t last2 = 0;
+                if (DUAL) last2 = __shfl_sync(FULL, Ev2, 31);
                 if (Em) {
                     if (is_end) {
                         const uint32_t below = Sm & lt_mask;
                         const uint32_t rs = below ? ((uint32_t)gr << 5) + (uint32_t)(31 - __clz((int)below)) : run_start;
                         const int idx = qn + __popc(Em & lt_mask);
                         q_rs[warp][idx] = ws + rs; q_n[warp][idx] = e - rs; q_v[warp][idx] = Ep;
+                        if (DUAL) q_v2[warp][idx] = Ep2;
                     }
                     qn += __popc(Em);
                     __syncwarp();
@@ -276,21 +338,24 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams P) {
                         drain(32);
                         __syncwarp();
                         const bool mv = lane < qn - 32;
-                        unsigned long long t0 = 0; uint32_t t1 = 0, t2 = 0;
-                        if (mv) { t0 = q_rs[warp][32 + lane]; t1 = q_n[warp][32 + lane]; t2 = q_v[warp][32 + lane]; }
+                        unsigned long long t0 = 0; uint32_t t1 = 0, t2 = 0, t3 = 0;
+                        if (mv) { t0 = q_rs[warp][32 + lane]; t1 = q_n[warp][32 + lane]; t2 = q_v[warp][32 + lane]; if (DUAL) t3 = q_v2[warp][32 + lane]; }
                         __syncwarp();
-                        if (mv) { q_rs[warp][lane] = t0; q_n[warp][lane] = t1; q_v[warp][lane] = t2; }
+                        if (mv) { q_rs[warp][lane] = t0; q_n[warp][lane] = t1; q_v[warp][lane] = t2; if (DUAL) q_v2[warp][lane] = t3; }
                         qn -= 32;
                         __syncwarp();
                     }
                 }
                 if (Sm) run_start = ((uint32_t)gr << 5) + (uint32_t)(31 - __clz((int)Sm));
-                if (real) prev_last = last;
+                if (real) { prev_last = last; prev_last2 = last2; }
             }
         }
         // the run still open at the end of the segment is cut here
         if (MODE != 2 && prev_last != kInvalidMin) {
-            if (lane == 0) { q_rs[warp][qn] = ws + run_start; q_n[warp][qn] = ((uint32_t)n_groups << 5) - run_start; q_v[warp][qn] = prev_last; }
+            if (lane == 0) {
+                q_rs[warp][qn] = ws + run_start; q_n[warp][qn] = ((uint32_t)n_groups << 5) - run_start; q_v[warp][qn] = prev_last;
+                if (DUAL) q_v2[warp][qn] = prev_last2;
+            }
             qn += 1;
             __syncwarp();
             if (qn >= 32) { drain(32); qn = 0; __syncwarp(); }     // qn == 32 exactly
@@ -301,7 +366,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams P) {
         if (qn > 0) drain(qn);
     }
 
-    if (MODE == 0 && P.smem_hist) {
+    if (MODE == 0 && !DUAL && P.smem_hist) {
         __syncthreads();
         for (uint32_t b = threadIdx.x; b < P.B; b += kScanThreads) {
             uint32_t r = s_hist_rec[b];

@@ -7,6 +7,7 @@
 //   foreachPartition(extractKXmers)     -> k_expand + segmented radix sort + k_rle
 // There is no CPU fallback: every entry point needs a CUDA device.
 #include "fkm_kernels.cuh"
+#include "fkm_smem.cuh"
 #include "fkm_ingest.cuh"
 #include "fkm_host.h"
 #include "../../include/fastkmer_b200.h"
@@ -98,6 +99,10 @@ struct fkm_ctx {
     double cas_first = 0.0;           // hash path: 1 = probe with the CAS itself instead of a read followed by a CAS
     double debug_force_lsd = 0.0;     // sort path: 0 = auto (MSD + shared-memory chunk sort for 64-bit keys, LSD passes for 128-bit), 1 = LSD, 2 = MSD
     double debug_rho_scale = 1.0;     // test hook: scales the learnt distinct/k-mer ratio (forces the overflow fallback)
+    double count_mode = 0.0;          // hash path: 1 = tables in shared memory (fkm_smem.cuh), 0 = tables in global memory (faster at one GPU today: DESIGN.md §4)
+    double smem_table_slots = 0.0;    // test hook: slots of the shared-memory table (0 = as many as fit)
+    double smem_slow_slots = 1048576.0;   // slots of every CTA's private global table (slow path of k_count_smem)
+    double smem_fill = 0.6;           // share of the table's capacity the planner aims at
     double async_table_bytes = 1024.0 * (1 << 20); // tables of one asynchronous batch; 0 disables the asynchronous phase (0.25-16 GB all within 8 %, profiles/r1_table_sweep.txt)
     uint64_t job_launches = 0;
     uint64_t gen = 0;                 // job generation: results of older jobs are invalid
@@ -176,6 +181,10 @@ extern "C" int fkm_ctx_set(fkm_ctx* c, const char* name, double v) {
     else if (!strcmp(name, "load_factor")) c->load_factor = v;
     else if (!strcmp(name, "async_table_bytes") || !strcmp(name, "l2_table_bytes")) c->async_table_bytes = v;
     else if (!strcmp(name, "debug_rho_scale")) c->debug_rho_scale = v;
+    else if (!strcmp(name, "count_mode")) c->count_mode = v;
+    else if (!strcmp(name, "smem_table_slots")) c->smem_table_slots = v;
+    else if (!strcmp(name, "smem_slow_slots")) c->smem_slow_slots = v;
+    else if (!strcmp(name, "smem_fill")) c->smem_fill = v;
     else if (!strcmp(name, "fold_records")) c->fold_records = v;
     else if (!strcmp(name, "fold_max_ratio")) c->fold_max_ratio = v;
     else if (!strcmp(name, "fold_pool")) c->fold_pool = v;
@@ -242,31 +251,47 @@ static int fkm_read_file_pinned(const char* path, uint8_t** out, uint64_t* n) {
 
 // ------------------------------------------------------------------ scan setup
 typedef void (*ScanKernel)(const ScanParams);
-template <int MODE> static ScanKernel scan_kernel(int L) {
-    switch (L) {
-        case 0: return k_scan<MODE, 0>; case 1: return k_scan<MODE, 1>; case 2: return k_scan<MODE, 2>;
-        case 3: return k_scan<MODE, 3>; case 4: return k_scan<MODE, 4>; default: return k_scan<MODE, 5>;
+template <int MODE, bool DUAL> static ScanKernel scan_kernel(int NL) {
+    switch (NL) {
+        case 1: return k_scan<MODE, 1, DUAL>; case 2: return k_scan<MODE, 2, DUAL>; case 3: return k_scan<MODE, 3, DUAL>;
+        case 4: return k_scan<MODE, 4, DUAL>; case 5: return k_scan<MODE, 5, DUAL>; default: return k_scan<MODE, 6, DUAL>;
     }
 }
+// doubling shifts of a sliding minimum over w values: 1, 2, 4, ... then the remainder; w = 1 + sum.  Returns the levels used.
+static int fill_shifts(int w, int sh[6]) {
+    int n = 0, have = 1;
+    for (int j = 0; j < 6; j++) sh[j] = 0;
+    while (have * 2 <= w) { sh[n++] = have; have *= 2; }
+    if (w > have) sh[n++] = w - have;
+    return n;
+}
+// length of the second (hash-ordered) minimizer of the shared-memory count path: long enough to spread a bin over many
+// cells, short enough to leave runs of several windows (only the partition depends on it, never a count)
+static int second_minimizer_len(int k) { return k >= 23 ? 15 : std::max(std::min(k, 10), k - 8); }
+
 struct ScanSetup { ScanParams P; size_t smem; int grid; ScanKernel fn; };
-template <int MODE>
+template <int MODE, bool DUAL>
 static int scan_setup(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const void* d_bases, const void* d_inv, uint64_t n_pos, ScanSetup* S) {
     ScanParams& P = S->P;
     memset(&P, 0, sizeof P);
     P.bases = (const uint64_t*)d_bases; P.inv = (const uint32_t*)d_inv;
     P.n_pos = n_pos; P.n_words = (n_pos + 31) / 32;
     P.k = cfg->k; P.m = cfg->m; P.w = cfg->k - cfg->m + 1;
-    P.L = 0; while ((2 << P.L) <= P.w) P.L++;
-    P.d = P.w - (1 << P.L);
+    int nl = std::max(1, fill_shifts(P.w, P.sh1));
+    if (DUAL) {
+        P.m2 = second_minimizer_len(cfg->k);
+        P.mask2 = (P.m2 >= 16) ? 0xFFFFFFFFu : ((1u << (2 * P.m2)) - 1u);
+        nl = std::max(nl, fill_shifts(cfg->k - P.m2 + 1, P.sh2));
+    }
     P.seg_len = 4096;
     P.e_total = (MODE == 2) ? n_pos + (uint64_t)cfg->k - 1 : n_pos;
     P.n_seg = (P.e_total + P.seg_len - 1) / P.seg_len;
     P.B = (uint32_t)B;
     P.wide = cfg->k > 32;
     P.cap = (cfg->k > 32) ? (125 - cfg->k) : (61 - cfg->k);
-    P.smem_hist = (MODE == 0 && B <= kSmemHistMaxB) ? 1 : 0;
+    P.smem_hist = (MODE == 0 && !DUAL && B <= kSmemHistMaxB) ? 1 : 0;
     S->smem = P.smem_hist ? (size_t)B * 8 : 0;
-    S->fn = scan_kernel<MODE>(P.L);
+    S->fn = scan_kernel<MODE, DUAL>(nl);
     CK(cudaFuncSetAttribute(S->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S->smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, S->fn, kScanThreads, S->smem));
@@ -300,9 +325,10 @@ static inline uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a
 struct ChunkScan {
     const void* d_bases = nullptr; const void* d_inv = nullptr; uint64_t n_pos = 0;
     ulonglong2* d_events = nullptr; uint64_t ev_cap = 0;
-    unsigned long long* d_count = nullptr;      // [0] events written
+    unsigned long long* d_count = nullptr;      // [0] events written ([0..1]: the two lists of a dual scan)
     int* d_ovf = nullptr;
     unsigned long long n_events = 0; int ev_ovf = 0;
+    ulonglong2* d_events2[2] = {nullptr, nullptr}; uint64_t ev_cap2[2] = {0, 0}; unsigned long long n_events2[2] = {0, 0};   // dual scan
 };
 struct ScanState {
     fkm_config cfg; int32_t B = 0;
@@ -311,16 +337,32 @@ struct ScanState {
     std::vector<unsigned long long> h_rec, h_kmer;
     uint64_t n_pos_total = 0;
     bool valid = false;
+    uint64_t gen = 0;                           // job generation of the context the state belongs to
+    // dual scan (shared-memory count path): runs cut by the signature and a second minimizer, histogram per (bin, cell)
+    bool dual = false; int cell_bits = 0; uint32_t sample_hi = 0;
+    unsigned long long *d_cell_rec = nullptr, *d_cell_kmer = nullptr;
 };
 
 static void free_scan_state(ScanState* p) { delete p; }
 
-static int scan_begin(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, ScanState* S) {
+// n_pos_hint: positions the whole job will scan (sizes the cells of a dual scan)
+static int scan_begin(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, ScanState* S, bool dual = false, uint64_t n_pos_hint = 0) {
     const size_t bB = (size_t)B * 8;
-    S->cfg = *cfg; S->B = B; S->chunks.clear(); S->n_pos_total = 0; S->valid = false;
+    S->cfg = *cfg; S->B = B; S->chunks.clear(); S->n_pos_total = 0; S->valid = false; S->gen = ctx->gen;
     S->h_rec.assign((size_t)B, 0); S->h_kmer.assign((size_t)B, 0);
     CK(dmalloc(ctx, &S->d_hist_rec, bB)); CK(dmalloc(ctx, &S->d_hist_kmer, bB));
     CK(cudaMemsetAsync(S->d_hist_rec, 0, bB, ctx->stream)); CK(cudaMemsetAsync(S->d_hist_kmer, 0, bB, ctx->stream));
+    S->dual = dual; S->cell_bits = 0; S->sample_hi = 0; S->d_cell_rec = S->d_cell_kmer = nullptr;
+    if (dual) {
+        // about 2048 k-windows per cell: fine enough to pack mid bins of a few thousand k-mers evenly
+        const uint64_t per_bin = n_pos_hint / (uint64_t)B;
+        while (S->cell_bits < 12 && (2048ull << S->cell_bits) < per_bin) S->cell_bits++;
+        while (S->cell_bits > 0 && ((uint64_t)B << S->cell_bits) > (1ull << 26)) S->cell_bits--;      // at most 64 M cells
+        S->sample_hi = (uint32_t)std::max(1, B / 64);
+        const size_t cells = (size_t)B << S->cell_bits;
+        CK(dmalloc(ctx, &S->d_cell_rec, cells * 8)); CK(dmalloc(ctx, &S->d_cell_kmer, cells * 8));
+        CK(cudaMemsetAsync(S->d_cell_rec, 0, cells * 8, ctx->stream)); CK(cudaMemsetAsync(S->d_cell_kmer, 0, cells * 8, ctx->stream));
+    }
     return FKM_OK;
 }
 // one scan launch (asynchronous): bin histogram += this chunk, run events of this chunk
@@ -332,12 +374,27 @@ static int scan_chunk(fkm_ctx* ctx, ScanState* S, const void* d_bases, const voi
     const int w_mm = cfg->k - cfg->m + 1;
     // runs average ~(w+1)/2 windows on random sequence; leave generous head-room, an overflow falls back to a second scan
     C.ev_cap = (uint64_t)(((double)n_pos * std::min(0.5, 2.4 / (double)(w_mm + 1)) + (double)(1u << 20)) * ctx->debug_event_scale) + 64;
-    CK(dmalloc(ctx, &C.d_events, (size_t)C.ev_cap * 16));
     CK(dmalloc(ctx, &C.d_count, 16)); CK(dmalloc(ctx, &C.d_ovf, 8));
     CK(cudaMemsetAsync(C.d_count, 0, 16, s)); CK(cudaMemsetAsync(C.d_ovf, 0, 8, s));
-    ScanSetup Q; int rc = scan_setup<0>(ctx, cfg, S->B, d_bases, d_inv, n_pos, &Q); if (rc) return rc;
+    ScanSetup Q; int rc;
+    if (!S->dual) {
+        CK(dmalloc(ctx, &C.d_events, (size_t)C.ev_cap * 16));
+        rc = scan_setup<0, false>(ctx, cfg, S->B, d_bases, d_inv, n_pos, &Q); if (rc) return rc;
+        Q.P.events = C.d_events; Q.P.ev_cap = C.ev_cap;
+    } else {
+        // two cut rules: about 2/(w+1) + 2/(w2+1) runs per position; the sample bins' events go to their own (short) list
+        const int w2 = cfg->k - second_minimizer_len(cfg->k) + 1;
+        const uint64_t total = (uint64_t)(((double)n_pos * std::min(0.7, 2.4 / (double)(w_mm + 1) + 2.4 / (double)(w2 + 1)) + (double)(1u << 20)) * ctx->debug_event_scale) + 64;
+        const double frac = (double)S->sample_hi / (double)S->B;
+        C.ev_cap2[0] = std::min<uint64_t>(total, (uint64_t)((double)total * frac * 3.0) + (1u << 18));     // the sample bins' events
+        C.ev_cap2[1] = total;                                                                                    // every event
+        CK(dmalloc(ctx, &C.d_events2[0], (size_t)C.ev_cap2[0] * 16)); CK(dmalloc(ctx, &C.d_events2[1], (size_t)C.ev_cap2[1] * 16));
+        rc = scan_setup<0, true>(ctx, cfg, S->B, d_bases, d_inv, n_pos, &Q); if (rc) return rc;
+        Q.P.events2[0] = C.d_events2[0]; Q.P.events2[1] = C.d_events2[1]; Q.P.ev_cap2[0] = C.ev_cap2[0]; Q.P.ev_cap2[1] = C.ev_cap2[1];
+        Q.P.cell_bits = S->cell_bits; Q.P.sample_hi = S->sample_hi; Q.P.cell_rec = S->d_cell_rec; Q.P.cell_kmer = S->d_cell_kmer;
+    }
     Q.P.hist_rec = S->d_hist_rec; Q.P.hist_kmer = S->d_hist_kmer;
-    Q.P.events = C.d_events; Q.P.ev_cap = C.ev_cap; Q.P.ev_count = C.d_count; Q.P.ev_overflow = C.d_ovf;
+    Q.P.ev_count = C.d_count; Q.P.ev_overflow = C.d_ovf;
     if (n_pos) { Q.fn<<<Q.grid, kScanThreads, Q.smem, s>>>(Q.P); CKL(); }
     S->chunks.push_back(C);
     S->n_pos_total += n_pos;
@@ -346,13 +403,17 @@ static int scan_chunk(fkm_ctx* ctx, ScanState* S, const void* d_bases, const voi
 static int scan_end(fkm_ctx* ctx, ScanState* S, fkm_stats* st) {
     cudaStream_t s = ctx->stream;
     const size_t bB = (size_t)S->B * 8;
+    if (S->dual) {      // the dual scan keeps its histogram per (bin, cell) only
+        k_cells_bin_totals<<<(unsigned)(((uint64_t)S->B * 32 + 255) / 256), 256, 0, s>>>(S->d_cell_rec, S->d_cell_kmer, S->cell_bits, S->B, S->d_hist_rec, S->d_hist_kmer); CKL();
+    }
     CK(cudaMemcpyAsync(S->h_rec.data(), S->d_hist_rec, bB, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(S->h_kmer.data(), S->d_hist_kmer, bB, cudaMemcpyDeviceToHost, s));
     for (ChunkScan& C : S->chunks) {
-        CK(cudaMemcpyAsync(&C.n_events, C.d_count, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(C.n_events2, C.d_count, 16, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(&C.ev_ovf, C.d_ovf, 4, cudaMemcpyDeviceToHost, s));
     }
     CK(cudaStreamSynchronize(s));
+    for (ChunkScan& C : S->chunks) if (!S->dual) C.n_events = C.n_events2[0];
     st->d2h_bytes += 2 * bB + 12 * S->chunks.size();
     S->valid = true;
     return FKM_OK;
@@ -371,8 +432,8 @@ static uint64_t compact_grid(fkm_ctx* ctx) {
 
 // stage 1 on input that is already resident: one chunk
 static int stage_scan(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const void* d_bases, const void* d_inv, uint64_t n_pos,
-                      ScanState* S, fkm_stats* st) {
-    int rc = scan_begin(ctx, cfg, B, S); if (rc) return rc;
+                      ScanState* S, fkm_stats* st, bool dual = false) {
+    int rc = scan_begin(ctx, cfg, B, S, dual, n_pos); if (rc) return rc;
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     rc = scan_chunk(ctx, S, d_bases, d_inv, n_pos); if (rc) return rc;
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -412,7 +473,7 @@ static int stage_scatter(fkm_ctx* ctx, ScanState* S, const unsigned long long* d
         } else {
             // the event list was too small for this chunk: scan it again, writing the records directly
             st->n_fallbacks++;
-            ScanSetup Q; int rc = scan_setup<1>(ctx, cfg, S->B, C.d_bases, C.d_inv, C.n_pos, &Q); if (rc) return rc;
+            ScanSetup Q; int rc = scan_setup<1, false>(ctx, cfg, S->B, C.d_bases, C.d_inv, C.n_pos, &Q); if (rc) return rc;
             Q.P.bin_base = d_bin_base; Q.P.cursor = d_cursor; Q.P.cursor_shift = cursor_shift; Q.P.records = d_records;
             if (n_rec && C.n_pos) { Q.fn<<<Q.grid, kScanThreads, Q.smem, s>>>(Q.P); CKL(); }
         }
@@ -983,6 +1044,196 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
 #undef CKLC
 }
 
+// ------------------------------------------------------------------ the shared-memory count pipeline (fkm_smem.cuh)
+static constexpr int kRetryGlobal = 1;          // internal: the job must be redone by the global-table pipeline
+
+// geometry of k_count_smem's shared memory for one key width
+struct SmemGeom { uint32_t cap_slots, max_fill, stage_recs; size_t bytes; };
+template <bool WIDE>
+static SmemGeom smem_geometry(fkm_ctx* ctx) {
+    typedef typename Traits<WIDE>::Key Key;
+    const size_t rec_bytes = Traits<WIDE>::kRecWords * 8;
+    SmemGeom g;
+    g.stage_recs = (uint32_t)(16384 / rec_bytes);                        // kSmStages staging buffers of 16 KB
+    const size_t avail = ctx->smem_optin - kSmStages * 16384 - 1024;     // 1 KB for the kernel's static shared memory
+    size_t cap = avail / (sizeof(Key) + 4);                              // per slot: key + count
+    if (ctx->smem_table_slots >= 64.0) cap = std::min<size_t>(cap, (size_t)ctx->smem_table_slots);
+    cap = cap / 32 * 32;
+    g.cap_slots = (uint32_t)cap;
+    g.max_fill = (uint32_t)std::min<size_t>(cap * 3 / 4, cap > 2 * (size_t)kSmThreads + 64 ? cap - 2 * (size_t)kSmThreads : cap / 4);
+    g.bytes = cap * (sizeof(Key) + 4) + (size_t)kSmStages * 16384;
+    return g;
+}
+
+// Hash path with the tables in shared memory: dual scan -> (bin, cell) histogram -> mid bins -> records mid-bin-major ->
+// k_count_smem.  Two phases: the first B/64 bins are a sample sized for all-distinct k-mers; the distinct / k-mer ratio
+// they show sizes the mid bins and the output arrays of the rest.
+template <bool WIDE>
+static int run_pipeline_smem(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, fkm_result* res, fkm_stats* st, ScanState& scan) {
+    typedef typename Traits<WIDE>::Key Key;
+    cudaStream_t s = ctx->stream;
+    const int rec_bytes = Traits<WIDE>::kRecWords * 8;
+    res->ctx = ctx; res->gen = ctx->gen;
+    res->B = B; res->k = cfg->k; res->wide = WIDE; res->sorted = false; res->device = ctx->device;
+    res->out_base.assign((size_t)B + 1, 0);
+    Trace tr;
+    const size_t bB = (size_t)B * 8;
+    for (const ChunkScan& C : scan.chunks) if (C.ev_ovf) return kRetryGlobal;          // the event lists were too small
+    const std::vector<unsigned long long>& h_rec = scan.h_rec; const std::vector<unsigned long long>& h_kmer = scan.h_kmer;
+    uint64_t n_rec = 0, n_kmers = 0, nonempty = 0;
+    for (int b = 0; b < B; b++) { n_rec += h_rec[(size_t)b]; n_kmers += h_kmer[(size_t)b]; nonempty += h_rec[(size_t)b] ? 1 : 0; }
+    st->n_kmers = n_kmers; st->n_superkmers = n_rec; st->superkmer_bytes = n_rec * rec_bytes; st->n_nonempty_bins = nonempty;
+
+    const SmemGeom G = smem_geometry<WIDE>(ctx);
+    CK(cudaFuncSetAttribute(k_count_smem<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.bytes));
+    const int cb = scan.cell_bits; const size_t n_cells = (size_t)B << cb;
+    const uint64_t C_cells = 1ull << cb;
+    const int s_hi = (int)std::min<uint32_t>(scan.sample_hi, (uint32_t)B);
+
+    unsigned long long *d_acc = nullptr, *d_counters = nullptr, *d_mid_first = nullptr;
+    uint32_t* d_cell2mid = nullptr; int* d_flags = nullptr; void* d_slow_keys = nullptr; uint32_t* d_slow_cnt = nullptr;
+    CK(dmalloc(ctx, &d_acc, 192 * 8)); CK(dmalloc(ctx, &d_counters, 64)); CK(dmalloc(ctx, &d_flags, 16));
+    CK(dmalloc(ctx, &d_mid_first, bB + 8)); CK(dmalloc(ctx, &d_cell2mid, n_cells * 4));
+    const uint64_t slow_slots = std::max<uint64_t>(1024, (uint64_t)ctx->smem_slow_slots);
+    CK(dmalloc(ctx, &d_slow_keys, (size_t)ctx->n_sm * slow_slots * sizeof(Key))); CK(dmalloc(ctx, &d_slow_cnt, (size_t)ctx->n_sm * slow_slots * 4));
+    CK(cudaMemsetAsync(d_acc, 0, 192 * 8, s));
+    CK(cudaMemsetAsync(d_counters, 0, 64, s)); CK(cudaMemsetAsync(d_flags, 0, 16, s));
+    float ms_pack = 0, ms_scatter = 0, ms_count = 0;
+    uint64_t out_total = 0, n_mid_total = 0;
+    std::vector<unsigned long long> h_mid_first((size_t)B + 1);
+    // one phase: bins [lo, hi), events of list `li`, mid bins of about T k-mers, output arrays of out_cap entries
+    const unsigned grid = (unsigned)ctx->n_sm;
+    std::vector<unsigned long long> h_cta_total((size_t)grid), h_bin_off((size_t)B);
+    std::vector<uint32_t> h_bin_cta((size_t)B);
+    unsigned long long* d_cta_total = nullptr; uint32_t* d_bin_cta = nullptr; unsigned long long* d_bin_off = nullptr;
+    CK(dmalloc(ctx, &d_cta_total, (size_t)grid * 8)); CK(dmalloc(ctx, &d_bin_cta, (size_t)B * 4)); CK(dmalloc(ctx, &d_bin_off, bB));
+    // one phase: bins [lo, hi), events of list `li`, mid bins of about T k-mers; rho = distinct / k-mers expected (sizes the output)
+    auto run_phase = [&](int lo, int hi, int li, uint64_t T, double rho) -> int {
+        if (lo >= hi) return FKM_OK;
+        uint64_t n_mid = 0, rec_phase = 0, km_phase = 0;
+        for (int b = 0; b <= B; b++) h_mid_first[(size_t)b] = 0;
+        for (int b = lo; b < hi; b++) {
+            h_mid_first[(size_t)b] = n_mid;
+            const uint64_t km = h_kmer[(size_t)b];
+            const uint64_t Tb = std::max<uint64_t>(T, (km + C_cells - 1) / C_cells);     // never more mid bins than cells
+            n_mid += km ? (km - 1) / Tb + 1 : 0;
+            rec_phase += h_rec[(size_t)b]; km_phase += km;
+        }
+        for (int b = hi; b <= B; b++) h_mid_first[(size_t)b] = n_mid;
+        for (int b = lo; b < hi; b++) res->out_base[(size_t)b] = out_total;
+        if (n_mid >= 0xFFFFFFFFull) return kRetryGlobal;
+        if (n_mid == 0) return FKM_OK;
+        // every CTA counts an equal share of the k-mers (plus at most one mid bin) into its own output region
+        const uint64_t share = km_phase / grid + 8 * T + 1;
+        const uint64_t region_cap = std::min<uint64_t>(share, (uint64_t)((double)share * std::min(1.0, rho * 1.25 + 0.01))) + 65536;
+        unsigned long long *d_mid_rec = nullptr, *d_mid_kmer = nullptr, *d_mid_base = nullptr, *d_mid_kbase = nullptr;
+        uint32_t* d_mid_bin = nullptr; void* d_records = nullptr; void* d_okeys = nullptr; uint32_t* d_ocnt = nullptr;
+        CK(dmalloc(ctx, &d_mid_rec, n_mid * 8)); CK(dmalloc(ctx, &d_mid_kmer, n_mid * 8)); CK(dmalloc(ctx, &d_mid_base, (n_mid + 1) * 8)); CK(dmalloc(ctx, &d_mid_kbase, (n_mid + 1) * 8));
+        CK(dmalloc(ctx, &d_mid_bin, n_mid * 4));
+        CK(dmalloc(ctx, &d_records, std::max<size_t>(16, (size_t)rec_phase * rec_bytes)));
+        CK(dmalloc(ctx, &d_okeys, (size_t)grid * region_cap * sizeof(Key))); CK(dmalloc(ctx, &d_ocnt, (size_t)grid * region_cap * 4));
+        CK(cudaMemsetAsync(d_mid_rec, 0, n_mid * 8, s)); CK(cudaMemsetAsync(d_mid_kmer, 0, n_mid * 8, s));
+        CK(cudaMemsetAsync(d_cta_total, 0, (size_t)grid * 8, s));
+        CK(cudaMemcpyAsync(d_mid_first, h_mid_first.data(), bB + 8, cudaMemcpyHostToDevice, s));
+        st->h2d_bytes += bB + 8;
+        CK(cudaEventRecord(ctx->ev[5], s));
+        CellsParams CP;
+        CP.cell_rec = scan.d_cell_rec; CP.cell_kmer = scan.d_cell_kmer; CP.cell_bits = cb; CP.bin_lo = lo; CP.bin_hi = hi; CP.T = T;
+        CP.bin_kmer = scan.d_hist_kmer; CP.mid_first = d_mid_first; CP.cell2mid = d_cell2mid; CP.mid_rec = d_mid_rec; CP.mid_kmer = d_mid_kmer; CP.mid_bin = d_mid_bin;
+        k_cells_assign<<<(unsigned)(((uint64_t)(hi - lo) * 32 + 255) / 256), 256, 0, s>>>(CP); CKL();
+        k_excl_scan_u64<<<1, 1024, 0, s>>>(d_mid_rec, d_mid_base, n_mid); CKL();
+        k_excl_scan_u64<<<1, 1024, 0, s>>>(d_mid_kmer, d_mid_kbase, n_mid); CKL();
+        const unsigned long long cell_lo = (unsigned long long)lo << cb, cell_hi = (unsigned long long)hi << cb;
+        unsigned long long* d_mid_next = nullptr;                                     // write cursors of the scatter: start at the mid bins' offsets
+        CK(dmalloc(ctx, &d_mid_next, n_mid * 8));
+        CK(cudaMemcpyAsync(d_mid_next, d_mid_base, n_mid * 8, cudaMemcpyDeviceToDevice, s));
+        CK(cudaEventRecord(ctx->ev[6], s));
+        for (const ChunkScan& C : scan.chunks) {
+            if (!C.n_events2[li]) continue;
+            Scatter2Params Q;
+            Q.events = C.d_events2[li]; Q.n_events = C.n_events2[li]; Q.bases = (const uint64_t*)C.d_bases; Q.n_words = (C.n_pos + 31) / 32;
+            Q.cap = WIDE ? (125 - cfg->k) : (61 - cfg->k); Q.k = cfg->k; Q.cell_bits = cb;
+            Q.cell_lo = cell_lo; Q.cell_hi = cell_hi; Q.cell2mid = d_cell2mid; Q.mid_next = d_mid_next; Q.records = d_records;
+            k_scatter2<WIDE><<<(unsigned)((Q.n_events + 255) / 256), 256, 0, s>>>(Q); CKL();
+        }
+        CK(cudaEventRecord(ctx->ev[7], s));
+        SmemCountParams P;
+        P.records = d_records; P.mid_rec_base = d_mid_base; P.mid_kmer_base = d_mid_kbase; P.mid_bin = d_mid_bin; P.mid_first = d_mid_first; P.n_mid = (uint32_t)n_mid;
+        P.out_keys = d_okeys; P.out_cnt = d_ocnt; P.region_cap = region_cap; P.cta_total = d_cta_total; P.bin_cta = d_bin_cta; P.bin_off = d_bin_off;
+        P.acc = d_acc; P.k = cfg->k; P.cap_slots = G.cap_slots; P.max_fill = G.max_fill; P.stage_recs = G.stage_recs;
+        P.slow_keys = d_slow_keys; P.slow_cnt = d_slow_cnt; P.slow_slots = slow_slots; P.slow_max_fill = slow_slots * 7 / 10; P.flags = d_flags; P.counters = d_counters;
+        k_count_smem<WIDE><<<grid, kSmBlock, G.bytes, s>>>(P); CKL();
+        CK(cudaEventRecord(ctx->ev[8], s));
+        int flags[4] = {0, 0, 0, 0};
+        CK(cudaMemcpyAsync(h_cta_total.data(), d_cta_total, (size_t)grid * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h_bin_cta.data() + lo, d_bin_cta + lo, (size_t)(hi - lo) * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h_bin_off.data() + lo, d_bin_off + lo, (size_t)(hi - lo) * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(flags, d_flags, 16, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        st->d2h_bytes += 16 + (size_t)grid * 8 + (size_t)(hi - lo) * 12;
+        { float ms; cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]); ms_pack += ms; cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); ms_scatter += ms;
+          cudaEventElapsedTime(&ms, ctx->ev[7], ctx->ev[8]); ms_count += ms; }
+        if (flags[2]) return fkm_set_error(FKM_EOVERFLOW, "a k-mer occurs more than 2^32-1 times: 32-bit counts overflow (the reference counts in Int, SBKC:562,676)");
+        if (flags[0] || flags[1]) return kRetryGlobal;
+        // one result chunk per CTA region; a bin's entries begin in the region of the CTA that counted its first mid bin
+        std::vector<unsigned long long> cta_start((size_t)grid + 1);
+        cta_start[0] = out_total;
+        for (unsigned c = 0; c < grid; c++) {
+            cta_start[(size_t)c + 1] = cta_start[(size_t)c] + h_cta_total[(size_t)c];
+            if (h_cta_total[(size_t)c]) {
+                Chunk ch; ch.keys = (char*)d_okeys + (size_t)c * region_cap * sizeof(Key); ch.cnt = d_ocnt + (size_t)c * region_cap; ch.n = h_cta_total[(size_t)c];
+                res->chunks.push_back(ch);
+            }
+        }
+        unsigned long long next = cta_start[(size_t)grid];
+        for (int b = hi - 1; b >= lo; b--) {
+            if (h_mid_first[(size_t)b + 1] > h_mid_first[(size_t)b]) next = cta_start[(size_t)h_bin_cta[(size_t)b]] + h_bin_off[(size_t)b];
+            res->out_base[(size_t)b] = next;
+        }
+        out_total = cta_start[(size_t)grid];
+        n_mid_total += n_mid;
+        st->n_batches++;
+        return FKM_OK;
+    };
+
+    CK(cudaEventRecord(ctx->ev[1], s));
+    // phase A: the sample, sized for all-distinct k-mers
+    uint64_t km_a = 0; for (int b = 0; b < s_hi; b++) km_a += h_kmer[(size_t)b];
+    const uint64_t T_safe = std::max<uint64_t>(32, (uint64_t)((double)G.max_fill * ctx->smem_fill));
+    int rc = run_phase(0, s_hi, 0, T_safe, 1.0); if (rc) return rc;
+    tr.mark("sample phase done", (long long)out_total);
+    if (s_hi < B) {
+        double rho = 1.0;
+        if (km_a > 100000) rho = std::min(1.0, (double)out_total / (double)km_a);
+        rho *= ctx->debug_rho_scale;
+        const double rho_plan = std::min(1.0, rho * 1.1 + 0.01);
+        const uint64_t T_b = std::max<uint64_t>(T_safe, (uint64_t)((double)G.max_fill * ctx->smem_fill / rho_plan));
+        rc = run_phase(s_hi, B, 1, T_b, rho); if (rc) return rc;
+    }
+    res->out_base[(size_t)B] = out_total;
+    CK(cudaEventRecord(ctx->ev[3], s));
+    unsigned long long h_acc[192], h_counters[8];
+    CK(cudaMemcpyAsync(h_acc, d_acc, 192 * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h_counters, d_counters, 64, cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(ctx->ev[4], s));
+    CK(cudaStreamSynchronize(s));
+    st->d2h_bytes += 192 * 8 + 64;
+    unsigned long long acc[3] = {0, 0, 0};
+    for (int i = 0; i < 64; i++) { acc[0] += h_acc[i]; acc[1] ^= h_acc[64 + i]; acc[2] += h_acc[128 + i]; }
+    res->total = out_total;
+    st->n_distinct = out_total; st->digest_sum = acc[0]; st->digest_xor = acc[1]; st->total_count = acc[2];
+    st->n_mid_bins = n_mid_total; st->n_slow_bins = h_counters[0];
+    st->ms_stage[2] = ms_scatter; st->ms_stage[3] = ms_count; st->ms_stage[4] = ms_pack;
+    float ms; cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); st->ms_stage[5] = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]); st->ms_stage[7] = ms;
+    if (st->total_count != st->n_kmers)
+        return fkm_set_error(FKM_ECUDA, "internal check failed (shared-memory path): sum of counts %llu != valid k-windows %llu",
+                             (unsigned long long)st->total_count, (unsigned long long)st->n_kmers);
+    return FKM_OK;
+}
+
+static bool want_smem_path(const fkm_ctx* ctx, const fkm_config* cfg) { return cfg->use_ht && ctx->count_mode >= 1.0; }
+
 static int count_device(fkm_ctx* ctx, const fkm_config* cfg, const void* d_bases, const void* d_inv, uint64_t n_pos,
                         fkm_result** out, fkm_stats* stats, const PreScattered* pre = nullptr, ScanState* scanned = nullptr) {
     int32_t B = 0; int rc = validate(cfg, &B); if (rc) return rc;
@@ -995,8 +1246,38 @@ static int count_device(fkm_ctx* ctx, const fkm_config* cfg, const void* d_bases
     st->n_positions = n_pos;
     auto t0 = std::chrono::steady_clock::now();
     fkm_result* res = new fkm_result();
-    rc = (cfg->k > 32) ? run_pipeline<true>(ctx, cfg, B, d_bases, d_inv, n_pos, res, st, pre, scanned)
-                       : run_pipeline<false>(ctx, cfg, B, d_bases, d_inv, n_pos, res, st, pre, scanned);
+    const bool wide = cfg->k > 32;
+    rc = -1000;
+    ScanState rescan;                                      // non-dual scan of the same chunks, for the fallback
+    if (!pre && want_smem_path(ctx, cfg) && (!scanned || scanned->dual)) {
+        // ---- tables in shared memory
+        ScanState local_scan;
+        ScanState* S = scanned;
+        const Arena::Mark mk = ctx->arena.mark();
+        if (!S) {
+            S = &local_scan;
+            rc = stage_scan(ctx, cfg, B, d_bases, d_inv, n_pos, S, st, true);
+        } else { CK(cudaEventRecord(ctx->ev[0], ctx->stream)); rc = FKM_OK; }
+        if (!rc) rc = wide ? run_pipeline_smem<true>(ctx, cfg, B, res, st, *S) : run_pipeline_smem<false>(ctx, cfg, B, res, st, *S);
+        if (rc == kRetryGlobal) {
+            // a table overflowed even on the slow path, or the output estimate was too small: the global-table pipeline redoes the job
+            const uint64_t fb = st->n_fallbacks + 1, h2d = st->h2d_bytes, d2h = st->d2h_bytes;
+            delete res; res = new fkm_result();
+            if (!scanned) ctx->arena.release(mk);
+            else {
+                rc = scan_begin(ctx, cfg, B, &rescan);
+                for (size_t c = 0; !rc && c < scanned->chunks.size(); c++) rc = scan_chunk(ctx, &rescan, scanned->chunks[c].d_bases, scanned->chunks[c].d_inv, scanned->chunks[c].n_pos);
+                if (!rc) { fkm_stats tmp; memset(&tmp, 0, sizeof tmp); rc = scan_end(ctx, &rescan, &tmp); }
+                if (rc) { fkm_result_free(res); return rc; }
+                scanned = &rescan;
+            }
+            st->n_fallbacks = fb; st->h2d_bytes = h2d; st->d2h_bytes = d2h; st->n_batches = 0;
+            rc = -1000;
+        }
+    }
+    if (rc == -1000)
+        rc = wide ? run_pipeline<true>(ctx, cfg, B, d_bases, d_inv, n_pos, res, st, pre, scanned)
+                  : run_pipeline<false>(ctx, cfg, B, d_bases, d_inv, n_pos, res, st, pre, scanned);
     st->gpu_launches = ctx->job_launches;       // everything since job_begin (ingest included)
     st->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (rc) { fkm_result_free(res); return rc; }
@@ -1110,13 +1391,13 @@ static void split_fasta(const uint8_t* t, uint64_t n, uint64_t target, std::vect
 // stream while earlier chunks are parsed (fkm_ingest.cuh) and scanned (k_scan) on the compute stream,
 // so the PCIe copy — the longest single step of an end-to-end job — hides the parse and the scan.
 static int front_end_fasta(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const uint8_t* fasta, uint64_t n_bytes,
-                           ScanState* S, uint64_t* n_bases_total) {
+                           ScanState* S, uint64_t* n_bases_total, bool dual) {
     std::vector<uint64_t> cuts;
     split_fasta(fasta, n_bytes, (uint64_t)std::max(4096.0, ctx->ingest_chunk_bytes), cuts);
     const size_t nc = cuts.size() - 1;
     uint64_t max_chunk = 16;
     for (size_t c = 0; c < nc; c++) max_chunk = std::max(max_chunk, cuts[c + 1] - cuts[c]);
-    int rc = scan_begin(ctx, cfg, B, S); if (rc) return rc;
+    int rc = scan_begin(ctx, cfg, B, S, dual, n_bytes); if (rc) return rc;
     uint8_t* d_text[2] = {nullptr, nullptr};
     CK(dmalloc(ctx, (void**)&d_text[0], max_chunk));
     if (nc > 1) CK(dmalloc(ctx, (void**)&d_text[1], max_chunk));
@@ -1156,7 +1437,7 @@ extern "C" int fkm_count_fasta(fkm_ctx* ctx, const fkm_config* cfg, const uint8_
     fkm_stats local; fkm_stats* st = stats ? stats : &local;
     memset(st, 0, sizeof *st);
     ScanState S; uint64_t n_bases = 0;
-    rc = front_end_fasta(ctx, cfg, B, fasta, n_bytes, &S, &n_bases); if (rc) return rc;
+    rc = front_end_fasta(ctx, cfg, B, fasta, n_bytes, &S, &n_bases, want_smem_path(ctx, cfg)); if (rc) return rc;
     fkm_stats tmp; memset(&tmp, 0, sizeof tmp);
     rc = scan_end(ctx, &S, &tmp); if (rc) return rc;
     const double ms_in = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -1210,7 +1491,7 @@ extern "C" int fkm_execute_job(fkm_ctx* ctx, const fkm_config* cfg, fkm_stats* s
 
 // ------------------------------------------------------------------ staged entry points (multi-GPU)
 static int front_end_fasta(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const uint8_t* fasta, uint64_t n_bytes,
-                           ScanState* S, uint64_t* n_bases_total);
+                           ScanState* S, uint64_t* n_bases_total, bool dual);
 extern "C" int32_t fkm_record_bytes(const fkm_config* cfg) { return (cfg && cfg->k > 32) ? 32 : 16; }
 
 extern "C" int fkm_mg_scan(fkm_ctx* ctx, const fkm_config* cfg, const void* d_bases, const void* d_inv, uint64_t n_pos,
@@ -1234,7 +1515,7 @@ extern "C" int fkm_mg_scan_fasta(fkm_ctx* ctx, const fkm_config* cfg, const uint
     rc = job_begin(ctx); if (rc) return rc;
     if (!ctx->mg_scan) ctx->mg_scan = new ScanState();
     uint64_t nb = 0;
-    rc = front_end_fasta(ctx, cfg, B, fasta, n_bytes, ctx->mg_scan, &nb); if (rc) return rc;
+    rc = front_end_fasta(ctx, cfg, B, fasta, n_bytes, ctx->mg_scan, &nb, false); if (rc) return rc;
     if (n_bases) *n_bases = nb;
     fkm_stats st; memset(&st, 0, sizeof st);
     rc = scan_end(ctx, ctx->mg_scan, &st); if (rc) return rc;
@@ -1599,7 +1880,7 @@ extern "C" int fkm_debug_window_bins(fkm_ctx* ctx, const fkm_config* cfg, const 
     CK(cudaMemcpyAsync(d_b, bases, nw * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_i, inv, nw * 4, cudaMemcpyHostToDevice, ctx->stream));
     ScanSetup S; S.grid = 1; S.smem = 0; S.fn = nullptr;
-    rc = scan_setup<2>(ctx, cfg, B, d_b, d_i, n_pos, &S);
+    rc = scan_setup<2, false>(ctx, cfg, B, d_b, d_i, n_pos, &S);
     if (!rc) { S.P.dbg_bins = d_o; S.fn<<<S.grid, kScanThreads, S.smem, ctx->stream>>>(S.P); }
     if (!rc) { CKL(); CK(cudaMemcpyAsync(bins_out, d_o, n_pos * 4, cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream)); }
     dfree(ctx, d_b); dfree(ctx, d_i); dfree(ctx, d_o);

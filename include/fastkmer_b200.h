@@ -79,6 +79,8 @@ typedef struct fkm_stats {
     double   ms_stage[8];        /* 0 parse/pack+H2D 1 histogram 2 scatter 3 count 4 compact/reduce 5 digest 6 D2H/write 7 whole device pipeline (CUDA events) */
     uint64_t n_folded_records;   /* records left after folding identical ones (knob fold_records); 0 = not folded */
     double   ms_fold;            /* device time of the folding stage (between scatter and count)       */
+    uint64_t n_mid_bins;         /* shared-memory count path: tables (mid bins) the bins were cut into; 0 = global-table path */
+    uint64_t n_slow_bins;        /* ... of which overflowed shared memory and were redone in a global-memory table */
 } fkm_stats;
 
 const char* fkm_last_error(void);
@@ -88,7 +90,10 @@ const char* fkm_last_error(void);
 int  fkm_ctx_create(int device, void* stream, fkm_ctx** out);
 void fkm_ctx_destroy(fkm_ctx* ctx);
 int  fkm_ctx_sync(fkm_ctx* ctx);
-/* tuning knobs (optional): name in {"table_budget_bytes","async_table_bytes","sort_budget_keys","load_factor","ingest_chunk_bytes",
+/* tuning knobs (optional): "count_mode" (use_ht = 1: 0 = tables in global memory, the default; 1 = tables in shared memory,
+ * csrc/fkm_smem.cuh: DRAM sees the records once and the result once and the stage does not depend on the input size),
+ * "smem_table_slots" / "smem_slow_slots" (test hooks: smaller tables force the slow path / the global-table fallback),
+ * and name in {"table_budget_bytes","async_table_bytes","sort_budget_keys","load_factor","ingest_chunk_bytes",
  * "fold_records" (default 1: hash path with k <= 32 folds identical super-k-mer records into one weighted record before
  * counting, unless the sampled first bins show more than "fold_max_ratio" (0.6) distinct records; 0 = never), "fold_table_bytes", "fold_pool" (records per warp in k_fold_insert: 64, 128, 256),
  * "cas_first" (experiment: probe with the CAS itself; slower, see profiles/README.md)} */

@@ -191,6 +191,7 @@ def test_small_table_budget_batches_and_retry(ctx, oracle):
     want = oracle.count(fasta, 28, 10, 3, 2048, 1, threads=8)
     c2 = fk.Context(0)
     try:
+        c2.set("count_mode", 0)                               # the global-table pipeline (fallback of the shared-memory path)
         c2.set("table_budget_bytes", 1 << 20)
         c2.set("async_table_bytes", 0)                        # synchronous batches only
         res, st = c2.count_fasta(cfg(28, 10, 3, 2048, 1), fasta)
@@ -212,6 +213,7 @@ def test_async_phase_overflow_falls_back(oracle):
     want = oracle.count(fasta, 28, 10, 3, 2048, 1, threads=8)
     c2 = fk.Context(0)
     try:
+        c2.set("count_mode", 0)                               # the global-table pipeline (fallback of the shared-memory path)
         res, st = c2.count_fasta(cfg(28, 10, 3, 2048, 1), fasta)
         assert st["n_fallbacks"] == 0 and st["n_batches"] >= 2
         assert_same(res.sorted_arrays(), want, "async phase")
@@ -239,6 +241,88 @@ def test_async_phase_overflow_falls_back(oracle):
         c2.close()
 
 
+def test_smem_path_tiers(oracle):
+    """useHT=1 counts in shared-memory tables (k_count_smem).  A mid bin with more distinct k-mers than the table holds is
+    redone by its CTA in a private global table (slow path); if that overflows too, or the output estimate is too small, or
+    the run-event lists overflow, the whole job is redone by the global-table pipeline.  Every tier gives the oracle's result."""
+    deep = fk.synth_fasta(dict(seeds=(31, 32, 33), genome_len=50000, n_reads=50000, read_len=100)).tobytes()      # 100x coverage
+    flat = fk.synth_fasta(dict(seeds=(34, 35, 36), genome_len=30000000, n_reads=40000, read_len=150)).tobytes()   # nearly all distinct
+    c2 = fk.Context(0)
+    try:
+        c2.set("count_mode", 1)
+        for text, label in ((deep, "deep"), (flat, "flat")):
+            for k, m, B in ((28, 10, 2048), (55, 13, 2048), (33, 9, 64), (31, 11, 1), (12, 4, 100), (22, 8, 300)):
+                want = oracle.count(text, k, m, 3, B, 1, threads=8)
+                ws = want["stats"]
+                for knobs, tier in (({}, "fast"), ({"smem_table_slots": 256}, "slow"),
+                                    ({"smem_table_slots": 256, "smem_slow_slots": 1024}, "fallback"),
+                                    ({"debug_rho_scale": 0.02}, "rho"), ({"debug_event_scale": 0.001}, "events")):
+                    for name in ("smem_table_slots", "debug_rho_scale", "debug_event_scale"):
+                        c2.set(name, {"smem_table_slots": 0, "debug_rho_scale": 1.0, "debug_event_scale": 1.0}[name])
+                    c2.set("smem_slow_slots", 1 << 20)
+                    for name, v in knobs.items():
+                        c2.set(name, v)
+                    res, st = c2.count_fasta(cfg(k, m, 3, B, 1), text)
+                    what = "smem %s %s k=%d B=%d" % (tier, label, k, B)
+                    assert_same(res.sorted_arrays(), want, what)
+                    assert (st["digest_sum"], st["digest_xor"]) == (ws["digest_sum"], ws["digest_xor"]), what
+                    assert st["n_kmers"] == ws["n_kmers"] == st["total_count"] and st["n_distinct"] == ws["n_distinct"], what
+                    if tier == "fast":      # (with few bins the one-bin sample may misjudge the distinct share: a few slow mid bins are fine)
+                        assert st["n_mid_bins"] > 0 and st["n_fallbacks"] == 0 and st["n_slow_bins"] <= (0 if B == 2048 else st["n_mid_bins"] // 4), what
+                    if tier == "slow":
+                        assert st["n_fallbacks"] == 0 and st["n_mid_bins"] > 0, what
+                        if B >= 64 and k >= 22:
+                            assert st["n_slow_bins"] > 0, what
+                    if tier == "events":
+                        assert st["n_fallbacks"] >= 1 and st["n_mid_bins"] == 0, what
+    finally:
+        c2.close()
+
+
+def test_smem_path_edge_cases(oracle):
+    """The reference's input edge cases (empty, short, all-N, lowercase, CRLF, homopolymers and short-period repeats far longer than
+    a record, k = m, k = 64, B = 1, B > 4096) through the shared-memory tables."""
+    rng = random.Random(11)
+    unit = "".join(rng.choice("ACGT") for _ in range(37))
+    seq = "A" * 5000 + unit * 300 + "C" * 3000 + "AC" * 2000 + "".join(rng.choice("ACGT") for _ in range(20000))
+    long_text = (">g\n" + "\n".join(seq[i:i + 70] for i in range(0, len(seq), 70)) + "\n").encode()
+    texts = [b"", b">empty\n", b">short\nACGT\n", b">allN\n" + b"N" * 500 + b"\n", b">lower\n" + b"acgt" * 50 + b"\n",
+             b">one\n" + b"ACGTTGCATGCAGGCTTAACCGGTAAGC" + b"\n", b">crlf\r\n" + b"ACGGTCAGGT" * 9 + b"\r\n" + b"ACGGTCAGGT" * 9 + b"\r\n", long_text]
+    for alphabet, width in (("ACGT", None), ("AC", 17), ("A", None)):
+        texts.append(_rand_fasta(rng, 40, 0, 250, alphabet=alphabet, width=width).encode())
+    c2 = fk.Context(0)
+    try:
+        c2.set("count_mode", 1)
+        for (k, m, B) in ((28, 10, 2048), (5, 3, 64), (31, 11, 4096), (32, 7, 333), (33, 8, 512), (55, 13, 2048), (64, 15, 5000), (15, 15, 3), (20, 5, 1), (7, 7, 1 << 20)):
+            for t in texts:
+                res, st = check(c2, oracle, t, k, m, 3, B, 1, "smem k=%d B=%d %r" % (k, B, t[:10]))
+                assert st["n_fallbacks"] == 0
+    finally:
+        c2.close()
+
+
+def test_smem_and_global_tables_agree_at_scale(ctx):
+    """2 M reads: the shared-memory tables and the global tables give the same digest, and the sum of counts is the number of windows."""
+    spec = dict(seeds=(41, 42, 43), genome_len=10_000_000, n_reads=2_000_000, read_len=150)
+    d_b, d_i, n_pos = ctx.synth_packed_device(spec)
+    try:
+        for k, m in ((28, 10), (55, 13)):
+            c = cfg(k, m, 3, 2048, 1)
+            ctx.set("count_mode", 1)
+            _, a = ctx.count_packed_device(c, d_b, d_i, n_pos, want_result=False)
+            ctx.set("count_mode", 0)
+            _, b = ctx.count_packed_device(c, d_b, d_i, n_pos, want_result=False)
+            ctx.set("count_mode", 1)
+            assert a["n_mid_bins"] > 0 and b["n_mid_bins"] == 0
+            for key in ("n_kmers", "n_distinct", "total_count", "digest_sum", "digest_xor"):
+                assert a[key] == b[key], (k, key)
+            assert a["total_count"] == a["n_kmers"] and a["n_fallbacks"] == 0
+    finally:
+        ctx.set("count_mode", 0)
+        ctx.free_device(d_b)
+        ctx.free_device(d_i)
+
+
 # ---------------------------------------------------------------- the drop-in call and its files
 def test_record_folding_gives_identical_counts(oracle):
     """fold_records=1 (hash path, k <= 32): identical super-k-mer records, either strand, are folded into one
@@ -251,6 +335,7 @@ def test_record_folding_gives_identical_counts(oracle):
             "".join(rng.choice("ACGT") for _ in range(3000)) * 3 + "\n").encode()
     c2 = fk.Context(0)
     try:
+        c2.set("count_mode", 0)                               # folding belongs to the global-table pipeline
         c2.set("fold_records", 1)
         for text, label in ((deep, "deep"), (poly, "poly"), (flat, "flat")):
             for k, m, B in ((28, 10, 2048), (31, 11, 64), (12, 4, 100), (32, 7, 1)):
