@@ -85,15 +85,16 @@ class Workload:
         api._check(api.load_library().fkm_synth_long_fasta_host(api.C.byref(s), None, 0, api.C.byref(n)))
         return fk.synth_long_fasta(sp, out=api.host_alloc(n.value))
 
-    def cpu_sample(self, fk):
-        """bounded sample of the same workload for the CPU oracle -> (fasta uint8 array, description)"""
+    def cpu_sample(self, oracle, threads):
+        """bounded sample of the same workload for the CPU oracle -> (fasta uint8 array, description).  The text comes from the
+        oracle's own restatement of the generator: the CPU arm never loads the product library."""
         c = self.c
         if self.kind == "reads":
             reads = min(c["reads"], 5_000_000)            # ~10 s of work for 16 host threads
             sp = dict(seeds=c["seeds"], genome_len=reads * c["L"] // c["cov"], n_reads=reads, read_len=c["L"])
-            return fk.synth_fasta(sp), "%d reads x %d bp of the same generator" % (reads, c["L"])
+            return oracle.synth_fasta(sp, threads=threads), "%d reads x %d bp of the same generator" % (reads, c["L"])
         n = min(c["n_bases"], 100_000_000)
-        return fk.synth_long_fasta(dict(seeds=c["seeds"], n_bases=n)), "first %d bp of the same synthetic genome" % n
+        return oracle.synth_long_fasta(dict(seeds=c["seeds"], n_bases=n), threads=threads), "first %d bp of the same synthetic genome" % n
 
 
 def measured_peaks():
@@ -149,9 +150,8 @@ def run_cpu_oracle(threads, wl):
     """Times the CPU oracle (port of the reference algorithm) on a bounded sample of the workload.  -> dict"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib
-    import fastkmer_b200 as fk
     oracle = oracle_lib.load()
-    fasta, desc = wl.cpu_sample(fk)                   # host generator of the product lib: data only, no counting
+    fasta, desc = wl.cpu_sample(oracle, threads)
     c = wl.c
     t0 = time.perf_counter()
     res = oracle.count(fasta, c["k"], c["m"], c["x"], c["B"], c["ht"], threads=threads, sorted_=False)
@@ -278,6 +278,37 @@ def main():
     n_distinct_total = st["n_distinct_global"] if "n_distinct_global" in st else st["n_distinct"]
     value = n_bases_total / (ms_step * 1e-3)
 
+    # ---------------- parity of this very path (same ranks, same exchange) against the CPU oracle on a bounded set ----------------
+    parity = None
+    if not args.no_cpu:
+        small = 100_000 if wl.kind == "reads" else 3_000_000
+        c = wl.c
+        if wl.kind == "reads":
+            sp_all = dict(seeds=c["seeds"], genome_len=max(2 * c["L"], small * world * c["L"] // c["cov"]), n_reads=small * world, read_len=c["L"])
+            sp_me = dict(sp_all, n_reads=small, first_read=rank * small)
+            sb, si, sn = ctx.synth_packed_device(sp_me)
+        else:
+            per = small // world
+            first = rank * per
+            n = (per if rank < world - 1 else small - first) + (c["k"] - 1 if rank < world - 1 else 0)
+            sp_all = dict(seeds=c["seeds"], n_bases=small)
+            sb, si, sn = ctx.synth_long_packed_device(dict(seeds=c["seeds"], first_pos=first, n_bases=n))
+        sst = ctx.count_packed_device(cfg, sb, si, sn, want_result=False)[1] if job is None else job.count_packed_device(sb, si, sn)
+        ctx.free_device(sb)
+        ctx.free_device(si)
+        if rank == 0:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_lib
+            oracle = oracle_lib.load()
+            text = oracle.synth_fasta(sp_all) if wl.kind == "reads" else oracle.synth_long_fasta(sp_all)
+            ws = oracle.count(text, c["k"], c["m"], c["x"], c["B"], c["ht"], threads=os.cpu_count() or 1, sorted_=False)["stats"]
+            g = (lambda key: sst[key + "_global"] if key + "_global" in sst else sst[key])
+            got = (g("n_kmers"), g("n_distinct"), g("digest_sum"), g("digest_xor"))
+            want = (ws["n_kmers"], ws["n_distinct"], ws["digest_sum"], ws["digest_xor"])
+            assert got == want, "GPU result differs from the CPU oracle on the bounded set: %r vs %r" % (got, want)
+            parity = {"oracle_checked": True, "what": "%s, all %d rank(s), digest of every (bin, k-mer, count)" %
+                      ("%d reads" % (small * world) if wl.kind == "reads" else "%d bp" % small, world), "n_kmers": int(ws["n_kmers"])}
+
     # ---------------- end to end from host FASTA ----------------
     e2e = None
     if not args.no_e2e:
@@ -329,24 +360,27 @@ def main():
     # dominant kernel: the count stage (stage 3; k_count_ht for useHT=1, k_expand + radix passes for useHT=0).  It reads
     # the super-k-mer stream once (L_s/4 algorithmic bytes); the distinct (k-mer,count) pairs leave through stage 4.
     n_count_launches = max(1, int(st["n_batches"]))
-    count_bytes = (L_s / 4) / world
-    count_ms = stage[3] + ms_fold                   # folding identical records (when on) is part of the count stage
-    traffic = None
-    try:                                              # measured DRAM bytes per record of k_count_ht (one ncu --set full capture)
-        if st["n_folded_records"]:                    # the kernel reads folded (weighted) records: its own capture
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1f_count_ht_traffic.json")))
+    smem_path = bool(st["n_mid_bins"])
+    # dominant kernel = the count stage's own kernel (stage 3), timed with CUDA events inside the library.  k_count_ht reads the
+    # super-k-mer stream once (L_s/4); k_count_smem (shared-memory tables) also writes the result (D*(W+4)): it has no compaction kernel
+    count_bytes = (L_s / 4 + (n_distinct_total * (key_bytes + 4) if smem_path else 0)) / world
+    count_ms = stage[3]
+    kernel = "k_count_smem" if smem_path else ("k_count_ht" if wl.c["ht"] else "k_expand+k_radix_*")
+    traffic, traffic_src = None, None
+    try:                                              # DRAM bytes per launch from an ncu --set full capture of the same kernel (profiles/)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_count_smem_traffic.json" if smem_path else "r1f_count_ht_traffic.json")))
+        if smem_path and wl.c["k"] <= 32:
+            traffic = tj["dram_bytes_per_kmer"] * (n_kmers_total / world / n_count_launches)
+            traffic_src = "static: ncu capture profiles/%s scaled by k-mers per launch" % tj.get("file", "r2_count_smem_traffic.json")
+        elif wl.c["ht"] and wl.c["k"] <= 32 and st["n_folded_records"]:
             traffic = tj["dram_bytes_per_record"] * (st["n_folded_records"] / n_count_launches)
-        else:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1d_count_ht_traffic.json")))
-            traffic = tj["dram_bytes_per_record"] * (st["n_superkmers"] / n_count_launches)
+            traffic_src = "static: ncu capture profiles/r1f_count_ht_traffic.json (round 1) scaled by folded records per launch"
     except Exception:
         pass
-    if not wl.c["ht"] or wl.c["k"] > 32:
-        traffic = None                                # the ncu capture is of the 64-bit hash-table kernel
-    roofline = {"bound": "hbm", "kernel": "k_count_ht" if wl.c["ht"] else "k_expand+k_radix_*", "achieved": count_bytes / (count_ms * 1e-3) / 1e9 if count_ms else None,
+    roofline = {"bound": "hbm", "kernel": kernel, "achieved": count_bytes / (count_ms * 1e-3) / 1e9 if count_ms else None,
                 "peak": peak, "unit": "GB/s", "frac": (count_bytes / (count_ms * 1e-3) / 1e9 / peak) if count_ms else None,
-                "traffic": traffic, "algorithmic_bytes_per_launch": count_bytes / n_count_launches, "peak_source": peak_src, "launches_per_step": n_count_launches,
-                "avg_launch_ms": count_ms / n_count_launches,
+                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": count_bytes / n_count_launches, "peak_source": peak_src,
+                "launches_per_step": n_count_launches, "avg_launch_ms": count_ms / n_count_launches,
                 "pipeline": {"bytes_alg": bytes_alg, "achieved": bytes_alg / (ms_step * 1e-3) / 1e9 / world,
                              "frac": bytes_alg / (ms_step * 1e-3) / 1e9 / world / peak}}
     shuffle = None
@@ -363,11 +397,12 @@ def main():
                        "reads_per_gpu": wl.c.get("reads"), "n_bases": n_bases_total,
                        "n_kmers": int(n_kmers_total), "n_distinct": int(n_distinct_total),
                        "n_superkmers": int(st["n_superkmers"]), "n_folded_records": int(st["n_folded_records"]),
+                       "count_tables": "shared memory (%d mid bins, %d on the slow path)" % (st["n_mid_bins"], st["n_slow_bins"]) if smem_path else "global memory",
                        "l2": "inputs (%.1f GB packed) larger than L2, no flush" % (n_pos * 3 / 8 / 1e9)},
             "stage_ms": {"histogram": stage[1], "scatter": stage[2], "fold": ms_fold, "count": stage[3], "compact": stage[4], "digest": stage[5],
                          "device_pipeline": stage[7]},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "shuffle": shuffle}
+            "shuffle": shuffle, "parity": parity}
     print(json.dumps(line))
     ctx.close()
     if dist is not None:

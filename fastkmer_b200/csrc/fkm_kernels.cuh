@@ -637,8 +637,8 @@ __global__ void __launch_bounds__(256) k_count_ht(const CountParams P) {
                 if constexpr (!WIDE) cp = &(reinterpret_cast<SlotN*>(tbl) + slot)->cnt;
                 else cp = &(reinterpret_cast<SlotW*>(tbl) + slot)->cnt;
                 if (state == 1 && is_empty) { claims++; if (kw > 1u) atomicAdd(cp, kw - 1u); state = 2; }   // claimed: count 0 == seen once, no RED
+                else if (state == 0 && maybe_empty) state = 1;               // (before any comparison: a torn view of a slot being claimed must not match)
                 else if (key_eq(got, key)) { atomicAdd(cp, kw); state = 2; }
-                else if (state == 0 && maybe_empty) state = 1;
                 else { if (++slot == size) slot = 0; state = first_state; }
             }
             if (round > (int)T + 2 * P.max_probe) { ovf = true; break; }            // warp-uniform bound on the rounds

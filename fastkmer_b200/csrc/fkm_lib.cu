@@ -1036,9 +1036,13 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
     cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); st->ms_stage[5] = ms;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4]); st->ms_stage[7] = ms;      // whole device pipeline
     cleanup();
-    if (st->total_count != st->n_kmers)
+    if (st->total_count != st->n_kmers) {
+        // counts are 32-bit (the reference counts in Int, SBKC:562,676): every wrap takes exactly 2^32 off the sum of counts
+        if (st->total_count < st->n_kmers && ((st->n_kmers - st->total_count) & 0xFFFFFFFFull) == 0)
+            return fkm_set_error(FKM_EOVERFLOW, "a k-mer occurs more than 2^32-1 times: 32-bit counts overflow (the reference counts in Int, SBKC:562,676)");
         return fkm_set_error(FKM_ECUDA, "internal check failed: sum of counts %llu != valid k-windows %llu",
                              (unsigned long long)st->total_count, (unsigned long long)st->n_kmers);
+    }
     return FKM_OK;
 #undef CKC
 #undef CKLC
@@ -1525,6 +1529,8 @@ extern "C" int fkm_mg_scan_fasta(fkm_ctx* ctx, const fkm_config* cfg, const uint
 
 extern "C" int fkm_mg_scatter(fkm_ctx* ctx, const uint64_t* bin_base, void* d_send) {
     if (!ctx || !bin_base || !ctx->mg_scan || !ctx->mg_scan->valid) return fkm_set_error(FKM_EINVAL, "fkm_mg_scatter needs a preceding fkm_mg_scan");
+    if (ctx->mg_scan->gen != ctx->gen)       // another job ran on this context since fkm_mg_scan: its arena (events, histograms, packed chunks) is gone
+        return fkm_set_error(FKM_EINVAL, "fkm_mg_scatter: the scan was invalidated by a later job on the same context (run fkm_mg_scan again)");
     CK(cudaSetDevice(ctx->device));
     ScanState* S = ctx->mg_scan;
     const size_t bB = (size_t)S->B * 8;
@@ -1541,6 +1547,8 @@ extern "C" int fkm_mg_scatter(fkm_ctx* ctx, const uint64_t* bin_base, void* d_se
 extern "C" int fkm_mg_regroup(fkm_ctx* ctx, const fkm_config* cfg, const void* d_recv, uint64_t n_records,
                               const uint64_t* seg_src, const uint64_t* seg_dst, uint64_t n_seg, void** d_out) {
     if (!ctx || !cfg || !d_out) return fkm_set_error(FKM_EINVAL, "null argument");
+    if (!ctx->mg_scan || ctx->mg_scan->gen != ctx->gen)
+        return fkm_set_error(FKM_EINVAL, "fkm_mg_regroup belongs to the job that fkm_mg_scan started; a later job on the context invalidated it");
     CK(cudaSetDevice(ctx->device));
     const int rb = fkm_record_bytes(cfg);
     unsigned long long *d_src = nullptr, *d_dst = nullptr; void* out = nullptr;
@@ -1560,6 +1568,8 @@ extern "C" int fkm_mg_regroup(fkm_ctx* ctx, const fkm_config* cfg, const void* d
 extern "C" int fkm_mg_count(fkm_ctx* ctx, const fkm_config* cfg, const void* d_records, const uint64_t* bin_rec, const uint64_t* bin_kmer,
                             fkm_result** out, fkm_stats* stats) {
     if (!ctx || !bin_rec || !bin_kmer) return fkm_set_error(FKM_EINVAL, "null argument");
+    if (!ctx->mg_scan || ctx->mg_scan->gen != ctx->gen)
+        return fkm_set_error(FKM_EINVAL, "fkm_mg_count belongs to the job that fkm_mg_scan started; a later job on the context invalidated it");
     if (stats) { stats->h2d_bytes = 0; stats->n_bases = 0; stats->ms_stage[0] = 0; }
     PreScattered pre{d_records, bin_rec, bin_kmer};
     return count_device(ctx, cfg, nullptr, nullptr, 0, out, stats, &pre);
@@ -1643,6 +1653,12 @@ extern "C" int fkm_multiseq_fasta(fkm_ctx* ctx, const fkm_config* cfg, const uin
         r->eof_trailer = false;
         total.n_nonempty_bins = st.n_nonempty_bins; total.digest_sum = st.digest_sum; total.digest_xor = st.digest_xor;
         total.gpu_launches += st.gpu_launches; total.ms_total += st.ms_total;
+        if (cfg->write) {                                   // the reference writes the merged counts per bin (MSKC:487,524), without a trailer
+            char dir[4096];
+            rc = fkm_derive(cfg, nullptr, dir, sizeof dir);
+            if (!rc) rc = fkm_result_write(r, dir);
+            if (rc) { fkm_result_free(r); return rc; }
+        }
         if (merged) *merged = r; else fkm_result_free(r);
     }
     if (stats) *stats = total;

@@ -21,58 +21,54 @@ import numpy as np
 
 def assign_owners(bin_kmers, world):
     """LPT (longest processing time first): bins by decreasing total k-mers, each to the least-loaded GPU.
-    Deterministic (ties by bin id), so every rank computes the same map."""
+    Deterministic (ties by bin id, then by rank), so every rank computes the same map."""
+    import heapq
     bin_kmers = np.asarray(bin_kmers, dtype=np.uint64)
     order = np.lexsort((np.arange(bin_kmers.size), -bin_kmers.astype(np.int64)))
-    load = [0] * world
+    heap = [(0, r) for r in range(world)]
     owner = np.zeros(bin_kmers.size, dtype=np.int32)
-    for b in order:
-        g = min(range(world), key=lambda r: (load[r], r))
+    for b, w in zip(order.tolist(), bin_kmers[order].tolist()):
+        load, g = heapq.heappop(heap)
         owner[b] = g
-        load[g] += int(bin_kmers[b])
+        heapq.heappush(heap, (load + w, g))
     return owner
 
 
 def plan_exchange(H_rec, H_kmer, rank, world, owner=None):
     """H_rec, H_kmer: [world, B] records / k-mers every rank puts into every bin.  owner: a fixed bin -> GPU map
     (jobs that must agree on the ownership, e.g. the samples of a distance job); default LPT on this job's histogram.
-    -> dict with everything rank `rank` needs for steps 4-7."""
+    -> dict with everything rank `rank` needs for steps 4-7.  Array arithmetic only (no loop over bins x ranks)."""
     H_rec = np.asarray(H_rec, dtype=np.uint64)
     H_kmer = np.asarray(H_kmer, dtype=np.uint64)
     B = H_rec.shape[1]
     owner = assign_owners(H_kmer.sum(axis=0), world) if owner is None else np.asarray(owner, dtype=np.int32)
     # send buffer: bins ordered by (owner, bin)
     order = np.lexsort((np.arange(B), owner))
-    send_base = np.zeros(B + 1, dtype=np.uint64)
     mine = H_rec[rank]
-    off = 0
-    for b in order:
-        send_base[b] = off
-        off += int(mine[b])
-    send_base[B] = off
-    send_splits = [int(mine[owner == g].sum()) for g in range(world)]
+    csum = np.cumsum(mine[order], dtype=np.uint64)
+    send_base = np.zeros(B + 1, dtype=np.uint64)
+    send_base[order] = csum - mine[order]
+    send_base[B] = csum[-1] if B else 0
+    send_splits = [int(mine[owner == g].sum(dtype=np.uint64)) for g in range(world)]
     my_bins = np.nonzero(owner == rank)[0]
-    recv_splits = [int(H_rec[s][my_bins].sum()) for s in range(world)]
+    M = H_rec[:, my_bins]                                      # [source, my bin] records this rank receives
+    recv_splits = [int(v) for v in M.sum(axis=1, dtype=np.uint64)]
     # bin-major layout of the bins this rank owns
     bin_rec = np.zeros(B, dtype=np.uint64)
     bin_kmer = np.zeros(B, dtype=np.uint64)
-    bin_rec[my_bins] = H_rec[:, my_bins].sum(axis=0)
-    bin_kmer[my_bins] = H_kmer[:, my_bins].sum(axis=0)
+    bin_rec[my_bins] = M.sum(axis=0, dtype=np.uint64)
+    bin_kmer[my_bins] = H_kmer[:, my_bins].sum(axis=0, dtype=np.uint64)
     dst_base = np.zeros(B + 1, dtype=np.uint64)
-    dst_base[1:] = np.cumsum(bin_rec)
-    # receive buffer is source-major, each source's block holds this rank's bins in bin order
-    seg_src, seg_dst = [0], []
-    filled = {int(b): 0 for b in my_bins}
-    for s in range(world):
-        for b in my_bins:
-            n = int(H_rec[s][b])
-            if n == 0:
-                continue
-            seg_dst.append(int(dst_base[b]) + filled[int(b)])
-            filled[int(b)] += n
-            seg_src.append(seg_src[-1] + n)
+    dst_base[1:] = np.cumsum(bin_rec, dtype=np.uint64)
+    # receive buffer is source-major, each source's block holds this rank's bins in bin order: segment (s, b) moves to
+    # the bin's place + what the sources before s put into the bin
+    flat = M.ravel()
+    keep = flat > 0
+    before = np.cumsum(M, axis=0, dtype=np.uint64) - M
+    seg_dst = (dst_base[my_bins][None, :] + before).ravel()[keep]
+    seg_src = np.concatenate([np.zeros(1, dtype=np.uint64), np.cumsum(flat[keep], dtype=np.uint64)])
     return dict(owner=owner, send_base=send_base, send_splits=send_splits, recv_splits=recv_splits, bin_rec=bin_rec,
-                bin_kmer=bin_kmer, seg_src=np.asarray(seg_src, dtype=np.uint64), seg_dst=np.asarray(seg_dst, dtype=np.uint64),
+                bin_kmer=bin_kmer, seg_src=seg_src.astype(np.uint64), seg_dst=seg_dst.astype(np.uint64),
                 n_send=int(send_base[B]), n_recv=int(sum(recv_splits)))
 
 

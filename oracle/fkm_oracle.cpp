@@ -545,6 +545,91 @@ void fkmo_result_stats(void* r, uint64_t* s) {
 }
 void fkmo_result_free(void* r) { delete (Result*)r; }
 
+// ---- the synthetic inputs of SURVEY §8(d) (counter-based splitmix64), restated here so that the CPU baseline of bench.py
+// builds its input without loading the product library.  Must produce the text of fkm_synth_fasta_host /
+// fkm_synth_long_fasta_host byte for byte (tests/test_oracle_kat.py::test_oracle_generators_match_the_library).
+static inline uint64_t sm64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+// reads first_read .. first_read + R - 1 as '>r<global index>\n<L bases>\n'; returns the bytes (out == NULL sizes)
+uint64_t fkmo_synth_fasta(uint64_t seedG, uint64_t seedR, uint64_t seedE, uint64_t G, uint64_t R, uint64_t L, uint64_t first_read,
+                          uint8_t* out, uint64_t cap, int32_t threads) {
+    // bytes of the reads with global index in [g0, g1): '>r' + decimal index + '\n' + L bases + '\n'
+    auto bytes_of = [&](uint64_t g0, uint64_t g1) {
+        uint64_t total = 0, lo_d = 0, hi_d = 10;
+        for (uint64_t d = 1; d <= 20; d++) {
+            const uint64_t a = std::max(g0, lo_d), e = (d == 20) ? g1 : std::min(g1, hi_d);
+            if (e > a) total += (e - a) * (d + L + 4);
+            lo_d = hi_d; hi_d = (d < 19) ? hi_d * 10 : ~0ull;
+        }
+        return total;
+    };
+    const unsigned nt = (unsigned)std::max<int32_t>(1, std::min<int32_t>(threads, 256));
+    std::vector<uint64_t> lo(nt + 1), start(nt + 1, 0);
+    for (unsigned t = 0; t <= nt; t++) lo[t] = R * t / nt;
+    for (unsigned t = 0; t < nt; t++) start[t + 1] = start[t] + bytes_of(first_read + lo[t], first_read + lo[t + 1]);
+    if (!out) return start[nt];
+    if (cap < start[nt]) return 0;
+    auto work = [&](unsigned t) {
+        uint8_t* p = out + start[t];
+        char num[32];
+        for (uint64_t r = lo[t]; r < lo[t + 1]; r++) {
+            const uint64_t g = first_read + r;
+            const int n = snprintf(num, sizeof num, ">r%llu\n", (unsigned long long)g);
+            memcpy(p, num, (size_t)n); p += n;
+            const uint64_t pos = sm64(seedR + 2 * g) % (G - L + 1), strand = sm64(seedR + 2 * g + 1) & 1ull;
+            for (uint64_t j = 0; j < L; j++) {
+                const uint64_t gi = strand ? pos + (L - 1 - j) : pos + j;
+                uint32_t b = (uint32_t)(sm64(seedG + gi) >> 62);
+                if (strand) b = 3u - b;
+                const uint64_t e = sm64(seedE + g * L + j);
+                if (e % 1000ull == 0ull) { *p++ = 'N'; continue; }
+                if (e % 100ull == 1ull) b = (b + 1u + (uint32_t)((e >> 32) % 3ull)) & 3u;
+                *p++ = (uint8_t)"ACGT"[b];
+            }
+            *p++ = '\n';
+        }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& q : th) q.join();
+    return start[nt];
+}
+// one long record (BASELINE config 3): '>chr1 synthetic\n' + 70-column lines of bases [first_pos, first_pos + n)
+uint64_t fkmo_synth_long_fasta(uint64_t seedG, uint64_t seedRep, uint64_t seedN, uint64_t first_pos, uint64_t n, uint8_t* out, uint64_t cap, int32_t threads) {
+    const char* hdr = ">chr1 synthetic\n";
+    const uint64_t hl = strlen(hdr), W = 70, lines = (n + W - 1) / W, total = hl + n + lines;
+    if (!out) return total;
+    if (cap < total) return 0;
+    memcpy(out, hdr, hl);
+    const unsigned nt = (unsigned)std::max<int32_t>(1, std::min<int32_t>(threads, 256));
+    auto work = [&](unsigned t) {
+        for (uint64_t ln = lines * t / nt; ln < lines * (t + 1) / nt; ln++) {
+            uint8_t* p = out + hl + ln * (W + 1);
+            const uint64_t a = ln * W, e = std::min(n, a + W);
+            for (uint64_t q = a; q < e; q++) {
+                const uint64_t i = first_pos + q;
+                if (sm64(seedN + i / 1000ull) % 200ull == 0ull) { *p++ = 'N'; continue; }
+                const uint64_t r = sm64(seedRep + i / 5000ull);
+                uint32_t b;
+                if (r % 20ull == 0ull) { const uint64_t t5 = (r >> 20) % 1000ull; b = (uint32_t)(sm64(seedG ^ 0x5bd1e995ull ^ (t5 * 5000ull + i % 5000ull) * 0x9E3779B97F4A7C15ull) >> 62); }
+                else b = (uint32_t)(sm64(seedG + i) >> 62);
+                *p++ = (uint8_t)"ACGT"[b];
+            }
+            *p = '\n';
+        }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto& q : th) q.join();
+    return total;
+}
+
 // SURVEY App. C.4 sequential-LCG read set as FASTA text ('>r<i>\n<seq>\n').
 // Returns bytes written (call with out==NULL to size).
 uint64_t fkmo_gen_lcg_fasta(uint64_t seed, uint64_t G, uint64_t R, uint64_t L, uint8_t* out, uint64_t cap) {

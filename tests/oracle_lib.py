@@ -48,6 +48,10 @@ class Oracle:
         lib.fkmo_result_free.argtypes = [C.c_void_p]
         lib.fkmo_gen_lcg_fasta.restype = C.c_uint64
         lib.fkmo_gen_lcg_fasta.argtypes = [C.c_uint64] * 4 + [C.c_void_p, C.c_uint64]
+        lib.fkmo_synth_fasta.restype = C.c_uint64
+        lib.fkmo_synth_fasta.argtypes = [C.c_uint64] * 7 + [C.c_void_p, C.c_uint64, C.c_int32]
+        lib.fkmo_synth_long_fasta.restype = C.c_uint64
+        lib.fkmo_synth_long_fasta.argtypes = [C.c_uint64] * 5 + [C.c_void_p, C.c_uint64, C.c_int32]
 
     def hash_to_bucket(self, s, B):
         return self.lib.fkmo_hash_to_bucket(s, B)
@@ -80,6 +84,21 @@ class Oracle:
         buf = np.empty(n, dtype=np.uint8)
         self.lib.fkmo_gen_lcg_fasta(seed, G, R, L, buf.ctypes.data, n)
         return buf.tobytes()
+
+    def synth_fasta(self, spec, threads=8) -> np.ndarray:
+        """SURVEY §8(d) synthetic reads as FASTA text; spec as for fastkmer_b200.synth_fasta (the oracle's own generator)."""
+        a = list(spec["seeds"]) + [spec["genome_len"], spec["n_reads"], spec["read_len"], spec.get("first_read", 0)]
+        n = self.lib.fkmo_synth_fasta(*a, None, 0, threads)
+        buf = np.empty(n, dtype=np.uint8)
+        assert self.lib.fkmo_synth_fasta(*a, buf.ctypes.data, n, threads) == n
+        return buf
+
+    def synth_long_fasta(self, spec, threads=8) -> np.ndarray:
+        a = list(spec["seeds"]) + [spec.get("first_pos", 0), spec["n_bases"]]
+        n = self.lib.fkmo_synth_long_fasta(*a, None, 0, threads)
+        buf = np.empty(n, dtype=np.uint8)
+        assert self.lib.fkmo_synth_long_fasta(*a, buf.ctypes.data, n, threads) == n
+        return buf
 
     def count(self, fasta, k, m, x, max_b, use_ht, threads=4, sorted_=True):
         """-> dict(bin, hi, lo, cnt numpy arrays sorted by (bin, key); stats dict)."""

@@ -301,6 +301,31 @@ def test_smem_path_edge_cases(oracle):
         c2.close()
 
 
+def test_count_overflow_is_reported():
+    """Counts are 32-bit like the reference's (Int: SBKC:562,676).  One k-mer seen more than 2^32 - 1 times (a homopolymer of
+    4.3 G bases) must end in FKM_EOVERFLOW on every count path, never in a wrapped count."""
+    from fastkmer_b200 import api
+    n_pos = (1 << 32) + 5000
+    nw = (n_pos + 31) // 32
+    bases = np.zeros(nw, dtype=np.uint64)                       # all 'A'
+    inv = np.zeros(nw, dtype=np.uint32)
+    c2 = fk.Context(0)
+    try:
+        for ht, mode in ((1, 0), (1, 1), (0, 0)):
+            c2.set("count_mode", mode)
+            with pytest.raises(api.FkmError) as e:
+                c2.count_packed_host(cfg(28, 10, 3, 2048, ht), bases, inv, n_pos, want_result=False)
+            assert e.value.code == api.FKM_EOVERFLOW, (ht, mode, str(e.value))
+        # just below the limit the count is exact
+        n_ok = (1 << 32) - 1 + 27
+        c2.set("count_mode", 0)
+        res, st = c2.count_packed_host(cfg(28, 10, 3, 2048, 1), bases, inv, n_ok)
+        a = res.arrays()
+        assert a["cnt"].tolist() == [0xFFFFFFFF] and a["lo"].tolist() == [0] and st["n_kmers"] == 0xFFFFFFFF
+    finally:
+        c2.close()
+
+
 def test_smem_and_global_tables_agree_at_scale(ctx):
     """2 M reads: the shared-memory tables and the global tables give the same digest, and the sum of counts is the number of windows."""
     spec = dict(seeds=(41, 42, 43), genome_len=10_000_000, n_reads=2_000_000, read_len=150)
@@ -648,3 +673,22 @@ def test_result_clone_survives_later_jobs_and_dot(ctx, oracle):
     assert ca.dot(ca) == sum(n * n for n in da.values())
     ca.free()
     cb.free()
+
+
+# ---------------------------------------------------------------- N ranks under torchrun / NCCL against the oracle
+def test_multigpu_ranks_match_oracle_under_torchrun():
+    """scripts/mg_check.py under `python -m torch.distributed.run` with every GPU of the box (at most 8): each rank counts its shard
+    through ShardedJob (NCCL all-to-all), rank 0 merges the per-rank results and compares them with the CPU oracle — short reads on
+    both count paths, 64- and 128-bit k-mers, and a halo-sharded long sequence.  With one GPU the same script runs as a single rank
+    (no exchange partner, same code path)."""
+    import sys
+    import torch
+    n = min(8, torch.cuda.device_count())
+    world = 1 if n < 2 else (8 if n >= 8 else 4 if n >= 4 else 2)
+    port = 29500 + (os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "scripts", "mg_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("mg_check")]
+    assert len(lines) == 6 and all(ln.split(":")[1].strip().startswith("OK") for ln in lines), r.stdout[-3000:]

@@ -41,6 +41,41 @@ def test_plan_is_consistent_across_ranks():
         assert sum(int(p["bin_kmer"].sum()) for p in plans) == Hk.sum()
 
 
+def test_plan_matches_straightforward_loops():
+    """plan_exchange is array arithmetic; the same plan written as loops over ranks and bins must give identical arrays."""
+    rng = np.random.default_rng(5)
+    for world, B in ((1, 7), (2, 64), (4, 300), (8, 2048)):
+        H_rec = rng.integers(0, 50, size=(world, B)).astype(np.uint64) * (rng.random((world, B)) < 0.7)
+        H_kmer = H_rec * rng.integers(1, 9, size=(world, B)).astype(np.uint64)
+        for rank in range(world):
+            p = mg.plan_exchange(H_rec, H_kmer, rank, world)
+            owner = p["owner"]
+            order = sorted(range(B), key=lambda b: (owner[b], b))
+            off, send_base = 0, np.zeros(B + 1, dtype=np.uint64)
+            for b in order:
+                send_base[b] = off
+                off += int(H_rec[rank][b])
+            send_base[B] = off
+            my_bins = [b for b in range(B) if owner[b] == rank]
+            dst, acc = {}, 0
+            for b in range(B):
+                dst[b] = acc
+                acc += int(H_rec[:, b].sum()) if owner[b] == rank else 0
+            seg_src, seg_dst, filled = [0], [], {b: 0 for b in my_bins}
+            for s_ in range(world):
+                for b in my_bins:
+                    n = int(H_rec[s_][b])
+                    if n:
+                        seg_dst.append(dst[b] + filled[b])
+                        filled[b] += n
+                        seg_src.append(seg_src[-1] + n)
+            assert np.array_equal(p["send_base"], send_base)
+            assert p["seg_src"].tolist() == seg_src and p["seg_dst"].tolist() == seg_dst
+            assert p["send_splits"] == [int(H_rec[rank][owner == g].sum()) for g in range(world)]
+            assert p["recv_splits"] == [int(H_rec[s_][my_bins].sum()) for s_ in range(world)]
+            assert p["n_recv"] == acc and p["n_send"] == off
+
+
 def test_fixed_owner_map_is_respected():
     rng = np.random.default_rng(5)
     Hr = rng.integers(0, 40, (3, 50))

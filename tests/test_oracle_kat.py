@@ -120,3 +120,18 @@ def test_strand_symmetry_and_bins(oracle):                # sig(w) == sig(rc w):
 def test_rejects_x0_on_sort_path(oracle):                 # App. A.8(3)
     with pytest.raises(ValueError):
         oracle.count(b">a\nACGTACGTACGT\n", 5, 3, 0, 64, 0)
+
+
+def test_oracle_generators_match_the_library(oracle):
+    """bench.py's CPU baseline builds its input with the oracle's own restatement of the SURVEY §8(d) generators (so that it never loads
+    the product library); the text must equal the product's host generator byte for byte (which the GPU tests hold equal to the
+    device generator)."""
+    import numpy as np
+    import fastkmer_b200 as fk
+    for spec in (dict(seeds=(2001, 2002, 2003), genome_len=100000, n_reads=20011, read_len=150),
+                 dict(seeds=(7, 8, 9), genome_len=3000, n_reads=1234, read_len=100, first_read=99_999_000),
+                 dict(seeds=(1, 2, 3), genome_len=500, n_reads=5, read_len=40, first_read=7)):
+        for threads in (1, 8):
+            assert np.array_equal(oracle.synth_fasta(spec, threads=threads), fk.synth_fasta(spec))
+    for spec in (dict(seeds=(3001, 3002, 3003), n_bases=300_001), dict(seeds=(5, 6, 7), n_bases=12_345, first_pos=4_999_000)):
+        assert np.array_equal(oracle.synth_long_fasta(spec, threads=3), fk.synth_long_fasta(spec))
