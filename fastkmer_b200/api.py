@@ -27,7 +27,7 @@ class fkm_stats(C.Structure):
                                           "n_distinct", "total_count", "digest_sum", "digest_xor", "n_nonempty_bins",
                                           "h2d_bytes", "d2h_bytes", "gpu_launches", "n_batches", "n_fallbacks")] + \
                [("ms_total", C.c_double), ("ms_stage", C.c_double * 8), ("n_folded_records", C.c_uint64), ("ms_fold", C.c_double),
-                ("n_mid_bins", C.c_uint64), ("n_slow_bins", C.c_uint64)]
+                ("n_mid_bins", C.c_uint64), ("n_slow_bins", C.c_uint64), ("ms_partition", C.c_double)]
 
 
 class fkm_synth(C.Structure):

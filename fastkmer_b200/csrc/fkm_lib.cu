@@ -8,6 +8,7 @@
 // There is no CPU fallback: every entry point needs a CUDA device.
 #include "fkm_kernels.cuh"
 #include "fkm_smem.cuh"
+#include "fkm_part.cuh"
 #include "fkm_ingest.cuh"
 #include "fkm_host.h"
 #include "../../include/fastkmer_b200.h"
@@ -15,6 +16,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -103,6 +105,9 @@ struct fkm_ctx {
     double smem_table_slots = 0.0;    // test hook: slots of the shared-memory table (0 = as many as fit)
     double smem_slow_slots = 1048576.0;   // slots of every CTA's private global table (slow path of k_count_smem)
     double smem_fill = 0.6;           // share of the table's capacity the planner aims at
+    double part_fill = 0.45;          // partitioned count path (count_mode 2): distinct k-mers per sub-bucket as a share of the table's slots
+    double part_budget_keys = 1024.0 * 1048576.0;   // ... k-mers per batch of bins (the key buffer holds one batch)
+    std::vector<cudaEvent_t> evpool;  // ... per-batch timing events
     double async_table_bytes = 1024.0 * (1 << 20); // tables of one asynchronous batch; 0 disables the asynchronous phase (0.25-16 GB all within 8 %, profiles/r1_table_sweep.txt)
     uint64_t job_launches = 0;
     uint64_t gen = 0;                 // job generation: results of older jobs are invalid
@@ -165,6 +170,7 @@ extern "C" void fkm_ctx_destroy(fkm_ctx* c) {
     cudaSetDevice(c->device);
     for (auto& ev : c->ev) cudaEventDestroy(ev);
     for (auto& ev : c->evs) cudaEventDestroy(ev);
+    for (auto& ev : c->evpool) cudaEventDestroy(ev);
     for (auto& ev : c->copied) cudaEventDestroy(ev);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaStreamSynchronize(c->stream);
@@ -185,6 +191,8 @@ extern "C" int fkm_ctx_set(fkm_ctx* c, const char* name, double v) {
     else if (!strcmp(name, "smem_table_slots")) c->smem_table_slots = v;
     else if (!strcmp(name, "smem_slow_slots")) c->smem_slow_slots = v;
     else if (!strcmp(name, "smem_fill")) c->smem_fill = v;
+    else if (!strcmp(name, "part_fill")) c->part_fill = v;
+    else if (!strcmp(name, "part_budget_keys")) c->part_budget_keys = v;
     else if (!strcmp(name, "fold_records")) c->fold_records = v;
     else if (!strcmp(name, "fold_max_ratio")) c->fold_max_ratio = v;
     else if (!strcmp(name, "fold_pool")) c->fold_pool = v;
@@ -482,6 +490,204 @@ static int stage_scatter(fkm_ctx* ctx, ScanState* S, const unsigned long long* d
     return FKM_OK;
 }
 
+static constexpr int kRetryGlobal = 1;          // internal: the job must be redone by the global-table pipeline
+
+// ------------------------------------------------------------------ the partitioned count stage (fkm_part.cuh)
+// Hash path with the tables in shared memory: bin-major records -> canonical k-mers, hash-partitioned into sub-buckets of a
+// few thousand distinct k-mers (k_expand_hist / k_sub_scan / k_place_keys) -> k_count_keys.  Batches of bins whose k-mers
+// fit the key buffer; the first B/64 bins are a synchronous sample sized for all-distinct k-mers, the distinct / k-mer
+// ratio they show sizes the sub-buckets and the output regions of the rest, which is queued without a host sync.
+// Returns kRetryGlobal when the input does not fit the scheme (a table or region overflowed, a bin of 2^32 k-mers).
+template <bool WIDE>
+static int count_partitioned(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const void* d_records, const unsigned long long* d_bin_base,
+                             const std::vector<unsigned long long>& h_rec, const std::vector<unsigned long long>& h_kmer,
+                             fkm_result* res, fkm_stats* st, unsigned long long* d_acc, uint64_t* out_total_p, float* ms_part_p, float* ms_count_p) {
+    typedef typename Traits<WIDE>::Key Key;
+    cudaStream_t s = ctx->stream;
+    constexpr uint64_t TR = PartGeom<WIDE>::kTileRecs;
+    for (int b = 0; b < B; b++) if (h_kmer[(size_t)b] >= 0xFFFFFFF0ull) return kRetryGlobal;
+    // geometry of k_count_keys's table
+    uint32_t cap = WIDE ? 8192u : 16384u;
+    while (cap > 64u && (size_t)cap * (sizeof(Key) + 6) + 2048 > ctx->smem_optin) cap >>= 1;
+    if (ctx->smem_table_slots >= 64.0) while (cap > 64u && (double)cap > ctx->smem_table_slots) cap >>= 1;
+    const size_t kc_smem = (size_t)cap * (sizeof(Key) + 6);
+    const size_t sc_smem = (size_t)PartGeom<WIDE>::kBufKeys * (sizeof(Key) + 2);
+    CK(cudaFuncSetAttribute(k_count_keys<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kc_smem));
+    CK(cudaFuncSetAttribute(k_place_keys<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
+    static int occ_hist[2] = {0, 0}, occ_scat[2] = {0, 0};
+    if (!occ_hist[WIDE]) {
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_hist[WIDE], k_expand_hist<WIDE>, PartGeom<WIDE>::kThreads, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_scat[WIDE], k_place_keys<WIDE>, PartGeom<WIDE>::kThreads, sc_smem));
+        if (occ_hist[WIDE] < 1) occ_hist[WIDE] = 1;
+        if (occ_scat[WIDE] < 1) occ_scat[WIDE] = 1;
+    }
+    const double d_target = std::max(16.0, (double)cap * ctx->part_fill);             // distinct k-mers a sub-bucket is planned for
+    const uint64_t budget_keys = std::max<uint64_t>(1u << 16, (uint64_t)ctx->part_budget_keys);
+    const unsigned grid = (unsigned)ctx->n_sm;
+    const size_t bB = (size_t)B * 8;
+
+    struct Batch { int lo, hi; size_t o32, o64h, o64k; uint64_t n_tiles, n_sub, hist_elems, n_keys, region_cap; double rho; };
+    std::vector<Batch> batches;
+    std::vector<uint32_t> h32;                  // per batch: tile_first[nb+1] | sub_first[nb+1]
+    std::vector<unsigned long long> h64;        // per batch: hist_off[nb] | key_base[nb+1]
+    auto plan = [&](int lo0, int hi_end, double rho_plan, double rho_out, bool one_batch) {
+        for (int lo = lo0; lo < hi_end;) {
+            Batch bt; bt.lo = lo; bt.n_tiles = bt.n_sub = bt.hist_elems = bt.n_keys = 0; bt.rho = rho_out;
+            int hi = lo;
+            while (hi < hi_end && (one_batch || hi == lo || bt.n_keys + h_kmer[(size_t)hi] <= budget_keys)) { bt.n_keys += h_kmer[(size_t)hi]; hi++; }
+            bt.hi = hi;
+            const int nb = hi - lo;
+            bt.o32 = h32.size(); h32.resize(h32.size() + 2 * (size_t)(nb + 1));
+            bt.o64h = h64.size(); h64.resize(h64.size() + (size_t)nb); bt.o64k = h64.size(); h64.resize(h64.size() + (size_t)nb + 1);
+            uint32_t* tf = h32.data() + bt.o32; uint32_t* sf = tf + nb + 1;
+            unsigned long long* ho = h64.data() + bt.o64h; unsigned long long* kb = h64.data() + bt.o64k;
+            uint64_t keys = 0;
+            for (int b = lo; b < hi; b++) {
+                const uint64_t km = h_kmer[(size_t)b], nr = h_rec[(size_t)b];
+                const uint64_t tiles = km ? (nr + TR - 1) / TR : 0;
+                uint64_t subs = km ? (uint64_t)std::ceil((double)km * rho_plan / d_target) : 0;
+                subs = km ? std::min<uint64_t>(std::max<uint64_t>(subs, 1), kPartMaxSubs) : 0;
+                tf[b - lo] = (uint32_t)bt.n_tiles; sf[b - lo] = (uint32_t)bt.n_sub; ho[b - lo] = bt.hist_elems; kb[b - lo] = keys;
+                bt.n_tiles += tiles; bt.n_sub += subs; bt.hist_elems += tiles * subs; keys += km;
+            }
+            tf[nb] = (uint32_t)bt.n_tiles; sf[nb] = (uint32_t)bt.n_sub; kb[nb] = keys;
+            // every CTA counts an equal share of the k-mers (plus at most one sub-bucket) into its own output region
+            const uint64_t share = bt.n_keys / grid + 1;
+            bt.region_cap = std::min<uint64_t>(share, (uint64_t)((double)share * std::min(1.0, rho_out * 1.25 + 0.01))) + 65536 + 4 * (uint64_t)cap;
+            batches.push_back(bt);
+            lo = hi;
+            if (one_batch) break;
+        }
+    };
+
+    unsigned long long *d_counters = nullptr, *d_cta_total = nullptr, *d_bin_off = nullptr; uint32_t* d_bin_cta = nullptr; int* d_flags = nullptr;
+    void* d_slow_keys = nullptr; uint32_t* d_slow_cnt = nullptr;
+    const uint64_t slow_slots = std::max<uint64_t>(1024, (uint64_t)ctx->smem_slow_slots);
+    CK(dmalloc(ctx, &d_counters, 64)); CK(dmalloc(ctx, &d_flags, 16)); CK(dmalloc(ctx, &d_bin_cta, (size_t)B * 4)); CK(dmalloc(ctx, &d_bin_off, bB));
+    CK(dmalloc(ctx, &d_slow_keys, (size_t)grid * slow_slots * sizeof(Key))); CK(dmalloc(ctx, &d_slow_cnt, (size_t)grid * slow_slots * 4));
+    CK(cudaMemsetAsync(d_counters, 0, 64, s)); CK(cudaMemsetAsync(d_flags, 0, 16, s));
+
+    uint64_t out_total = 0, n_sub_total = 0;
+    float ms_part = 0, ms_count = 0;
+    std::vector<unsigned long long> h_cta_total, h_bin_off((size_t)B);
+    std::vector<uint32_t> h_bin_cta((size_t)B);
+    // queues batches [b0, b1) of `batches` and waits for them; fills res->chunks / res->out_base
+    auto run = [&](size_t b0, size_t b1) -> int {
+        if (b0 >= b1) return FKM_OK;
+        const size_t nbt = b1 - b0;
+        uint64_t max_keys = 1, max_hist = 1, max_sub = 1;
+        size_t lo32 = batches[b0].o32, lo64 = batches[b0].o64h;
+        for (size_t i = b0; i < b1; i++) { max_keys = std::max(max_keys, batches[i].n_keys); max_hist = std::max(max_hist, batches[i].hist_elems); max_sub = std::max(max_sub, batches[i].n_sub); }
+        uint32_t *d32 = nullptr, *d_hist = nullptr, *d_base = nullptr, *d_mid_bin = nullptr; unsigned long long *d64 = nullptr, *d_mid_key = nullptr; void* d_keys = nullptr;
+        CK(dmalloc(ctx, &d32, (h32.size() - lo32) * 4 + 16)); CK(dmalloc(ctx, &d64, (h64.size() - lo64) * 8 + 16));
+        CK(dmalloc(ctx, &d_hist, max_hist * 4)); CK(dmalloc(ctx, &d_base, max_hist * 4));
+        CK(dmalloc(ctx, &d_keys, max_keys * sizeof(Key) + 64)); CK(dmalloc(ctx, &d_mid_key, (max_sub + 1) * 8)); CK(dmalloc(ctx, &d_mid_bin, max_sub * 4));
+        void* d_keys_lin = nullptr; uint32_t *d_tile_off = nullptr, *d_tile_nk = nullptr, *d_kcur = nullptr;
+        uint64_t max_tiles = 1, max_nb = 1;
+        for (size_t i = b0; i < b1; i++) { max_tiles = std::max(max_tiles, batches[i].n_tiles); max_nb = std::max<uint64_t>(max_nb, (uint64_t)(batches[i].hi - batches[i].lo)); }
+        CK(dmalloc(ctx, &d_keys_lin, max_keys * sizeof(Key))); CK(dmalloc(ctx, &d_tile_off, max_tiles * 4)); CK(dmalloc(ctx, &d_tile_nk, max_tiles * 4));
+        CK(dmalloc(ctx, &d_kcur, max_nb * 4));
+        CK(dmalloc(ctx, &d_cta_total, nbt * grid * 8));
+        CK(cudaMemcpyAsync(d32, h32.data() + lo32, (h32.size() - lo32) * 4, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d64, h64.data() + lo64, (h64.size() - lo64) * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemsetAsync(d_cta_total, 0, nbt * grid * 8, s));
+        st->h2d_bytes += (h32.size() - lo32) * 4 + (h64.size() - lo64) * 8;
+        while (ctx->evpool.size() < 3 * nbt) { cudaEvent_t e; CK(cudaEventCreate(&e)); ctx->evpool.push_back(e); }
+        std::vector<void*> ok(nbt); std::vector<uint32_t*> oc(nbt);
+        for (size_t i = b0; i < b1; i++) {
+            const Batch& bt = batches[i];
+            const int nb = bt.hi - bt.lo;
+            CK(dmalloc(ctx, &ok[i - b0], (size_t)grid * bt.region_cap * sizeof(Key))); CK(dmalloc(ctx, &oc[i - b0], (size_t)grid * bt.region_cap * 4));
+            CK(cudaEventRecord(ctx->evpool[3 * (i - b0)], s));
+            if (bt.n_keys) {
+                PartParams P;
+                P.records = d_records; P.bin_rec_base = d_bin_base; P.bin_lo = bt.lo; P.bin_hi = bt.hi;
+                P.tile_first = d32 + (bt.o32 - lo32); P.sub_first = P.tile_first + nb + 1;
+                P.hist_off = d64 + (bt.o64h - lo64); P.key_base = d64 + (bt.o64k - lo64);
+                P.n_tiles = (uint32_t)bt.n_tiles; P.n_sub = (uint32_t)bt.n_sub; P.tile_hist = d_hist; P.tile_base = d_base; P.keys = d_keys;
+                P.mid_key_base = d_mid_key; P.mid_bin = d_mid_bin; P.k = cfg->k;
+                P.keys_lin = d_keys_lin; P.tile_key_off = d_tile_off; P.tile_nkeys = d_tile_nk; P.bin_key_cursor = d_kcur;
+                CK(cudaMemsetAsync(d_kcur, 0, (size_t)nb * 4, s));
+                const unsigned g1 = (unsigned)std::min<uint64_t>(bt.n_tiles, (uint64_t)ctx->n_sm * occ_hist[WIDE]);
+                const unsigned g3 = (unsigned)std::min<uint64_t>(bt.n_tiles, (uint64_t)ctx->n_sm * occ_scat[WIDE]);
+                k_expand_hist<WIDE><<<g1, PartGeom<WIDE>::kThreads, 0, s>>>(P); CKL();
+                k_sub_scan<<<(unsigned)nb, 256, 0, s>>>(P); CKL();
+                k_place_keys<WIDE><<<g3, PartGeom<WIDE>::kThreads, sc_smem, s>>>(P); CKL();
+                CK(cudaEventRecord(ctx->evpool[3 * (i - b0) + 1], s));
+                KeyCountParams Q;
+                Q.keys = d_keys; Q.mid_key_base = d_mid_key; Q.mid_bin = d_mid_bin; Q.sub_first = P.sub_first; Q.bin_lo = bt.lo; Q.n_sub = (uint32_t)bt.n_sub;
+                Q.out_keys = ok[i - b0]; Q.out_cnt = oc[i - b0]; Q.region_cap = bt.region_cap; Q.cta_total = d_cta_total + (i - b0) * grid;
+                Q.bin_cta = d_bin_cta; Q.bin_off = d_bin_off; Q.acc = d_acc; Q.cap_slots = cap; Q.max_fill = cap * 3 / 4;
+                Q.slow_keys = d_slow_keys; Q.slow_cnt = d_slow_cnt; Q.slow_slots = slow_slots; Q.slow_max_fill = slow_slots * 7 / 10; Q.flags = d_flags; Q.counters = d_counters;
+                k_count_keys<WIDE><<<grid, kKcThreads, kc_smem, s>>>(Q); CKL();
+            } else CK(cudaEventRecord(ctx->evpool[3 * (i - b0) + 1], s));
+            CK(cudaEventRecord(ctx->evpool[3 * (i - b0) + 2], s));
+        }
+        int flags[4] = {0, 0, 0, 0};
+        h_cta_total.resize(nbt * grid);
+        const int lo = batches[b0].lo, hi = batches[b1 - 1].hi;
+        CK(cudaMemcpyAsync(h_cta_total.data(), d_cta_total, nbt * grid * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h_bin_cta.data() + lo, d_bin_cta + lo, (size_t)(hi - lo) * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h_bin_off.data() + lo, d_bin_off + lo, (size_t)(hi - lo) * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(flags, d_flags, 16, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        st->d2h_bytes += 16 + nbt * grid * 8 + (size_t)(hi - lo) * 12;
+        for (size_t i = 0; i < nbt; i++) {
+            float a = 0, c = 0;
+            cudaEventElapsedTime(&a, ctx->evpool[3 * i], ctx->evpool[3 * i + 1]); cudaEventElapsedTime(&c, ctx->evpool[3 * i + 1], ctx->evpool[3 * i + 2]);
+            ms_part += a; ms_count += c;
+        }
+        if (flags[2]) return fkm_set_error(FKM_EOVERFLOW, "a k-mer occurs more than 2^32-1 times: 32-bit counts overflow (the reference counts in Int, SBKC:562,676)");
+        if (flags[0] || flags[1]) return kRetryGlobal;
+        // one result chunk per CTA region; a bin's entries begin in the region of the CTA that counted its first sub-bucket
+        for (size_t i = b0; i < b1; i++) {
+            const Batch& bt = batches[i];
+            const uint32_t* sf = h32.data() + bt.o32 + (size_t)(bt.hi - bt.lo) + 1;
+            std::vector<unsigned long long> cta_start((size_t)grid + 1);
+            cta_start[0] = out_total;
+            for (unsigned c = 0; c < grid; c++) {
+                const unsigned long long n = h_cta_total[(i - b0) * grid + c];
+                cta_start[(size_t)c + 1] = cta_start[(size_t)c] + n;
+                if (n) {
+                    Chunk ch; ch.keys = (char*)ok[i - b0] + (size_t)c * bt.region_cap * sizeof(Key); ch.cnt = oc[i - b0] + (size_t)c * bt.region_cap; ch.n = n;
+                    res->chunks.push_back(ch);
+                }
+            }
+            unsigned long long next = cta_start[(size_t)grid];
+            for (int b = bt.hi - 1; b >= bt.lo; b--) {
+                if (sf[b - bt.lo + 1] > sf[b - bt.lo]) next = cta_start[(size_t)h_bin_cta[(size_t)b]] + h_bin_off[(size_t)b];
+                res->out_base[(size_t)b] = next;
+            }
+            out_total = cta_start[(size_t)grid];
+            n_sub_total += bt.n_sub;
+            st->n_batches++;
+        }
+        return FKM_OK;
+    };
+
+    // phase A: the sample, sized for all-distinct k-mers
+    const int s_hi = std::min(B, std::max(1, B / 64));
+    uint64_t km_a = 0; for (int b = 0; b < s_hi; b++) km_a += h_kmer[(size_t)b];
+    plan(0, s_hi, 1.0, 1.0, true);
+    int rc = run(0, batches.size()); if (rc) return rc;
+    if (s_hi < B) {
+        double rho = 1.0;
+        if (km_a > 100000) rho = std::min(1.0, (double)out_total / (double)km_a);
+        rho *= ctx->debug_rho_scale;
+        const size_t b0 = batches.size();
+        plan(s_hi, B, std::min(1.0, rho * 1.1 + 0.01), rho, false);
+        rc = run(b0, batches.size()); if (rc) return rc;
+    }
+    res->out_base[(size_t)B] = out_total;
+    unsigned long long h_counters[8];
+    CK(cudaMemcpyAsync(h_counters, d_counters, 64, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    st->d2h_bytes += 64;
+    st->n_mid_bins = n_sub_total; st->n_slow_bins = h_counters[0];
+    *out_total_p = out_total; *ms_part_p = ms_part; *ms_count_p = ms_count;
+    return FKM_OK;
+}
+
 // records that are already bin-major on this device (multi-GPU: after the exchange)
 struct PreScattered { const void* d_records; const uint64_t* bin_rec; const uint64_t* bin_kmer; };
 
@@ -540,7 +746,6 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
     st->n_kmers = n_kmers; st->n_superkmers = n_rec; st->superkmer_bytes = n_rec * rec_bytes; st->n_nonempty_bins = nonempty;
     CKC(cudaMemcpyAsync(d_bin_base, h_base.data(), bB + 8, cudaMemcpyHostToDevice, s));
     st->h2d_bytes += bB + 8;
-    const bool want_fold = !WIDE && cfg->use_ht && ctx->fold_records >= 1.0 && n_rec >= 4096;
     if (!pre) {
         CKC(dmalloc(ctx, &d_records, std::max<size_t>(16, (size_t)n_rec * rec_bytes)));
         tr.mark("records allocated", (long long)n_rec);
@@ -549,6 +754,26 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
         d_records = const_cast<void*>(pre->d_records);
         CKC(cudaEventRecord(ctx->ev[2], s));
     }
+
+    // ---- hash path, count_mode 2: the partitioned count stage with its tables in shared memory (fkm_part.cuh)
+    uint64_t out_total = 0;
+    float ms_count = 0, ms_compact = 0, ms_part = 0;
+    bool part_done = false;
+    if (cfg->use_ht && ctx->count_mode >= 2.0 && n_rec) {
+        const Arena::Mark mk = ctx->arena.mark();
+        rc = count_partitioned<WIDE>(ctx, cfg, B, d_records, d_bin_base, h_rec, h_kmer, res, st, d_acc, &out_total, &ms_part, &ms_count);
+        if (rc == FKM_OK) part_done = true;
+        else if (rc != kRetryGlobal) { cleanup(); return rc; }
+        else {      // the global-table pipeline below redoes the count
+            rc = FKM_OK;
+            ctx->arena.release(mk);
+            st->n_fallbacks++; st->n_batches = 0; st->n_mid_bins = 0; st->n_slow_bins = 0;
+            res->chunks.clear(); out_total = 0; ms_count = 0; ms_part = 0;
+            CKC(cudaMemsetAsync(d_acc, 0, 192 * 8, s));
+        }
+    }
+    st->ms_partition = ms_part;
+    const bool want_fold = !part_done && !WIDE && cfg->use_ht && ctx->fold_records >= 1.0 && n_rec >= 4096;
 
     // ---- stage 2b (hash path, 64-bit k-mers, optional): fold identical records.  Reads of a deeply sequenced
     // genome repeat its super-k-mers once per covering read (either strand); every k-mer of a repeated record costs
@@ -671,9 +896,8 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
     st->ms_fold = ms_fold;
 
     // ---- stage 3/4: per-bin exact count, batches of consecutive bins
-    uint64_t out_total = 0;
-    float ms_count = 0, ms_compact = 0;
-    if (cfg->use_ht) {
+    if (part_done) {
+    } else if (cfg->use_ht) {
         double rho = 1.0;                         // sizing estimate of distinct / k-mers (with margin), learnt from the first batch
         double rho_obs = 1.0;                     // the ratio actually observed
         uint64_t table_cap = 0;
@@ -1006,7 +1230,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
     CKC(cudaEventRecord(ctx->ev[3], s));
 
     // ---- stage 5: digest + bookkeeping
-    CKC(cudaMemcpyAsync(res->out_base.data(), d_out_base, bB + 8, cudaMemcpyDeviceToHost, s));
+    if (!part_done) CKC(cudaMemcpyAsync(res->out_base.data(), d_out_base, bB + 8, cudaMemcpyDeviceToHost, s));
     if (!cfg->use_ht) {                         // the HT path folds its digest into k_compact_ht
         uint64_t origin = 0;
         for (const Chunk& ch : res->chunks) {
@@ -1049,7 +1273,6 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
 }
 
 // ------------------------------------------------------------------ the shared-memory count pipeline (fkm_smem.cuh)
-static constexpr int kRetryGlobal = 1;          // internal: the job must be redone by the global-table pipeline
 
 // geometry of k_count_smem's shared memory for one key width
 struct SmemGeom { uint32_t cap_slots, max_fill, stage_recs; size_t bytes; };
@@ -1236,7 +1459,7 @@ static int run_pipeline_smem(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, fkm
     return FKM_OK;
 }
 
-static bool want_smem_path(const fkm_ctx* ctx, const fkm_config* cfg) { return cfg->use_ht && ctx->count_mode >= 1.0; }
+static bool want_smem_path(const fkm_ctx* ctx, const fkm_config* cfg) { return cfg->use_ht && ctx->count_mode >= 1.0 && ctx->count_mode < 2.0; }
 
 static int count_device(fkm_ctx* ctx, const fkm_config* cfg, const void* d_bases, const void* d_inv, uint64_t n_pos,
                         fkm_result** out, fkm_stats* stats, const PreScattered* pre = nullptr, ScanState* scanned = nullptr) {

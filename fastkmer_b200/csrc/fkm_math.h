@@ -55,7 +55,17 @@ FKM_DEV uint64_t swap_pairs(uint64_t x) {
 }
 // reverse complement of a right-aligned len-mer (len <= 32)
 FKM_DEV uint64_t revcomp64(uint64_t x, int len) {
+#if defined(__CUDA_ARCH__)
+    // two BREVs, then per word ONE LOP3 that swaps the two bits of every pair and complements:
+    // ~(((v >> 1) & 0x55555555) | ((v << 1) & 0xAAAAAAAA))   (LUT 0x1B over a = v >> 1, b = v << 1, c = 0x55555555)
+    const uint32_t a = __brev((uint32_t)x), b = __brev((uint32_t)(x >> 32));
+    uint32_t ra, rb;
+    asm("lop3.b32 %0, %1, %2, 0x55555555, 0x1B;" : "=r"(ra) : "r"(a >> 1), "r"(a << 1));
+    asm("lop3.b32 %0, %1, %2, 0x55555555, 0x1B;" : "=r"(rb) : "r"(b >> 1), "r"(b << 1));
+    return (((uint64_t)ra << 32) | rb) >> (64 - 2 * len);
+#else
     return swap_pairs(brev64(~x)) >> (64 - 2 * len);
+#endif
 }
 FKM_DEV key128 revcomp128(key128 x, int len) {          // 32 < len <= 64
     uint64_t rh = swap_pairs(brev64(~x.lo)), rl = swap_pairs(brev64(~x.hi));
@@ -121,6 +131,19 @@ FKM_DEV uint32_t key_hash(key128 key) {
     return fmix32(((uint32_t)key.lo * 0x9E3779B1u ^ (uint32_t)(key.lo >> 32) * 0x85EBCA77u) +
                   ((uint32_t)key.hi * 0xC2B2AE3Du ^ (uint32_t)(key.hi >> 32) * 0x27D4EB2Fu));
 }
+// Hash of the partitioned count path (fkm_part.cuh): the sub-bucket of a k-mer is mulhi(h, sub-buckets) (the high bits of h),
+// its table slot part_slot(h) (low bits, folded once more), so that the k-mers of one sub-bucket spread over the whole table.
+FKM_DEV uint32_t part_hash(uint64_t key) {
+    uint32_t x = (uint32_t)key * 0x9E3779B1u ^ (uint32_t)(key >> 32) * 0x85EBCA77u;
+    x ^= x >> 16; x *= 0xC2B2AE3Du;
+    return x;
+}
+FKM_DEV uint32_t part_hash(key128 key) {
+    uint32_t x = ((uint32_t)key.lo * 0x9E3779B1u ^ (uint32_t)(key.lo >> 32) * 0x85EBCA77u) + ((uint32_t)key.hi * 0x27D4EB2Fu ^ (uint32_t)(key.hi >> 32) * 0x165667B1u);
+    x ^= x >> 16; x *= 0xC2B2AE3Du;
+    return x;
+}
+FKM_DEV uint32_t part_slot(uint32_t h, uint32_t mask) { return (h ^ (h >> 13)) & mask; }
 FKM_DEV unsigned long long slot_of(uint32_t h, unsigned long long size) {
     return (size <= 0xFFFFFFFFull) ? (unsigned long long)umulhi32(h, (uint32_t)size)
                                    : umulhi64(((unsigned long long)h << 32) | fmix32(h), size);

@@ -81,6 +81,7 @@ typedef struct fkm_stats {
     double   ms_fold;            /* device time of the folding stage (between scatter and count)       */
     uint64_t n_mid_bins;         /* shared-memory count path: tables (mid bins) the bins were cut into; 0 = global-table path */
     uint64_t n_slow_bins;        /* ... of which overflowed shared memory and were redone in a global-memory table */
+    double   ms_partition;       /* partitioned count path (count_mode 2): device time of the k-mer partition (k_sub_hist/scan/scatter); ms_stage[3] is then k_count_keys alone */
 } fkm_stats;
 
 const char* fkm_last_error(void);

@@ -22,6 +22,6 @@ for v in (vals.split(",") if vals else [None]):
         ctx.set(name, float(v))
     for rep in range(2):
         _, st = ctx.count_packed_device(cfg, d_b, d_i, n_pos, want_result=False)
-    print(json.dumps({"knob": name, "value": v, "ms": [round(x, 2) for x in st["ms_stage"]], "n_mid": st["n_mid_bins"], "n_slow": st["n_slow_bins"],
+    print(json.dumps({"knob": name, "value": v, "ms": [round(x, 2) for x in st["ms_stage"]], "ms_partition": round(st["ms_partition"], 2), "ms_fold": round(st["ms_fold"], 2), "n_mid": st["n_mid_bins"], "n_slow": st["n_slow_bins"],
                       "fallbacks": st["n_fallbacks"], "records": st["n_superkmers"], "distinct": st["n_distinct"], "kmers": st["n_kmers"]}), flush=True)
 ctx.close()

@@ -63,11 +63,12 @@ def test_cuda_reproduces_golden_files(v, tmp_path):
             if not use_ht:
                 assert triples(res.arrays(), v["k"]) == want  # device order == file order
         # the hash path with its tables in shared memory (k_count_smem) instead of global memory
-        ctx.set("count_mode", 1)
-        cfg = fk.TestConfiguration("", "", v["k"], v["m"], v["x"], max_b=v["max_b"], useHT=True, write=False)
-        res, st = ctx.count_fasta(cfg, fasta)
-        assert triples(res.sorted_arrays(), v["k"]) == want, "shared-memory tables"
-        assert (st["n_kmers"], st["n_distinct"], st["total_count"]) == (v["n_kmers"], v["n_distinct"], v["n_kmers"]) and st["n_mid_bins"] > 0
+        for mode in (2, 1):      # 2: hash-partitioned k-mers (k_count_keys), 1: dual-minimizer mid bins (k_count_smem)
+            ctx.set("count_mode", mode)
+            cfg = fk.TestConfiguration("", "", v["k"], v["m"], v["x"], max_b=v["max_b"], useHT=True, write=False)
+            res, st = ctx.count_fasta(cfg, fasta)
+            assert triples(res.sorted_arrays(), v["k"]) == want, "shared-memory tables, mode %d" % mode
+            assert (st["n_kmers"], st["n_distinct"], st["total_count"]) == (v["n_kmers"], v["n_distinct"], v["n_kmers"]) and st["n_mid_bins"] > 0
         ctx.set("count_mode", 0)
         # the job as the reference runs it: dataset file in, <outputDir>/bin<id> files out (sorted + "EOF", SBKC:550-606)
         src = tmp_path / "in.fasta"

@@ -241,21 +241,25 @@ def test_async_phase_overflow_falls_back(oracle):
         c2.close()
 
 
-def test_smem_path_tiers(oracle):
-    """useHT=1 counts in shared-memory tables (k_count_smem).  A mid bin with more distinct k-mers than the table holds is
+@pytest.mark.parametrize("mode", [2, 1])
+def test_smem_path_tiers(oracle, mode):
+    """useHT=1 counts in shared-memory tables (mode 2: k-mers hash-partitioned into sub-buckets, k_count_keys; mode 1: dual-minimizer
+    mid bins, k_count_smem).  A sub-bucket / mid bin with more distinct k-mers than the table holds is
     redone by its CTA in a private global table (slow path); if that overflows too, or the output estimate is too small, or
-    the run-event lists overflow, the whole job is redone by the global-table pipeline.  Every tier gives the oracle's result."""
+    (mode 1) the run-event lists overflow, the whole job is redone by the global-table pipeline.  Every tier gives the oracle's result."""
     deep = fk.synth_fasta(dict(seeds=(31, 32, 33), genome_len=50000, n_reads=50000, read_len=100)).tobytes()      # 100x coverage
     flat = fk.synth_fasta(dict(seeds=(34, 35, 36), genome_len=30000000, n_reads=40000, read_len=150)).tobytes()   # nearly all distinct
     c2 = fk.Context(0)
     try:
-        c2.set("count_mode", 1)
+        c2.set("count_mode", mode)
         for text, label in ((deep, "deep"), (flat, "flat")):
             for k, m, B in ((28, 10, 2048), (55, 13, 2048), (33, 9, 64), (31, 11, 1), (12, 4, 100), (22, 8, 300)):
                 want = oracle.count(text, k, m, 3, B, 1, threads=8)
                 ws = want["stats"]
-                for knobs, tier in (({}, "fast"), ({"smem_table_slots": 256}, "slow"),
-                                    ({"smem_table_slots": 256, "smem_slow_slots": 1024}, "fallback"),
+                # (mode 2 plans its sub-buckets for the table it has: a small table alone never overflows, a wrong distinct / k-mer estimate does)
+                small = {"smem_table_slots": 256} if mode == 1 else {"smem_table_slots": 64, "debug_rho_scale": 0.02}
+                for knobs, tier in (({}, "fast"), (small, "slow"),
+                                    (dict(small, smem_slow_slots=1024), "fallback"),
                                     ({"debug_rho_scale": 0.02}, "rho"), ({"debug_event_scale": 0.001}, "events")):
                     for name in ("smem_table_slots", "debug_rho_scale", "debug_event_scale"):
                         c2.set(name, {"smem_table_slots": 0, "debug_rho_scale": 1.0, "debug_event_scale": 1.0}[name])
@@ -263,7 +267,7 @@ def test_smem_path_tiers(oracle):
                     for name, v in knobs.items():
                         c2.set(name, v)
                     res, st = c2.count_fasta(cfg(k, m, 3, B, 1), text)
-                    what = "smem %s %s k=%d B=%d" % (tier, label, k, B)
+                    what = "smem mode %d %s %s k=%d B=%d" % (mode, tier, label, k, B)
                     assert_same(res.sorted_arrays(), want, what)
                     assert (st["digest_sum"], st["digest_xor"]) == (ws["digest_sum"], ws["digest_xor"]), what
                     assert st["n_kmers"] == ws["n_kmers"] == st["total_count"] and st["n_distinct"] == ws["n_distinct"], what
@@ -271,15 +275,18 @@ def test_smem_path_tiers(oracle):
                         assert st["n_mid_bins"] > 0 and st["n_fallbacks"] == 0 and st["n_slow_bins"] <= (0 if B == 2048 else st["n_mid_bins"] // 4), what
                     if tier == "slow":
                         assert st["n_fallbacks"] == 0 and st["n_mid_bins"] > 0, what
-                        if B >= 64 and k >= 22:
+                        if B >= 64 and k >= 22 and (mode == 1 or label == "flat"):
                             assert st["n_slow_bins"] > 0, what
-                    if tier == "events":
+                    if tier == "fallback" and mode == 2 and label == "flat" and B >= 64 and k >= 22:
                         assert st["n_fallbacks"] >= 1 and st["n_mid_bins"] == 0, what
+                    if tier == "events":      # (mode 2 keeps its tables: only the scatter stage falls back to a second scan)
+                        assert st["n_fallbacks"] >= 1 and (st["n_mid_bins"] == 0) == (mode == 1), what
     finally:
         c2.close()
 
 
-def test_smem_path_edge_cases(oracle):
+@pytest.mark.parametrize("mode", [2, 1])
+def test_smem_path_edge_cases(oracle, mode):
     """The reference's input edge cases (empty, short, all-N, lowercase, CRLF, homopolymers and short-period repeats far longer than
     a record, k = m, k = 64, B = 1, B > 4096) through the shared-memory tables."""
     rng = random.Random(11)
@@ -292,10 +299,10 @@ def test_smem_path_edge_cases(oracle):
         texts.append(_rand_fasta(rng, 40, 0, 250, alphabet=alphabet, width=width).encode())
     c2 = fk.Context(0)
     try:
-        c2.set("count_mode", 1)
+        c2.set("count_mode", mode)
         for (k, m, B) in ((28, 10, 2048), (5, 3, 64), (31, 11, 4096), (32, 7, 333), (33, 8, 512), (55, 13, 2048), (64, 15, 5000), (15, 15, 3), (20, 5, 1), (7, 7, 1 << 20)):
             for t in texts:
-                res, st = check(c2, oracle, t, k, m, 3, B, 1, "smem k=%d B=%d %r" % (k, B, t[:10]))
+                res, st = check(c2, oracle, t, k, m, 3, B, 1, "smem mode %d k=%d B=%d %r" % (mode, k, B, t[:10]))
                 assert st["n_fallbacks"] == 0
     finally:
         c2.close()
@@ -311,7 +318,7 @@ def test_count_overflow_is_reported():
     inv = np.zeros(nw, dtype=np.uint32)
     c2 = fk.Context(0)
     try:
-        for ht, mode in ((1, 0), (1, 1), (0, 0)):
+        for ht, mode in ((1, 0), (1, 1), (1, 2), (0, 0)):
             c2.set("count_mode", mode)
             with pytest.raises(api.FkmError) as e:
                 c2.count_packed_host(cfg(28, 10, 3, 2048, ht), bases, inv, n_pos, want_result=False)
@@ -326,18 +333,18 @@ def test_count_overflow_is_reported():
         c2.close()
 
 
-def test_smem_and_global_tables_agree_at_scale(ctx):
+@pytest.mark.parametrize("mode", [2, 1])
+def test_smem_and_global_tables_agree_at_scale(ctx, mode):
     """2 M reads: the shared-memory tables and the global tables give the same digest, and the sum of counts is the number of windows."""
     spec = dict(seeds=(41, 42, 43), genome_len=10_000_000, n_reads=2_000_000, read_len=150)
     d_b, d_i, n_pos = ctx.synth_packed_device(spec)
     try:
         for k, m in ((28, 10), (55, 13)):
             c = cfg(k, m, 3, 2048, 1)
-            ctx.set("count_mode", 1)
+            ctx.set("count_mode", mode)
             _, a = ctx.count_packed_device(c, d_b, d_i, n_pos, want_result=False)
             ctx.set("count_mode", 0)
             _, b = ctx.count_packed_device(c, d_b, d_i, n_pos, want_result=False)
-            ctx.set("count_mode", 1)
             assert a["n_mid_bins"] > 0 and b["n_mid_bins"] == 0
             for key in ("n_kmers", "n_distinct", "total_count", "digest_sum", "digest_xor"):
                 assert a[key] == b[key], (k, key)
