@@ -255,12 +255,14 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage = [0.0] * 8
     ms_fold = 0.0
+    ms_part = 0.0
     e0.record(stream)
     for _ in range(args.steps):
         st = step_resident()
         for i in range(8):
             stage[i] += st["ms_stage"][i]
         ms_fold += st["ms_fold"]
+        ms_part += st.get("ms_partition", 0.0)
     e1.record(stream)
     barrier()
     launches = api.load_library().fkm_total_launches() - launches0
@@ -273,6 +275,7 @@ def main():
     ms_step = ms / args.steps
     stage = [s / args.steps for s in stage]
     ms_fold /= args.steps
+    ms_part /= args.steps
     n_bases_total = wl.n_bases_total(world)
     n_kmers_total = st["n_kmers_global"] if "n_kmers_global" in st else st["n_kmers"]
     n_distinct_total = st["n_distinct_global"] if "n_distinct_global" in st else st["n_distinct"]
@@ -361,17 +364,20 @@ def main():
     # the super-k-mer stream once (L_s/4 algorithmic bytes); the distinct (k-mer,count) pairs leave through stage 4.
     n_count_launches = max(1, int(st["n_batches"]))
     smem_path = bool(st["n_mid_bins"])
-    # dominant kernel = the count stage's own kernel (stage 3), timed with CUDA events inside the library.  k_count_ht reads the
-    # super-k-mer stream once (L_s/4); k_count_smem (shared-memory tables) also writes the result (D*(W+4)): it has no compaction kernel
+    part_path = smem_path and ms_part > 0.0
+    # dominant kernel = the count stage's own kernel (stage 3), timed with CUDA events inside the library.  Algorithmic bytes per
+    # the count stage reads the super-k-mer stream once (L_s/4); the shared-memory kernels (k_count_keys, k_count_smem)
+    # also write the result (D*(W+4)) themselves: they have no compaction kernel.  `traffic` is what DRAM really moved per launch.
     count_bytes = (L_s / 4 + (n_distinct_total * (key_bytes + 4) if smem_path else 0)) / world
     count_ms = stage[3]
-    kernel = "k_count_smem" if smem_path else ("k_count_ht" if wl.c["ht"] else "k_expand+k_radix_*")
+    kernel = "k_count_keys" if part_path else "k_count_smem" if smem_path else ("k_count_ht" if wl.c["ht"] else "k_expand+k_radix_*")
     traffic, traffic_src = None, None
     try:                                              # DRAM bytes per launch from an ncu --set full capture of the same kernel (profiles/)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_count_smem_traffic.json" if smem_path else "r1f_count_ht_traffic.json")))
+        tname = "r2_count_keys_traffic.json" if part_path else "r2_count_smem_traffic.json" if smem_path else "r1f_count_ht_traffic.json"
+        tj = json.load(open(os.path.join(ROOT, "profiles", tname)))
         if smem_path and wl.c["k"] <= 32:
             traffic = tj["dram_bytes_per_kmer"] * (n_kmers_total / world / n_count_launches)
-            traffic_src = "static: ncu capture profiles/%s scaled by k-mers per launch" % tj.get("file", "r2_count_smem_traffic.json")
+            traffic_src = "static: ncu capture profiles/%s scaled by k-mers per launch" % tname
         elif wl.c["ht"] and wl.c["k"] <= 32 and st["n_folded_records"]:
             traffic = tj["dram_bytes_per_record"] * (st["n_folded_records"] / n_count_launches)
             traffic_src = "static: ncu capture profiles/r1f_count_ht_traffic.json (round 1) scaled by folded records per launch"
@@ -397,9 +403,9 @@ def main():
                        "reads_per_gpu": wl.c.get("reads"), "n_bases": n_bases_total,
                        "n_kmers": int(n_kmers_total), "n_distinct": int(n_distinct_total),
                        "n_superkmers": int(st["n_superkmers"]), "n_folded_records": int(st["n_folded_records"]),
-                       "count_tables": "shared memory (%d mid bins, %d on the slow path)" % (st["n_mid_bins"], st["n_slow_bins"]) if smem_path else "global memory",
+                       "count_tables": ("shared memory (%d %s, %d on the slow path)" % (st["n_mid_bins"], "hash-partitioned sub-buckets" if part_path else "mid bins", st["n_slow_bins"])) if smem_path else "global memory",
                        "l2": "inputs (%.1f GB packed) larger than L2, no flush" % (n_pos * 3 / 8 / 1e9)},
-            "stage_ms": {"histogram": stage[1], "scatter": stage[2], "fold": ms_fold, "count": stage[3], "compact": stage[4], "digest": stage[5],
+            "stage_ms": {"histogram": stage[1], "scatter": stage[2], "fold": ms_fold, "partition": ms_part, "count": stage[3], "compact": stage[4], "digest": stage[5],
                          "device_pipeline": stage[7]},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "shuffle": shuffle, "parity": parity}

