@@ -100,7 +100,7 @@ struct fkm_ctx {
     double fold_max_ratio = 0.6;      // ... unless the first batch shows that more than this share of the records is distinct
     double cas_first = 0.0;           // hash path: 1 = probe with the CAS itself instead of a read followed by a CAS
     double debug_force_lsd = 0.0;     // sort path: 0 = auto (MSD + shared-memory chunk sort for 64-bit keys, LSD passes for 128-bit), 1 = LSD, 2 = MSD
-    double sort_partition = 1.0;      // sort path: 1 = expand once + sub-buckets by the top key bits + shared-memory chunk sort (fkm_part.cuh kernels), 0 = the older passes
+    double sort_partition = 1.0;      // sort path: 1 = expand once, sub-buckets by the top key bits, shared-memory chunk sort (k_radix_local) + run-length count; 2 = the same sub-buckets + ordered shared-memory tables (k_count_keys_ordered: no sort at all; opt-in: the top bits of the k-mers of a minimizer bin are too unevenly spread for it); 0 = the round-1 passes
     double debug_rho_scale = 1.0;     // test hook: scales the learnt distinct/k-mer ratio (forces the overflow fallback)
     double count_mode = 2.0;          // hash path: 2 = k-mers hash-partitioned into sub-buckets, tables in shared memory (fkm_part.cuh); 1 = dual-minimizer mid bins, tables in shared memory (fkm_smem.cuh); 0 = tables in global memory
     double smem_table_slots = 0.0;    // test hook: slots of the shared-memory table (0 = as many as fit)
@@ -493,6 +493,7 @@ static int stage_scatter(fkm_ctx* ctx, ScanState* S, const unsigned long long* d
 }
 
 static constexpr int kRetryGlobal = 1;          // internal: the job must be redone by the global-table pipeline
+static constexpr int kBinTooBig = 2;            // internal: the sort path met a bin of 2^32 k-mers
 
 // ------------------------------------------------------------------ the partitioned count stage (fkm_part.cuh)
 // Hash path with the tables in shared memory: bin-major records -> canonical k-mers, hash-partitioned into sub-buckets of a
@@ -503,19 +504,23 @@ static constexpr int kRetryGlobal = 1;          // internal: the job must be red
 template <bool WIDE>
 static int count_partitioned(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const void* d_records, const unsigned long long* d_bin_base,
                              const std::vector<unsigned long long>& h_rec, const std::vector<unsigned long long>& h_kmer,
-                             fkm_result* res, fkm_stats* st, unsigned long long* d_acc, uint64_t* out_total_p, float* ms_part_p, float* ms_count_p) {
+                             fkm_result* res, fkm_stats* st, unsigned long long* d_acc, uint64_t* out_total_p, float* ms_part_p, float* ms_count_p, const bool ordered) {
     typedef typename Traits<WIDE>::Key Key;
     cudaStream_t s = ctx->stream;
     constexpr uint64_t TR = PartGeom<WIDE>::kTileRecs;
+    // ordered (sort path): the sub-buckets of a bin are 2^j key ranges and k_count_keys_ordered's table keeps the k-mers in order
     for (int b = 0; b < B; b++) if (h_kmer[(size_t)b] >= 0xFFFFFFF0ull) return kRetryGlobal;
     // geometry of k_count_keys's table
     uint32_t cap = WIDE ? 8192u : 16384u;
     while (cap > 64u && (size_t)cap * (sizeof(Key) + 6) + 2048 > ctx->smem_optin) cap >>= 1;
     if (ctx->smem_table_slots >= 64.0) while (cap > 64u && (double)cap > ctx->smem_table_slots) cap >>= 1;
-    const size_t kc_smem = (size_t)cap * (sizeof(Key) + 6);
+    const uint32_t tail = ordered ? 512u : 0u;
+    const size_t kc_smem = ordered ? (size_t)(cap + tail) * (sizeof(Key) + 4) : (size_t)cap * (sizeof(Key) + 6);
     const size_t sc_smem = (size_t)PartGeom<WIDE>::kBufKeys * (sizeof(Key) + 2);
-    CK(cudaFuncSetAttribute(k_count_keys<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kc_smem));
+    CK(cudaFuncSetAttribute(k_count_keys<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)cap * (sizeof(Key) + 6))));
+    CK(cudaFuncSetAttribute(k_count_keys_ordered<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)(cap + 512u) * (sizeof(Key) + 4))));
     CK(cudaFuncSetAttribute(k_place_keys<WIDE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
+    CK(cudaFuncSetAttribute(k_place_keys<WIDE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
     static int occ_hist[2] = {0, 0}, occ_scat[2] = {0, 0};
     if (!occ_hist[WIDE]) {
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_hist[WIDE], k_expand_hist<WIDE, false>, PartGeom<WIDE>::kThreads, 0));
@@ -523,7 +528,8 @@ static int count_partitioned(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, con
         if (occ_hist[WIDE] < 1) occ_hist[WIDE] = 1;
         if (occ_scat[WIDE] < 1) occ_scat[WIDE] = 1;
     }
-    const double d_target = std::max(16.0, (double)cap * ctx->part_fill);             // distinct k-mers a sub-bucket is planned for
+    // distinct k-mers a sub-bucket is planned for (key ranges are up to twice as full as the average: canonical k-mers crowd the low end of the key space)
+    const double d_target = std::max(16.0, (double)cap * ctx->part_fill * (ordered ? 0.5 : 1.0));
     const uint64_t budget_keys = std::max<uint64_t>(1u << 16, (uint64_t)ctx->part_budget_keys);
     const unsigned grid = (unsigned)ctx->n_sm;
     const size_t bB = (size_t)B * 8;
@@ -549,6 +555,7 @@ static int count_partitioned(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, con
                 const uint64_t tiles = km ? (nr + TR - 1) / TR : 0;
                 uint64_t subs = km ? (uint64_t)std::ceil((double)km * rho_plan / d_target) : 0;
                 subs = km ? std::min<uint64_t>(std::max<uint64_t>(subs, 1), kPartMaxSubs) : 0;
+                if (ordered && km) { uint64_t p2 = 1; while (p2 < subs) p2 <<= 1; subs = std::min<uint64_t>(p2, kPartMaxSubs); }
                 tf[b - lo] = (uint32_t)bt.n_tiles; sf[b - lo] = (uint32_t)bt.n_sub; ho[b - lo] = bt.hist_elems; kb[b - lo] = keys;
                 bt.n_tiles += tiles; bt.n_sub += subs; bt.hist_elems += tiles * subs; keys += km;
             }
@@ -612,16 +619,20 @@ static int count_partitioned(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, con
                 CK(cudaMemsetAsync(d_kcur, 0, (size_t)nb * 4, s));
                 const unsigned g1 = (unsigned)std::min<uint64_t>(bt.n_tiles, (uint64_t)ctx->n_sm * occ_hist[WIDE]);
                 const unsigned g3 = (unsigned)std::min<uint64_t>(bt.n_tiles, (uint64_t)ctx->n_sm * occ_scat[WIDE]);
-                k_expand_hist<WIDE, false><<<g1, PartGeom<WIDE>::kThreads, 0, s>>>(P); CKL();
+                if (ordered) k_expand_hist<WIDE, true><<<g1, PartGeom<WIDE>::kThreads, 0, s>>>(P); else k_expand_hist<WIDE, false><<<g1, PartGeom<WIDE>::kThreads, 0, s>>>(P);
+                CKL();
                 k_sub_scan<<<(unsigned)nb, 256, 0, s>>>(P); CKL();
-                k_place_keys<WIDE, false><<<g3, PartGeom<WIDE>::kThreads, sc_smem, s>>>(P); CKL();
+                if (ordered) k_place_keys<WIDE, true><<<g3, PartGeom<WIDE>::kThreads, sc_smem, s>>>(P); else k_place_keys<WIDE, false><<<g3, PartGeom<WIDE>::kThreads, sc_smem, s>>>(P);
+                CKL();
                 CK(cudaEventRecord(ctx->evpool[3 * (i - b0) + 1], s));
                 KeyCountParams Q;
                 Q.keys = d_keys; Q.mid_key_base = d_mid_key; Q.mid_bin = d_mid_bin; Q.sub_first = P.sub_first; Q.bin_lo = bt.lo; Q.n_sub = (uint32_t)bt.n_sub;
                 Q.out_keys = ok[i - b0]; Q.out_cnt = oc[i - b0]; Q.region_cap = bt.region_cap; Q.cta_total = d_cta_total + (i - b0) * grid;
                 Q.bin_cta = d_bin_cta; Q.bin_off = d_bin_off; Q.acc = d_acc; Q.cap_slots = cap; Q.max_fill = cap * 3 / 4;
                 Q.slow_keys = d_slow_keys; Q.slow_cnt = d_slow_cnt; Q.slow_slots = slow_slots; Q.slow_max_fill = slow_slots * 7 / 10; Q.flags = d_flags; Q.counters = d_counters;
-                k_count_keys<WIDE><<<grid, kKcThreads, kc_smem, s>>>(Q); CKL();
+                Q.k = cfg->k; Q.tail_slots = tail;
+                if (ordered) k_count_keys_ordered<WIDE><<<grid, kKcThreads, kc_smem, s>>>(Q); else k_count_keys<WIDE><<<grid, kKcThreads, kc_smem, s>>>(Q);
+                CKL();
             } else CK(cudaEventRecord(ctx->evpool[3 * (i - b0) + 1], s));
             CK(cudaEventRecord(ctx->evpool[3 * (i - b0) + 2], s));
         }
@@ -762,9 +773,9 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
     uint64_t out_total = 0;
     float ms_count = 0, ms_compact = 0, ms_part = 0;
     bool part_done = false;
-    if (cfg->use_ht && ctx->count_mode >= 2.0 && n_rec) {
+    if ((cfg->use_ht ? ctx->count_mode >= 2.0 : (ctx->sort_partition >= 2.0 && ctx->debug_force_lsd < 1.0)) && n_rec) {
         const Arena::Mark mk = ctx->arena.mark();
-        rc = count_partitioned<WIDE>(ctx, cfg, B, d_records, d_bin_base, h_rec, h_kmer, res, st, d_acc, &out_total, &ms_part, &ms_count);
+        rc = count_partitioned<WIDE>(ctx, cfg, B, d_records, d_bin_base, h_rec, h_kmer, res, st, d_acc, &out_total, &ms_part, &ms_count, !cfg->use_ht);
         if (rc == FKM_OK) part_done = true;
         else if (rc != kRetryGlobal) { cleanup(); return rc; }
         else {      // the global-table pipeline below redoes the count
@@ -1087,17 +1098,10 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
         if (!fast_ok && lo < B) { rc = safe_batches(lo, B, false, &lo); if (rc) { cleanup(); return rc; } }
     } else {
         // The sort kernels index a bin's keys with 32 bits (as the reference indexes its arrays with Int: a bin of 2^31 (k,x)-mers
-        // cannot exist there, SBKC:484-542).  A bin that large is counted by the hash path first: if a count really exceeds 32
-        // bits the job ends with FKM_EOVERFLOW like every other path; otherwise the configuration needs more bins.
+        // cannot exist there, SBKC:484-542): count_device counts such an input with the hash path instead, to tell a real 32-bit
+        // count overflow (FKM_EOVERFLOW, as on every other path) from a configuration that only needs more bins.
         for (int b = 0; b < B; b++)
-            if (h_kmer[(size_t)b] >= 0xFFFFFFF0ull) {
-                fkm_config c2 = *cfg; c2.use_ht = 1;
-                fkm_result tmp; fkm_stats st2; memset(&st2, 0, sizeof st2);
-                cleanup();
-                rc = run_pipeline<WIDE>(ctx, &c2, B, d_bases, d_inv, n_pos, &tmp, &st2, pre, scanned);
-                if (rc) return rc;
-                return fkm_set_error(FKM_EINVAL, "bin %d holds %llu k-mers: the sort path (useHT=0) indexes a bin with 32 bits, use more bins or useHT=1", b, (unsigned long long)h_kmer[(size_t)b]);
-            }
+            if (h_kmer[(size_t)b] >= 0xFFFFFFF0ull) { cleanup(); return kBinTooBig; }
         const uint64_t budget_keys = std::max<uint64_t>(kSortTile, (uint64_t)ctx->sort_budget_keys);
         const int n_pass = (2 * cfg->k + 7) / 8;
         const uint64_t local_cap = LocalSort<WIDE>::kCap;
@@ -1332,7 +1336,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
 
     // ---- stage 5: digest + bookkeeping
     if (!part_done) CKC(cudaMemcpyAsync(res->out_base.data(), d_out_base, bB + 8, cudaMemcpyDeviceToHost, s));
-    if (!cfg->use_ht) {                         // the HT path folds its digest into k_compact_ht
+    if (!cfg->use_ht && !part_done) {           // the HT path folds its digest into k_compact_ht, the partitioned paths into their count kernels
         uint64_t origin = 0;
         for (const Chunk& ch : res->chunks) {
             if (!ch.n) continue;
@@ -1603,9 +1607,19 @@ static int count_device(fkm_ctx* ctx, const fkm_config* cfg, const void* d_bases
             rc = -1000;
         }
     }
-    if (rc == -1000)
+    if (rc == -1000) {
+        const Arena::Mark mk2 = ctx->arena.mark();
         rc = wide ? run_pipeline<true>(ctx, cfg, B, d_bases, d_inv, n_pos, res, st, pre, scanned)
                   : run_pipeline<false>(ctx, cfg, B, d_bases, d_inv, n_pos, res, st, pre, scanned);
+        if (rc == kBinTooBig) {
+            ctx->arena.release(mk2);
+            fkm_config c2 = *cfg; c2.use_ht = 1;
+            delete res; res = new fkm_result();
+            rc = wide ? run_pipeline<true>(ctx, &c2, B, d_bases, d_inv, n_pos, res, st, pre, scanned)
+                      : run_pipeline<false>(ctx, &c2, B, d_bases, d_inv, n_pos, res, st, pre, scanned);
+            if (!rc) rc = fkm_set_error(FKM_EINVAL, "a bin holds 2^32 k-mers or more: the sort path (useHT=0) indexes a bin with 32 bits, use more bins or useHT=1");
+        }
+    }
     st->gpu_launches = ctx->job_launches;       // everything since job_begin (ingest included)
     st->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (rc) { fkm_result_free(res); return rc; }

@@ -362,6 +362,8 @@ struct KeyCountParams {
     unsigned long long slow_slots; unsigned long long slow_max_fill;
     int* flags;                                 // [0] slow table overflow (job must be redone), [1] output region too small, [2] a 32-bit count wrapped
     unsigned long long* counters;               // [0] sub-buckets that took the slow path
+    int k;                                      // k_count_keys_ordered: k-mer length (the slot is cut from the k-mer's top bits)
+    uint32_t tail_slots;                        // k_count_keys_ordered: slots behind cap_slots (its probing never wraps around)
 };
 
 static constexpr int kKcThreads = 1024;
@@ -448,7 +450,7 @@ __global__ void __launch_bounds__(kKcThreads, 1) k_count_keys(const KeyCountPara
         if (ke == kb) continue;
         const Key* const kp = keys + kb;
         const unsigned long long K = ke - kb;
-        // ---- insert (one key in the registers, the next one on its way; the sub-bucket after this one is pulled into L2 meanwhile)
+        // ---- insert (one key at work, the next two on their way; the sub-bucket after this one is pulled into L2 meanwhile)
         if (threadIdx.x == 0 && m + 1 < m_hi) {
             const unsigned long long nb0 = (ke * sizeof(Key)) & ~15ull, nb1 = (P.mid_key_base[m + 2] * sizeof(Key) + 15ull) & ~15ull;
             if (nb1 > nb0) bulk_prefetch_l2(reinterpret_cast<const unsigned char*>(keys) + nb0, (uint32_t)min(nb1 - nb0, (unsigned long long)(1u << 20)));
@@ -458,6 +460,7 @@ __global__ void __launch_bounds__(kKcThreads, 1) k_count_keys(const KeyCountPara
             uint32_t p = threadIdx.x;
             bool have = p < K32; Key key = Key(); if (have) key = kc_load(kp + p); p += kKcThreads;
             bool hn = p < K32; Key nxt = Key(); if (hn) nxt = kc_load(kp + p); p += kKcThreads;
+            bool hn2 = p < K32; Key nxt2 = Key(); if (hn2) nxt2 = kc_load(kp + p); p += kKcThreads;     // two loads in flight behind the key at work
             uint32_t slot = part_slot(part_hash(key), mask), probes = 0;
             while (have) {
                 bool hit;
@@ -468,7 +471,7 @@ __global__ void __launch_bounds__(kKcThreads, 1) k_count_keys(const KeyCountPara
                 }
                 if (hit) {
                     atomicAdd(&t_cnt[slot], 1u);             // (cannot wrap: a sub-bucket has fewer than 2^32 k-mers)
-                    have = hn; key = nxt; hn = p < K32; if (hn) nxt = kc_load(kp + p); p += kKcThreads;
+                    have = hn; key = nxt; hn = hn2; nxt = nxt2; hn2 = p < K32; if (hn2) nxt2 = kc_load(kp + p); p += kKcThreads;
                     slot = part_slot(part_hash(key), mask); probes = 0;
                 } else {
                     slot = (slot + 1u) & mask;
@@ -564,6 +567,155 @@ __global__ void __launch_bounds__(kKcThreads, 1) k_count_keys(const KeyCountPara
     if (threadIdx.x == 0) P.cta_total[blockIdx.x] = off;
     if (out_full && threadIdx.x == 0) P.flags[1] = 1;
     if (wrapped) P.flags[2] = 1;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        dsum += __shfl_xor_sync(0xFFFFFFFFu, dsum, o); dxor ^= __shfl_xor_sync(0xFFFFFFFFu, dxor, o); dcnt += __shfl_xor_sync(0xFFFFFFFFu, dcnt, o);
+    }
+    if (lane == 0 && dcnt) {
+        const int a = (blockIdx.x * (kKcThreads / 32) + warp) & 63;
+        atomicAdd(&P.acc[a], dsum); atomicXor(&P.acc[64 + a], dxor); atomicAdd(&P.acc[128 + a], dcnt);
+    }
+}
+
+// ------------------------------------------------------------------ the count kernel of the sort path (useHT = 0)
+// The sub-buckets of a bin are KEY RANGES in order (k_expand_hist / k_place_keys in ORDERED mode), and so is the table: a
+// k-mer's home slot is cut from the bits that follow its sub-bucket's prefix, which is monotone in the k-mer; linear
+// probing never wraps (tail_slots spare slots behind the table; running past them sends the job to the older sort
+// kernels).  After the inserts a k-mer sits between its home slot and the end of its cluster (the run of occupied slots
+// around it), so k-mers of different clusters are already in order; every cluster is sorted in place by one thread (the
+// clusters are a few slots long), and the table, read from slot 0 upwards, is the sub-bucket's (k-mer, count) list in
+// ascending order — extractKXmers' sort + heap merge + run-length count (SBKC:540-597, UTIL:642-681) without a sort.
+// dynamic shared memory: keys[cap_slots + tail_slots] | cnt[cap_slots + tail_slots]
+template <bool WIDE>
+__global__ void __launch_bounds__(kKcThreads, 1) k_count_keys_ordered(const KeyCountParams P) {
+    typedef typename SmTraits<WIDE>::Key Key;
+    extern __shared__ __align__(128) unsigned char kc_raw[];
+    const uint32_t n_slots = P.cap_slots + P.tail_slots;
+    Key* const t_keys = reinterpret_cast<Key*>(kc_raw);
+    uint32_t* const t_cnt = reinterpret_cast<uint32_t*>(t_keys + n_slots);
+    __shared__ unsigned int s_ovf;
+    __shared__ unsigned int s_wsum[kKcThreads / 32];
+    __shared__ unsigned int s_range[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const Key empty = sm_empty(Key());
+    const int cap_bits = 31 - __clz(P.cap_slots);
+    for (uint32_t i = threadIdx.x; i < n_slots; i += kKcThreads) { t_keys[i] = empty; t_cnt[i] = 0; }
+    if (threadIdx.x == 0) {
+        s_ovf = 0;
+        const unsigned long long total = P.mid_key_base[P.n_sub];
+        for (int e = 0; e < 2; e++) {
+            const unsigned long long want = (total / gridDim.x) * (blockIdx.x + e) + min((unsigned long long)(blockIdx.x + e), total % gridDim.x);
+            uint32_t lo = 0, hi = P.n_sub;
+            if (blockIdx.x + e >= gridDim.x) lo = P.n_sub;
+            else while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (P.mid_key_base[mid] >= want) hi = mid; else lo = mid + 1; }
+            s_range[e] = lo;
+        }
+    }
+    __syncthreads();
+    const uint32_t m_lo = s_range[0], m_hi = s_range[1];
+    Key* const okeys = reinterpret_cast<Key*>(P.out_keys) + (size_t)blockIdx.x * P.region_cap;
+    uint32_t* const ocnt = P.out_cnt + (size_t)blockIdx.x * P.region_cap;
+    const Key* const keys = reinterpret_cast<const Key*>(P.keys);
+    unsigned long long off = 0;
+    unsigned long long dsum = 0, dxor = 0, dcnt = 0;
+    bool out_full = false;
+    const uint32_t spt = (n_slots + kKcThreads - 1) / kKcThreads;               // slots per thread in the ordered passes (<= 32)
+    const uint32_t s_lo = min(n_slots, threadIdx.x * spt), s_hi = min(n_slots, s_lo + spt);
+    auto home = [&](Key key, int lb) -> uint32_t {          // monotone in the key inside one sub-bucket
+        uint32_t top;
+        if constexpr (!WIDE) top = (uint32_t)((key << (64 - 2 * P.k)) >> 32);
+        else { const int sh = 128 - 2 * P.k; top = (uint32_t)(((sh ? ((key.hi << sh) | (key.lo >> (64 - sh))) : key.hi)) >> 32); }
+        return (lb ? top << lb : top) >> (32 - cap_bits);
+    };
+    auto less = [&](Key a, Key b) -> bool { if constexpr (!WIDE) return a < b; else return key_less(a, b); };
+
+    for (uint32_t m = m_lo; m < m_hi; m++) {
+        const uint32_t bin = P.mid_bin[m];
+        const uint32_t bl = bin - (uint32_t)P.bin_lo;
+        if (threadIdx.x == 0 && P.sub_first[bl] == m) { P.bin_cta[bin] = blockIdx.x; P.bin_off[bin] = off; }
+        const unsigned long long kb = P.mid_key_base[m], ke = P.mid_key_base[m + 1];
+        if (ke == kb) continue;
+        const int lb = 31 - __clz(P.sub_first[bl + 1] - P.sub_first[bl]);          // the bin has 2^lb sub-buckets
+        const Key* const kp = keys + kb;
+        if (threadIdx.x == 0 && m + 1 < m_hi) {
+            const unsigned long long nb0 = (ke * sizeof(Key)) & ~15ull, nb1 = (P.mid_key_base[m + 2] * sizeof(Key) + 15ull) & ~15ull;
+            if (nb1 > nb0) bulk_prefetch_l2(reinterpret_cast<const unsigned char*>(keys) + nb0, (uint32_t)min(nb1 - nb0, (unsigned long long)(1u << 20)));
+        }
+        {
+            const uint32_t K32 = (uint32_t)(ke - kb);       // (a bin, hence a sub-bucket, has fewer than 2^32 k-mers)
+            uint32_t p = threadIdx.x;
+            bool have = p < K32; Key key = Key(); if (have) key = kc_load(kp + p); p += kKcThreads;
+            bool hn = p < K32; Key nxt = Key(); if (hn) nxt = kc_load(kp + p); p += kKcThreads;
+            bool hn2 = p < K32; Key nxt2 = Key(); if (hn2) nxt2 = kc_load(kp + p); p += kKcThreads;
+            uint32_t slot = home(key, lb);
+            while (have) {
+                bool hit;
+                kc_probe(&t_keys[slot], key, hit);
+                if (hit) {
+                    atomicAdd(&t_cnt[slot], 1u);
+                    have = hn; key = nxt; hn = hn2; nxt = nxt2; hn2 = p < K32; if (hn2) nxt2 = kc_load(kp + p); p += kKcThreads;
+                    slot = home(key, lb);
+                } else if (++slot >= n_slots) { s_ovf = 1; have = false; }
+            }
+        }
+        __syncthreads();                                     // all inserts of the sub-bucket are done
+        if (s_ovf) {                                         // ran past the table: the job is redone by the older sort kernels
+            __syncthreads();
+            if (threadIdx.x == 0) { P.flags[0] = 1; s_ovf = 0; }
+            for (uint32_t i = threadIdx.x; i < n_slots; i += kKcThreads) { t_keys[i] = empty; t_cnt[i] = 0; }
+            __syncthreads();
+            continue;
+        }
+        // ---- cluster heads in this thread's slots (read-only pass), then one insertion sort per cluster
+        uint32_t heads = 0, occ = 0;
+        for (uint32_t sl = s_lo; sl < s_hi; sl++) {
+            const bool o = !sm_is_empty(t_keys[sl]);
+            if (o) { occ |= 1u << (sl - s_lo); if (sl == 0 || sm_is_empty(t_keys[sl - 1])) heads |= 1u << (sl - s_lo); }
+        }
+        __syncthreads();
+        while (heads) {
+            const uint32_t h0 = s_lo + (uint32_t)(__ffs((int)heads) - 1);
+            heads &= heads - 1u;
+            for (uint32_t j = h0 + 1; j < n_slots; j++) {
+                const Key kj = t_keys[j];
+                if (sm_is_empty(kj)) break;
+                const uint32_t cj = t_cnt[j];
+                uint32_t i = j;
+                while (i > h0 && less(kj, t_keys[i - 1])) { t_keys[i] = t_keys[i - 1]; t_cnt[i] = t_cnt[i - 1]; i--; }
+                if (i != j) { t_keys[i] = kj; t_cnt[i] = cj; }
+            }
+        }
+        // ---- the table in slot order is the sorted list: dense output, every thread its own run of slots
+        const unsigned int c = (unsigned)__popc(occ);
+        unsigned int incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned int t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();                                     // (also: every cluster is sorted)
+        unsigned int wb = 0, D = 0;
+#pragma unroll
+        for (int i = 0; i < kKcThreads / 32; i++) { const unsigned int t = s_wsum[i]; if (i < warp) wb += t; D += t; }
+        const bool skip = off + D > P.region_cap;
+        if (skip) out_full = true;
+        const uint64_t hbin = mix64((uint64_t)bin);
+        const uint64_t hpre = mix64(hbin);
+        unsigned long long o = off + wb + incl - c;
+        for (uint32_t sl = s_lo; sl < s_hi; sl++) {
+            if (!((occ >> (sl - s_lo)) & 1u)) continue;
+            const Key kk = t_keys[sl]; const uint32_t n = t_cnt[sl];
+            t_keys[sl] = empty; t_cnt[sl] = 0;
+            if (!skip) {
+                okeys[o] = kk; ocnt[o] = n; o++;
+                uint64_t h;
+                if constexpr (!WIDE) h = mix64(kk ^ hpre); else h = mix64(kk.lo ^ mix64(kk.hi ^ hbin));
+                dsum += h * (uint64_t)n; dxor ^= mix64(h + n); dcnt += n;
+            }
+        }
+        if (!skip) off += D;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) P.cta_total[blockIdx.x] = off;
+    if (out_full && threadIdx.x == 0) P.flags[1] = 1;
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
         dsum += __shfl_xor_sync(0xFFFFFFFFu, dsum, o); dxor ^= __shfl_xor_sync(0xFFFFFFFFu, dxor, o); dcnt += __shfl_xor_sync(0xFFFFFFFFu, dcnt, o);

@@ -526,8 +526,12 @@ def test_sort_path_variants(oracle):
                 assert (st["n_fallbacks"] > 0) == expect_fallback
                 c2.set("debug_force_lsd", 0)
                 res, st = c2.count_fasta(cfg(k, m, 3, B, 0), text)
-                assert_same(res.arrays(), want, "auto B=%d k=%d" % (B, k))          # (expanded once, sub-buckets by the top key bits: fkm_part.cuh)
+                assert_same(res.arrays(), want, "auto B=%d k=%d" % (B, k))          # expanded once, sub-buckets by the top key bits (fkm_part.cuh kernels)
                 assert (st["n_fallbacks"] > 0) == expect_fallback
+                c2.set("sort_partition", 2)                                        # the same sub-buckets, counted in ordered shared-memory tables
+                res, st = c2.count_fasta(cfg(k, m, 3, B, 0), text)                 # (or, when a key range is too dense for the table, by the kernels above)
+                assert_same(res.arrays(), want, "ordered tables B=%d k=%d" % (B, k))
+                c2.set("sort_partition", 1)
                 c2.set("debug_force_lsd", 1)
                 res, st = c2.count_fasta(cfg(k, m, 3, B, 0), text)
                 assert_same(res.arrays(), want, "lsd B=%d k=%d" % (B, k))
