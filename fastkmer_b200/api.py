@@ -92,6 +92,7 @@ def load_library():
         "fkm_device_free": (C.c_int, [vp, vp]),
         "fkm_debug_window_bins": (C.c_int, [vp, cfgp, vp, vp, u64, vp]),
         "fkm_record_bytes": (i32, [cfgp]),
+        "fkm_job_bins": (C.c_int, [vp, cfgp, u64, C.POINTER(i32)]),
         "fkm_mg_scan": (C.c_int, [vp, cfgp, vp, vp, u64, vp, vp]),
         "fkm_mg_scan_fasta": (C.c_int, [vp, cfgp, vp, u64, vp, vp, C.POINTER(u64)]),
         "fkm_mg_scatter": (C.c_int, [vp, vp, vp]),
@@ -357,9 +358,16 @@ class Context:
         _check(load_library().fkm_device_free(self._h, C.c_void_p(ptr)))
 
     # ---- staged entry points (multi-GPU; see fastkmer_b200/multigpu.py)
+    def job_bins(self, configuration, n_positions=0):
+        """Internal bins of a job on this context: the configuration's bins times the job's bin split (knob bin_split)."""
+        n = C.c_int32()
+        cfg = _cfg(configuration)
+        _check(load_library().fkm_job_bins(self._h, C.byref(cfg), n_positions, C.byref(n)))
+        return n.value
+
     def mg_scan(self, configuration, d_bases, d_inv, n_positions):
-        """-> (hist_rec, hist_kmer) uint64[b]: records / k-mers this shard puts into every bin."""
-        b = int(min(4 ** configuration.m, configuration.max_b))
+        """-> (hist_rec, hist_kmer) uint64[internal bins]: records / k-mers this shard puts into every (internal) bin."""
+        b = self.job_bins(configuration, n_positions)
         rec = np.zeros(b, dtype=np.uint64)
         kmer = np.zeros(b, dtype=np.uint64)
         cfg = _cfg(configuration)
@@ -369,7 +377,7 @@ class Context:
 
     def mg_scan_fasta(self, configuration, fasta):
         arr = np.frombuffer(fasta, dtype=np.uint8) if isinstance(fasta, (bytes, bytearray)) else fasta
-        b = int(min(4 ** configuration.m, configuration.max_b))
+        b = self.job_bins(configuration, arr.size)
         rec = np.zeros(b, dtype=np.uint64)
         kmer = np.zeros(b, dtype=np.uint64)
         nb = C.c_uint64()

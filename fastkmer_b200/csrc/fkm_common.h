@@ -21,6 +21,15 @@ FKM_HD uint32_t hash_to_bucket(uint32_t key, uint32_t B) {
     return (key & 0x7FFFFFFFu) % B;
 }
 
+// Internal bins.  When a bin would hold more k-mers than the partitioned count stage likes (very deep inputs, few bins, a rank
+// of a multi-GPU job that owns B/N bins of N times the data), every bin is cut into 2^split internal bins by a second hash of
+// the signature: a canonical k-mer has ONE signature, so all its occurrences still meet in one internal bin, and the
+// internal bins of a bin are consecutive, so the bin's entries stay contiguous in the (unordered) hash-path output.
+FKM_HD uint32_t split_bin(uint32_t sig, uint32_t B, int split) {
+    const uint32_t b = hash_to_bucket(sig, B);
+    return split ? (b << split) | ((sig * 0x9E3779B1u) >> (32 - split)) : b;
+}
+
 // splitmix64 step applied to a counter: the synthetic-data generator of SURVEY
 // §8(d) and the result digest use it (neither exists in the reference).
 FKM_HD uint64_t mix64(uint64_t x) {

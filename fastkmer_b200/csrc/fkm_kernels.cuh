@@ -71,7 +71,8 @@ struct ScanParams {
     uint64_t n_seg; uint32_t seg_len;   // segments of seg_len window ends (multiple of 32), one warp each
     int k, m, w;                    // w = k-m+1 m-mers per window
     int sh1[6];                     // shifts of the doubling levels of the signature window: w = 1 + sum(sh1), 0 = unused level
-    uint32_t B;
+    uint32_t B;                     // the configuration's bins (hash_to_bucket)
+    uint32_t Bi; int split;         // internal bins = B << split (fkm_common.h split_bin): what the histograms and the scatter index
     int cap;                        // max k-mers per record
     int wide;                       // record format (MODE 1 only)
     int smem_hist;                  // 1: per-CTA histogram in shared memory (B <= 4096)
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams P) {
     __shared__ uint32_t q_v[kScanThreads / 32][64];
     __shared__ uint32_t q_v2[DUAL ? kScanThreads / 32 : 1][64];
     uint32_t* s_hist_rec = reinterpret_cast<uint32_t*>(smem_raw);
-    uint32_t* s_hist_kmer = s_hist_rec + P.B;
+    uint32_t* s_hist_kmer = s_hist_rec + P.Bi;
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams P) {
     const uint32_t fsh = (2u * (31u - (uint32_t)lane)) & 31u;
 
     if (MODE == 0 && !DUAL && P.smem_hist) {
-        for (uint32_t b = threadIdx.x; b < P.B; b += kScanThreads) { s_hist_rec[b] = 0; s_hist_kmer[b] = 0; }
+        for (uint32_t b = threadIdx.x; b < P.Bi; b += kScanThreads) { s_hist_rec[b] = 0; s_hist_kmer[b] = 0; }
         __syncthreads();
     }
 
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams P) {
                 if (have) P.events[base + lane] = make_ulonglong2(rs, (unsigned long long)n | ((unsigned long long)v << 32));
             } else if (lane == 0) *P.ev_overflow = 1;
         }
-        const uint32_t bin = have ? hash_to_bucket(v, P.B) : 0u;
+        const uint32_t bin = have ? split_bin(v, P.B, P.split) : 0u;
         if (MODE == 0 && DUAL) {
             // every event goes to list 1 in lane order; the events of the sample bins (few) are appended to list 0 as well
             const uint32_t h16 = cell_hash16(v2);
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams P) {
 
     if (MODE == 0 && !DUAL && P.smem_hist) {
         __syncthreads();
-        for (uint32_t b = threadIdx.x; b < P.B; b += kScanThreads) {
+        for (uint32_t b = threadIdx.x; b < P.Bi; b += kScanThreads) {
             uint32_t r = s_hist_rec[b];
             if (r) { atomicAdd(&P.hist_rec[b], (unsigned long long)r); atomicAdd(&P.hist_kmer[b], (unsigned long long)s_hist_kmer[b]); }
         }
@@ -379,7 +380,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan(const ScanParams P) {
 struct ScatterParams {
     const ulonglong2* events; unsigned long long n_events;
     const uint64_t* bases; uint64_t n_words;
-    uint32_t B; int cap; int k;
+    uint32_t B; int split; int cap; int k;          // bin of an event = split_bin(signature, B, split)
     const unsigned long long* bin_base; void* records;
     unsigned long long* cursor; int cursor_shift;   // write cursor of bin b at cursor[b << cursor_shift]
 };
@@ -397,7 +398,7 @@ __global__ void __launch_bounds__(256) k_scatter_events(const ScatterParams P) {
     uint64_t w[NW];
 #pragma unroll
     for (int q = 0; q < NW; q++) w[q] = (j0 + q < P.n_words) ? P.bases[j0 + q] : 0ull;
-    const uint32_t bin = hash_to_bucket(v, P.B);
+    const uint32_t bin = split_bin(v, P.B, P.split);
     const uint32_t pieces = (n + (uint32_t)P.cap - 1) / (uint32_t)P.cap;
     const unsigned long long slot0 = P.bin_base[bin] + atomicAdd(&P.cursor[(size_t)bin << P.cursor_shift], (unsigned long long)pieces);
     {
@@ -771,6 +772,7 @@ struct CompactParams {
     int clear;                                             // 1: write EMPTY back into every occupied slot (table reusable without a memset)
     int* cap_overflow;                                     // set when the output arrays are too small
     unsigned long long* acc;                               // [3][64] digest accumulators (sum, xor, count), or NULL
+    int bin_shift;                                         // the digest's bin id = internal bin >> bin_shift
 };
 // table -> dense output, persistent grid-stride over 1024-slot tiles.  Order inside a bin
 // is slot order up to tile permutation (the reference's HT order is fastutil's iteration
@@ -843,7 +845,7 @@ __global__ void __launch_bounds__(256) k_compact_ht(const CompactParams P) {
         }
         __syncthreads();
         if (total == 0) continue;
-        const unsigned long long base = s_base; const uint32_t bin = (uint32_t)s_bin;
+        const unsigned long long base = s_base; const uint32_t bin = (uint32_t)s_bin >> P.bin_shift;
         if (base + total > P.out_cap) { if (threadIdx.x == 0) *P.cap_overflow = 1; continue; }
         // dense part: coalesced stores, every lane busy in the digest
         const uint64_t hbin = mix64((uint64_t)bin);
@@ -1288,6 +1290,7 @@ struct DigestParams {
     const void* keys; const uint32_t* cnt; const unsigned long long* out_base; int B;
     unsigned long long n; unsigned long long origin;  // entries in this chunk, global offset of its first entry
     unsigned long long* acc;                          // [3][64]: sum(h*cnt), xor(mix(h+cnt)), sum(cnt), spread over 64 slots
+    int bin_shift;                                    // bin id of an entry = internal bin >> bin_shift
 };
 template <bool WIDE>
 __global__ void __launch_bounds__(256) k_digest(const DigestParams P) {
@@ -1300,7 +1303,7 @@ __global__ void __launch_bounds__(256) k_digest(const DigestParams P) {
         if constexpr (!WIDE) { hi = 0; lo = reinterpret_cast<const uint64_t*>(P.keys)[i]; }
         else { key128 kk = reinterpret_cast<const key128*>(P.keys)[i]; hi = kk.hi; lo = kk.lo; }
         uint32_t n = P.cnt[i];
-        uint64_t h = entry_hash((uint32_t)bin, hi, lo);
+        uint64_t h = entry_hash((uint32_t)bin >> P.bin_shift, hi, lo);
         s += h * (uint64_t)n; x ^= mix64(h + n); c += n;
     }
 #pragma unroll

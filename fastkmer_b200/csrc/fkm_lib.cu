@@ -107,6 +107,9 @@ struct fkm_ctx {
     double smem_slow_slots = 1048576.0;   // slots of every CTA's private global table (slow path of k_count_smem)
     double smem_fill = 0.6;           // share of the table's capacity the planner aims at
     double part_fill = 0.45;          // partitioned count path (count_mode 2): distinct k-mers per sub-bucket as a share of the table's slots
+    double bin_split = 0.0;           // internal bins per bin (hash path, count_mode 0 or 2): 0 = chosen from the input size, else a power of two (a multi-GPU job sets the same value on every rank)
+    int job_split = 0;                // log2 of the internal bins per bin of the job in progress (fkm_common.h split_bin)
+    double part_max_subs = 320.0;     // ... sub-buckets a bin may need before the job is left to the global-table pipeline
     double part_budget_keys = 1024.0 * 1048576.0;   // ... k-mers per batch of bins (the key buffer holds one batch)
     std::vector<cudaEvent_t> evpool;  // ... per-batch timing events
     double async_table_bytes = 1024.0 * (1 << 20); // tables of one asynchronous batch; 0 disables the asynchronous phase (0.25-16 GB all within 8 %, profiles/r1_table_sweep.txt)
@@ -193,6 +196,8 @@ extern "C" int fkm_ctx_set(fkm_ctx* c, const char* name, double v) {
     else if (!strcmp(name, "smem_slow_slots")) c->smem_slow_slots = v;
     else if (!strcmp(name, "smem_fill")) c->smem_fill = v;
     else if (!strcmp(name, "part_fill")) c->part_fill = v;
+    else if (!strcmp(name, "bin_split")) c->bin_split = v;
+    else if (!strcmp(name, "part_max_subs")) c->part_max_subs = v;
     else if (!strcmp(name, "sort_partition")) c->sort_partition = v;
     else if (!strcmp(name, "part_budget_keys")) c->part_budget_keys = v;
     else if (!strcmp(name, "fold_records")) c->fold_records = v;
@@ -214,6 +219,7 @@ static int job_begin(fkm_ctx* ctx) {
     CK(ctx->arena.reset());
     ctx->gen++;
     ctx->job_launches = 0;
+    ctx->job_split = 0;
     return FKM_OK;
 }
 
@@ -225,6 +231,23 @@ static int validate(const fkm_config* cfg, int32_t* B) {
     if (!cfg->use_ht && cfg->x < 1) return fkm_set_error(FKM_EINVAL, "x=%d: the reference's sort path fails for x < 1 (SBKC:495-508)", cfg->x);
     int64_t b = std::min<int64_t>((int64_t)1 << (2 * cfg->m), (int64_t)cfg->max_b);     // TCFG:32
     *B = (int32_t)b;
+    return FKM_OK;
+}
+
+// log2 of the internal bins every bin is cut into for this job (fkm_common.h split_bin).  Only the hash path with its own
+// partition levels uses them (the sort path's output is ordered inside a bin; the dual-minimizer mode has its cells).
+static int choose_split(const fkm_ctx* ctx, const fkm_config* cfg, int32_t B, uint64_t n_pos_hint) {
+    if (!cfg->use_ht || (ctx->count_mode >= 1.0 && ctx->count_mode < 2.0)) return 0;
+    int s = 0;
+    if (ctx->bin_split >= 1.0) { while ((1 << (s + 1)) <= (int)ctx->bin_split && s < 6) s++; }
+    else { const double per_bin = (double)n_pos_hint / (double)B; while (per_bin / (double)(1 << s) > 6.0e6 && s < 6) s++; }
+    while (s > 0 && ((int64_t)B << s) > 65536) s--;
+    return s;
+}
+extern "C" int fkm_job_bins(fkm_ctx* ctx, const fkm_config* cfg, uint64_t n_positions, int32_t* bins) {
+    if (!ctx || !bins) return fkm_set_error(FKM_EINVAL, "null argument");
+    int32_t B = 0; int rc = validate(cfg, &B); if (rc) return rc;
+    *bins = B << choose_split(ctx, cfg, B, n_positions);
     return FKM_OK;
 }
 
@@ -296,7 +319,7 @@ static int scan_setup(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const void
     P.seg_len = 4096;
     P.e_total = (MODE == 2) ? n_pos + (uint64_t)cfg->k - 1 : n_pos;
     P.n_seg = (P.e_total + P.seg_len - 1) / P.seg_len;
-    P.B = (uint32_t)B;
+    P.Bi = (uint32_t)B; P.split = ctx->job_split; P.B = (uint32_t)B >> ctx->job_split;      // B counts internal bins here
     P.wide = cfg->k > 32;
     P.cap = (cfg->k > 32) ? (125 - cfg->k) : (61 - cfg->k);
     P.smem_hist = (MODE == 0 && !DUAL && B <= kSmemHistMaxB) ? 1 : 0;
@@ -473,7 +496,7 @@ static int stage_scatter(fkm_ctx* ctx, ScanState* S, const unsigned long long* d
         if (!C.ev_ovf) {
             ScatterParams Q;
             Q.events = C.d_events; Q.n_events = C.n_events; Q.bases = (const uint64_t*)C.d_bases; Q.n_words = (C.n_pos + 31) / 32;
-            Q.B = (uint32_t)S->B; Q.cap = wide ? (125 - cfg->k) : (61 - cfg->k); Q.k = cfg->k;
+            Q.B = (uint32_t)S->B >> ctx->job_split; Q.split = ctx->job_split; Q.cap = wide ? (125 - cfg->k) : (61 - cfg->k); Q.k = cfg->k;
             Q.bin_base = d_bin_base; Q.cursor = d_cursor; Q.cursor_shift = cursor_shift; Q.records = d_records;
             if (C.n_events) {
                 const unsigned grid = (unsigned)((C.n_events + 255) / 256);
@@ -630,7 +653,7 @@ static int count_partitioned(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, con
                 Q.out_keys = ok[i - b0]; Q.out_cnt = oc[i - b0]; Q.region_cap = bt.region_cap; Q.cta_total = d_cta_total + (i - b0) * grid;
                 Q.bin_cta = d_bin_cta; Q.bin_off = d_bin_off; Q.acc = d_acc; Q.cap_slots = cap; Q.max_fill = cap * 3 / 4;
                 Q.slow_keys = d_slow_keys; Q.slow_cnt = d_slow_cnt; Q.slow_slots = slow_slots; Q.slow_max_fill = slow_slots * 7 / 10; Q.flags = d_flags; Q.counters = d_counters;
-                Q.k = cfg->k; Q.tail_slots = tail;
+                Q.k = cfg->k; Q.tail_slots = tail; Q.bin_shift = ctx->job_split;
                 if (ordered) k_count_keys_ordered<WIDE><<<grid, kKcThreads, kc_smem, s>>>(Q); else k_count_keys<WIDE><<<grid, kKcThreads, kc_smem, s>>>(Q);
                 CKL();
             } else CK(cudaEventRecord(ctx->evpool[3 * (i - b0) + 1], s));
@@ -689,7 +712,13 @@ static int count_partitioned(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, con
         if (km_a > 100000) rho = std::min(1.0, (double)out_total / (double)km_a);
         rho *= ctx->debug_rho_scale;
         const size_t b0 = batches.size();
-        plan(s_hi, B, std::min(1.0, rho * 1.1 + 0.01), rho, false);
+        const double rho_plan = std::min(1.0, rho * 1.1 + 0.01);
+        // A tile's k-mers spread over all sub-buckets of its bin: beyond a few hundred sub-buckets the runs k_place_keys writes
+        // shrink to a few keys and the per-(tile, sub-bucket) matrices outgrow the keys (8-GPU weak scaling, 23 M k-mers per
+        // bin: partition 186 ms instead of 57).  Such bins are left to the global-table pipeline.
+        for (int b = s_hi; b < B; b++)
+            if ((double)h_kmer[(size_t)b] * rho_plan / d_target > ctx->part_max_subs) return kRetryGlobal;
+        plan(s_hi, B, rho_plan, rho, false);
         rc = run(b0, batches.size()); if (rc) return rc;
     }
     res->out_base[(size_t)B] = out_total;
@@ -851,7 +880,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
                         CompactParams Q;
                         Q.table = d_ftab; Q.n_slots = fb.slots; Q.tbl_base = d_ftb + fb.tb_idx; Q.n_bins = fb.hi - fb.lo; Q.bin_lo = fb.lo;
                         Q.out_base = d_fbase; Q.out_cursor = d_fcursor; Q.out_origin = 0; Q.out_cap = n_rec;
-                        Q.out_keys = d_frec; Q.out_cnt = d_fwt; Q.clear = 1; Q.cap_overflow = d_ovf + 1; Q.acc = nullptr;
+                        Q.out_keys = d_frec; Q.out_cnt = d_fwt; Q.clear = 1; Q.cap_overflow = d_ovf + 1; Q.acc = nullptr; Q.bin_shift = 0;
                         const unsigned grid = (unsigned)std::min<uint64_t>((fb.slots + 1023) / 1024, compact_grid<true>(ctx));
                         k_compact_ht<true><<<grid, 256, 0, s>>>(Q); CKLC();
                     }
@@ -971,7 +1000,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
                         CompactParams Q;
                         Q.table = d_table; Q.n_slots = slots; Q.tbl_base = d_tbl_base; Q.n_bins = hi - lo; Q.bin_lo = lo;
                         Q.out_base = d_out_base; Q.out_cursor = d_cursor; Q.out_origin = out_total; Q.out_cap = batch_total;
-                        Q.out_keys = ch.keys; Q.out_cnt = ch.cnt; Q.clear = 0; Q.cap_overflow = d_ovf + 1; Q.acc = d_acc;
+                        Q.out_keys = ch.keys; Q.out_cnt = ch.cnt; Q.clear = 0; Q.cap_overflow = d_ovf + 1; Q.acc = d_acc; Q.bin_shift = ctx->job_split;
                         CKC(cudaMemsetAsync(d_cursor + lo, 0, (size_t)(hi - lo) * 8, s));
                         CKC(cudaEventRecord(ctx->ev[6], s));
                         const unsigned grid = (unsigned)std::min<uint64_t>((slots + 1023) / 1024, compact_grid<WIDE>(ctx));
@@ -1046,7 +1075,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
                     CompactParams Q;
                     Q.table = d_tab; Q.n_slots = bt.slots; Q.tbl_base = d_tb_all + bt.tb_idx; Q.n_bins = bt.hi - bt.lo; Q.bin_lo = bt.lo;
                     Q.out_base = d_out_base; Q.out_cursor = d_cursor; Q.out_origin = out_total; Q.out_cap = out_cap;
-                    Q.out_keys = ch.keys; Q.out_cnt = ch.cnt; Q.clear = 1; Q.cap_overflow = d_ovf + 1; Q.acc = d_acc;
+                    Q.out_keys = ch.keys; Q.out_cnt = ch.cnt; Q.clear = 1; Q.cap_overflow = d_ovf + 1; Q.acc = d_acc; Q.bin_shift = ctx->job_split;
                     const unsigned grid = (unsigned)std::min<uint64_t>((bt.slots + 1023) / 1024, compact_grid<WIDE>(ctx));
                     k_compact_ht<WIDE><<<grid, 256, 0, s>>>(Q); CKLC();
                 }
@@ -1341,7 +1370,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
         for (const Chunk& ch : res->chunks) {
             if (!ch.n) continue;
             DigestParams D;
-            D.keys = ch.keys; D.cnt = ch.cnt; D.out_base = d_out_base; D.B = B; D.n = ch.n; D.origin = origin; D.acc = d_acc;
+            D.keys = ch.keys; D.cnt = ch.cnt; D.out_base = d_out_base; D.B = B; D.n = ch.n; D.origin = origin; D.acc = d_acc; D.bin_shift = ctx->job_split;
             int grid = (int)std::min<uint64_t>((ch.n + 255) / 256, (uint64_t)ctx->n_sm * 8);
             k_digest<WIDE><<<grid, 256, 0, s>>>(D); CKLC();
             origin += ch.n;
@@ -1571,6 +1600,10 @@ static int count_device(fkm_ctx* ctx, const fkm_config* cfg, const void* d_bases
     int32_t B = 0; int rc = validate(cfg, &B); if (rc) return rc;
     if (!ctx) return fkm_set_error(FKM_EINVAL, "ctx is NULL");
     CK(cudaSetDevice(ctx->device));
+    // internal bins (fkm_common.h split_bin): chosen here unless the job's scan has already run with its choice
+    const int32_t B_user = B;
+    if (!pre && !scanned) ctx->job_split = choose_split(ctx, cfg, B, n_pos);
+    B = B_user << ctx->job_split;
     fkm_stats local; fkm_stats* st = stats ? stats : &local;
     const uint64_t keep_h2d = st->h2d_bytes, keep_bases = st->n_bases; const double keep_ms0 = st->ms_stage[0];
     memset(st, 0, sizeof *st);
@@ -1623,6 +1656,14 @@ static int count_device(fkm_ctx* ctx, const fkm_config* cfg, const void* d_bases
     st->gpu_launches = ctx->job_launches;       // everything since job_begin (ingest included)
     st->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (rc) { fkm_result_free(res); return rc; }
+    if (ctx->job_split) {                       // the caller sees the configuration's bins: internal bin b << split is where bin b begins
+        std::vector<uint64_t> ob((size_t)B_user + 1);
+        for (int32_t b = 0; b <= B_user; b++) ob[(size_t)b] = res->out_base[(size_t)b << ctx->job_split];
+        res->out_base.swap(ob); res->B = B_user;
+        uint64_t nonempty = 0;
+        for (int32_t b = 0; b < B_user; b++) nonempty += res->out_base[(size_t)b + 1] > res->out_base[(size_t)b] ? 1 : 0;
+        st->n_nonempty_bins = nonempty;
+    }
     if (out) *out = res; else fkm_result_free(res);
     return FKM_OK;
 }
@@ -1779,7 +1820,8 @@ extern "C" int fkm_count_fasta(fkm_ctx* ctx, const fkm_config* cfg, const uint8_
     fkm_stats local; fkm_stats* st = stats ? stats : &local;
     memset(st, 0, sizeof *st);
     ScanState S; uint64_t n_bases = 0;
-    rc = front_end_fasta(ctx, cfg, B, fasta, n_bytes, &S, &n_bases, want_smem_path(ctx, cfg)); if (rc) return rc;
+    ctx->job_split = choose_split(ctx, cfg, B, n_bytes);
+    rc = front_end_fasta(ctx, cfg, B << ctx->job_split, fasta, n_bytes, &S, &n_bases, want_smem_path(ctx, cfg)); if (rc) return rc;
     fkm_stats tmp; memset(&tmp, 0, sizeof tmp);
     rc = scan_end(ctx, &S, &tmp); if (rc) return rc;
     const double ms_in = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -1844,6 +1886,8 @@ extern "C" int fkm_mg_scan(fkm_ctx* ctx, const fkm_config* cfg, const void* d_ba
     if (!ctx->mg_scan) ctx->mg_scan = new ScanState();
     ctx->mg_scan->valid = false;
     fkm_stats st; memset(&st, 0, sizeof st);
+    ctx->job_split = choose_split(ctx, cfg, B, n_pos);
+    B <<= ctx->job_split;                        // the histograms are per INTERNAL bin (fkm_job_bins entries)
     rc = stage_scan(ctx, cfg, B, d_bases, d_inv, n_pos, ctx->mg_scan, &st); if (rc) return rc;
     for (int b = 0; b < B; b++) { hist_rec[b] = ctx->mg_scan->h_rec[(size_t)b]; hist_kmer[b] = ctx->mg_scan->h_kmer[(size_t)b]; }
     return FKM_OK;
@@ -1857,6 +1901,8 @@ extern "C" int fkm_mg_scan_fasta(fkm_ctx* ctx, const fkm_config* cfg, const uint
     rc = job_begin(ctx); if (rc) return rc;
     if (!ctx->mg_scan) ctx->mg_scan = new ScanState();
     uint64_t nb = 0;
+    ctx->job_split = choose_split(ctx, cfg, B, n_bytes);
+    B <<= ctx->job_split;                        // the histograms are per INTERNAL bin (fkm_job_bins entries)
     rc = front_end_fasta(ctx, cfg, B, fasta, n_bytes, ctx->mg_scan, &nb, false); if (rc) return rc;
     if (n_bases) *n_bases = nb;
     fkm_stats st; memset(&st, 0, sizeof st);

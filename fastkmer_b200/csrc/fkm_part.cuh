@@ -364,6 +364,7 @@ struct KeyCountParams {
     unsigned long long* counters;               // [0] sub-buckets that took the slow path
     int k;                                      // k_count_keys_ordered: k-mer length (the slot is cut from the k-mer's top bits)
     uint32_t tail_slots;                        // k_count_keys_ordered: slots behind cap_slots (its probing never wraps around)
+    int bin_shift;                              // the digest's bin id = internal bin >> bin_shift
 };
 
 static constexpr int kKcThreads = 1024;
@@ -514,7 +515,7 @@ __global__ void __launch_bounds__(kKcThreads, 1) k_count_keys(const KeyCountPara
         const bool skip = off + D > P.region_cap;
         if (skip) out_full = true;
         // the claimed slots leave in claim order (dense, every lane busy) and are emptied; the slow path scans its global table
-        const uint64_t hbin = mix64((uint64_t)bin);
+        const uint64_t hbin = mix64((uint64_t)(bin >> P.bin_shift));
         const uint64_t hpre = mix64(hbin);                   // entry_hash's inner term when hi == 0 (64-bit keys)
         auto emit = [&](unsigned long long o, Key kk, uint32_t n) { if (!skip) { okeys[o] = kk; ocnt[o] = n; } };
         if (!slow) {
@@ -697,7 +698,7 @@ __global__ void __launch_bounds__(kKcThreads, 1) k_count_keys_ordered(const KeyC
         for (int i = 0; i < kKcThreads / 32; i++) { const unsigned int t = s_wsum[i]; if (i < warp) wb += t; D += t; }
         const bool skip = off + D > P.region_cap;
         if (skip) out_full = true;
-        const uint64_t hbin = mix64((uint64_t)bin);
+        const uint64_t hbin = mix64((uint64_t)(bin >> P.bin_shift));
         const uint64_t hpre = mix64(hbin);
         unsigned long long o = off + wb + incl - c;
         for (uint32_t sl = s_lo; sl < s_hi; sl++) {

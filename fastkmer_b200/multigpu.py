@@ -34,14 +34,21 @@ def assign_owners(bin_kmers, world):
     return owner
 
 
-def plan_exchange(H_rec, H_kmer, rank, world, owner=None):
+def plan_exchange(H_rec, H_kmer, rank, world, owner=None, split=1):
     """H_rec, H_kmer: [world, B] records / k-mers every rank puts into every bin.  owner: a fixed bin -> GPU map
     (jobs that must agree on the ownership, e.g. the samples of a distance job); default LPT on this job's histogram.
+    split: B counts INTERNAL bins, `split` consecutive ones per bin of the configuration (fkm_job_bins); a bin's
+    internal bins always share an owner.
     -> dict with everything rank `rank` needs for steps 4-7.  Array arithmetic only (no loop over bins x ranks)."""
     H_rec = np.asarray(H_rec, dtype=np.uint64)
     H_kmer = np.asarray(H_kmer, dtype=np.uint64)
     B = H_rec.shape[1]
-    owner = assign_owners(H_kmer.sum(axis=0), world) if owner is None else np.asarray(owner, dtype=np.int32)
+    if owner is None:
+        owner = np.repeat(assign_owners(H_kmer.sum(axis=0).reshape(B // split, split).sum(axis=1, dtype=np.uint64), world), split)
+    else:
+        owner = np.asarray(owner, dtype=np.int32)
+        if owner.size * split == B and split > 1:
+            owner = np.repeat(owner, split)
     # send buffer: bins ordered by (owner, bin)
     order = np.lexsort((np.arange(B), owner))
     mine = H_rec[rank]
@@ -99,6 +106,14 @@ class ShardedJob:
         self.fixed_owner = None           # set to a bin -> GPU map to override the per-job LPT assignment
         self.last_plan = None
         self.last_exchange_ms = 0.0
+        # A rank owns 1/world of the bins but receives them from every rank: the hash path cuts every bin into `world` (rounded up
+        # to a power of two) internal bins, so that a bin of this job is as large as a bin of a one-GPU job of the same shard
+        # size.  Same value on every rank (the histograms that are exchanged are per internal bin).
+        self.split = 1
+        if configuration.useHT:
+            while self.split < world and self.split < 64:
+                self.split *= 2
+            ctx.set("bin_split", self.split)
 
     def count_packed_device(self, d_bases, d_inv, n_positions, want_result=False):
         rec, kmer = self.ctx.mg_scan(self.cfg, d_bases, d_inv, n_positions)
@@ -115,12 +130,13 @@ class ShardedJob:
 
     def _exchange_and_count(self, rec, kmer, want_result):
         torch, dist = self.torch, self.dist
-        B = rec.size
+        B = rec.size                                                  # internal bins (fkm_job_bins)
+        split = B // self.cfg.b
         mine = torch.from_numpy(np.concatenate([rec, kmer]).astype(np.int64)).cuda()
         allh = torch.empty(self.world * 2 * B, dtype=torch.int64, device="cuda")
         dist.all_gather_into_tensor(allh, mine)
         allh = allh.cpu().numpy().reshape(self.world, 2, B).astype(np.uint64)
-        plan = plan_exchange(allh[:, 0, :], allh[:, 1, :], self.rank, self.world, owner=self.fixed_owner)
+        plan = plan_exchange(allh[:, 0, :], allh[:, 1, :], self.rank, self.world, owner=self.fixed_owner, split=split)
         self.last_plan = plan
         send = torch.empty((max(plan["n_send"], 1), self.rec_bytes), dtype=torch.uint8, device="cuda")
         self.ctx.mg_scatter(plan["send_base"], send.data_ptr())

@@ -189,8 +189,12 @@ int  fkm_device_free(fkm_ctx* ctx, void* d_ptr);
  *                   moves to record offset seg_dst[i] of a bin-major buffer (returned in d_out,
  *                   owned by the context until its next job).
  *   fkm_mg_count    count the bins this rank owns: bin_rec / bin_kmer [b] = records and k-mers
- *                   of bin b in d_records (0 for bins owned elsewhere).                        */
+ *                   of bin b in d_records (0 for bins owned elsewhere).
+ * "b" above is the job's number of INTERNAL bins, fkm_job_bins(): for deep inputs the hash path cuts every bin of the
+ * configuration into 2^j internal bins by a second hash of the signature (all internal bins of a bin are consecutive
+ * and must have one owner); knob "bin_split" fixes 2^j, and every rank of a job must use the same value.            */
 int32_t fkm_record_bytes(const fkm_config* cfg);
+int  fkm_job_bins(fkm_ctx* ctx, const fkm_config* cfg, uint64_t n_positions, int32_t* bins);
 int  fkm_mg_scan(fkm_ctx* ctx, const fkm_config* cfg, const void* d_bases, const void* d_invalid, uint64_t n_positions,
                  uint64_t* hist_rec, uint64_t* hist_kmer);
 /* fkm_mg_scan on FASTA text in host memory (copied to the GPU and parsed there) */

@@ -7,13 +7,14 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--reads", type=int, default=50_000_000)
 ap.add_argument("--k", type=int, default=28)
 ap.add_argument("--m", type=int, default=10)
+ap.add_argument("--B", type=int, default=2048)
 ap.add_argument("--set", action="append", default=[])
 ap.add_argument("--sweep", default="")          # e.g. smem_fill=0.3,0.45,0.6
 args = ap.parse_args()
 ctx = fk.Context(0)
 spec = dict(seeds=(2001, 2002, 2003), genome_len=args.reads * 150 // 30, n_reads=args.reads, read_len=150)
 d_b, d_i, n_pos = ctx.synth_packed_device(spec)
-cfg = fk.TestConfiguration("", "", args.k, args.m, 3, max_b=2048, useHT=True, write=False)
+cfg = fk.TestConfiguration("", "", args.k, args.m, 3, max_b=args.B, useHT=True, write=False)
 for kv in args.set:
     n, v = kv.split("="); ctx.set(n, float(v))
 name, vals = (args.sweep.split("=") + [""])[:2] if args.sweep else ("", "")

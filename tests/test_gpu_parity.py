@@ -356,6 +356,36 @@ def test_smem_and_global_tables_agree_at_scale(ctx, mode):
         ctx.free_device(d_i)
 
 
+def test_internal_bins(oracle):
+    """Deep inputs / multi-GPU ranks cut every bin into 2^j internal bins by a second hash of the signature (knob bin_split; chosen
+    from the input size otherwise): same (bin, k-mer, count) as the oracle, the configuration's bins outside, on the hash path with
+    shared-memory and with global-memory tables; the sort path and the dual-minimizer mode ignore the knob."""
+    deep = fk.synth_fasta(dict(seeds=(81, 82, 83), genome_len=60000, n_reads=40000, read_len=100)).tobytes()
+    flat = fk.synth_fasta(dict(seeds=(84, 85, 86), genome_len=20000000, n_reads=30000, read_len=150)).tobytes()
+    c2 = fk.Context(0)
+    try:
+        for text, label in ((deep, "deep"), (flat, "flat")):
+            for k, m, B in ((28, 10, 2048), (55, 13, 300), (31, 11, 1), (12, 4, 100)):
+                want = oracle.count(text, k, m, 3, B, 1, threads=8)
+                for mode in (2, 0, 1):
+                    c2.set("count_mode", mode)
+                    for split in (4, 64, 1):
+                        c2.set("bin_split", split)
+                        res, st = c2.count_fasta(cfg(k, m, 3, B, 1), text)
+                        what = "%s k=%d B=%d mode %d split %d" % (label, k, B, mode, split)
+                        assert_same(res.sorted_arrays(), want, what)
+                        assert (st["digest_sum"], st["digest_xor"], st["n_nonempty_bins"]) == \
+                               (want["stats"]["digest_sum"], want["stats"]["digest_xor"], np.unique(want["bin"]).size), what
+                        a = res.arrays()
+                        assert np.all(np.diff(a["bin"]) >= 0), what              # a bin's entries are contiguous
+                c2.set("count_mode", 2)
+                c2.set("bin_split", 8)
+                res, st = c2.count_fasta(cfg(k, m, 3, B, 0), text)               # sort path: one ascending list per bin
+                assert_same(res.arrays(), oracle.count(text, k, m, 3, B, 0, threads=8), "sort path ignores bin_split")
+    finally:
+        c2.close()
+
+
 # ---------------------------------------------------------------- the drop-in call and its files
 def test_record_folding_gives_identical_counts(oracle):
     """fold_records=1 (hash path, k <= 32): identical super-k-mer records, either strand, are folded into one

@@ -26,6 +26,26 @@ def test_assign_owners_is_lpt_and_deterministic():
     assert l8.max() / l8.mean() < 1.01                       # LPT balances 2048 bins over 8 GPUs to < 1 %
 
 
+def test_internal_bins_share_an_owner():
+    """A job with internal bins (fkm_job_bins: `split` consecutive internal bins per bin of the configuration) exchanges per-internal-bin
+    histograms; ownership is decided per bin of the configuration, by LPT over the bins' totals."""
+    rng = np.random.default_rng(5)
+    G, B, split = 4, 96, 8
+    Hr = rng.integers(0, 50, (G, B * split))
+    Hk = Hr * rng.integers(1, 30, (G, B * split))
+    plans = [mg.plan_exchange(Hr, Hk, r, G, split=split) for r in range(G)]
+    owner = plans[0]["owner"]
+    assert owner.shape == (B * split,) and all((p["owner"] == owner).all() for p in plans)
+    assert (owner.reshape(B, split) == owner.reshape(B, split)[:, :1]).all()          # one owner per bin
+    assert owner.reshape(B, split)[:, 0].tolist() == mg.assign_owners(Hk.sum(axis=0).reshape(B, split).sum(axis=1), G).tolist()
+    for r, p in enumerate(plans):                                                     # what r sends to g is what g expects from r
+        for g in range(G):
+            assert p["send_splits"][g] == plans[g]["recv_splits"][r]
+        assert p["bin_rec"].sum() == Hr[:, owner == r].sum()
+    fixed = np.arange(B, dtype=np.int32) % G                                          # a fixed per-bin map is expanded the same way
+    assert (mg.plan_exchange(Hr, Hk, 0, G, owner=fixed, split=split)["owner"] == np.repeat(fixed, split)).all()
+
+
 def test_plan_is_consistent_across_ranks():
     rng = np.random.default_rng(3)
     for G, B in ((2, 64), (3, 17), (8, 2048)):
