@@ -109,7 +109,7 @@ struct fkm_ctx {
     double part_fill = 0.45;          // partitioned count path (count_mode 2): distinct k-mers per sub-bucket as a share of the table's slots
     double bin_split = 0.0;           // internal bins per bin (hash path, count_mode 0 or 2): 0 = chosen from the input size, else a power of two (a multi-GPU job sets the same value on every rank)
     int job_split = 0;                // log2 of the internal bins per bin of the job in progress (fkm_common.h split_bin)
-    double part_max_subs = 320.0;     // ... sub-buckets a bin may need before the job is left to the global-table pipeline
+    double part_max_subs = 768.0;     // ... sub-buckets a bin may need before the job is left to the global-table pipeline
     double part_budget_keys = 1024.0 * 1048576.0;   // ... k-mers per batch of bins (the key buffer holds one batch)
     std::vector<cudaEvent_t> evpool;  // ... per-batch timing events
     double async_table_bytes = 1024.0 * (1 << 20); // tables of one asynchronous batch; 0 disables the asynchronous phase (0.25-16 GB all within 8 %, profiles/r1_table_sweep.txt)
@@ -532,7 +532,11 @@ static int count_partitioned(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, con
     cudaStream_t s = ctx->stream;
     constexpr uint64_t TR = PartGeom<WIDE>::kTileRecs;
     // ordered (sort path): the sub-buckets of a bin are 2^j key ranges and k_count_keys_ordered's table keeps the k-mers in order
-    for (int b = 0; b < B; b++) if (h_kmer[(size_t)b] >= 0xFFFFFFF0ull) return kRetryGlobal;
+    auto retry = [&](const char* why, long long a = 0, long long b2 = 0) -> int {
+        if (getenv("FKM_TRACE")) fprintf(stderr, "[fkm trace] partitioned count stage gives up: %s (%lld, %lld)\n", why, a, b2);
+        return kRetryGlobal;
+    };
+    for (int b = 0; b < B; b++) if (h_kmer[(size_t)b] >= 0xFFFFFFF0ull) return retry("a bin of 2^32 k-mers", b);
     // geometry of k_count_keys's table
     uint32_t cap = WIDE ? 8192u : 16384u;
     while (cap > 64u && (size_t)cap * (sizeof(Key) + 6) + 2048 > ctx->smem_optin) cap >>= 1;
@@ -674,7 +678,7 @@ static int count_partitioned(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, con
             ms_part += a; ms_count += c;
         }
         if (flags[2]) return fkm_set_error(FKM_EOVERFLOW, "a k-mer occurs more than 2^32-1 times: 32-bit counts overflow (the reference counts in Int, SBKC:562,676)");
-        if (flags[0] || flags[1]) return kRetryGlobal;
+        if (flags[0] || flags[1]) return retry(flags[0] ? "a table overflowed on the slow path too" : "an output region was too small", flags[0], flags[1]);
         // one result chunk per CTA region; a bin's entries begin in the region of the CTA that counted its first sub-bucket
         for (size_t i = b0; i < b1; i++) {
             const Batch& bt = batches[i];
@@ -717,7 +721,7 @@ static int count_partitioned(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, con
         // shrink to a few keys and the per-(tile, sub-bucket) matrices outgrow the keys (8-GPU weak scaling, 23 M k-mers per
         // bin: partition 186 ms instead of 57).  Such bins are left to the global-table pipeline.
         for (int b = s_hi; b < B; b++)
-            if ((double)h_kmer[(size_t)b] * rho_plan / d_target > ctx->part_max_subs) return kRetryGlobal;
+            if ((double)h_kmer[(size_t)b] * rho_plan / d_target > ctx->part_max_subs) return retry("a bin needs too many sub-buckets", b, (long long)h_kmer[(size_t)b]);
         plan(s_hi, B, rho_plan, rho, false);
         rc = run(b0, batches.size()); if (rc) return rc;
     }
