@@ -70,6 +70,7 @@ def load_library():
         "fkm_ctx_set": (C.c_int, [vp, C.c_char_p, C.c_double]),
         "fkm_derive": (C.c_int, [cfgp, C.POINTER(i32), C.c_char_p, C.c_size_t]),
         "fkm_execute_job": (C.c_int, [vp, cfgp, stp]),
+        "fkm_execute_job_multi": (C.c_int, [vp, i32, cfgp, stp]),
         "fkm_count_fasta": (C.c_int, [vp, cfgp, vp, u64, C.POINTER(vp), stp]),
         "fkm_count_packed_host": (C.c_int, [vp, cfgp, vp, vp, u64, C.POINTER(vp), stp]),
         "fkm_count_packed_device": (C.c_int, [vp, cfgp, vp, vp, u64, C.POINTER(vp), stp]),
@@ -312,6 +313,15 @@ class Context:
         st = fkm_stats()
         cfg = _cfg(configuration)
         _check(load_library().fkm_execute_job(self._h, C.byref(cfg), C.byref(st)))
+        return _stats(st)
+
+    @staticmethod
+    def execute_job_multi(configuration, devices) -> Stats:
+        """The drop-in call on several GPUs of this node (fkm_execute_job_multi): no context needed, the library makes its own."""
+        st = fkm_stats()
+        cfg = _cfg(configuration)
+        dev = (C.c_int32 * len(devices))(*devices)
+        _check(load_library().fkm_execute_job_multi(dev, len(devices), C.byref(cfg), C.byref(st)))
         return _stats(st)
 
     # ---- in-memory variants

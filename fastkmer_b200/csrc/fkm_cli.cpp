@@ -25,10 +25,19 @@ int main(int argc, char** argv) {
         if (argc < 14) { fprintf(stderr, "numPartitionTasks missing\n"); return 2; }
         c.num_partition_tasks = atoi(argv[13]);
     }
+    // FKM_GPUS=N: the job runs on GPUs 0..N-1 of this node (the reference spreads it over its Spark executors)
+    const int n_gpus = getenv("FKM_GPUS") ? atoi(getenv("FKM_GPUS")) : 1;
     fkm_ctx* ctx = nullptr;
-    if (fkm_ctx_create(-1, nullptr, &ctx) != FKM_OK) { fprintf(stderr, "fastkmer_cli: %s\n", fkm_last_error()); return 1; }
     fkm_stats st;
-    int rc = fkm_execute_job(ctx, &c, &st);
+    int rc;
+    if (n_gpus > 1) {
+        int32_t dev[64];
+        for (int i = 0; i < n_gpus && i < 64; i++) dev[i] = i;
+        rc = fkm_execute_job_multi(dev, n_gpus < 64 ? n_gpus : 64, &c, &st);
+    } else {
+        if (fkm_ctx_create(-1, nullptr, &ctx) != FKM_OK) { fprintf(stderr, "fastkmer_cli: %s\n", fkm_last_error()); return 1; }
+        rc = fkm_execute_job(ctx, &c, &st);
+    }
     if (rc != FKM_OK) { fprintf(stderr, "fastkmer_cli: %s\n", fkm_last_error()); fkm_ctx_destroy(ctx); return 1; }
     char dir[4096]; int32_t b = 0;
     fkm_derive(&c, &b, dir, sizeof dir);

@@ -1963,6 +1963,180 @@ extern "C" int fkm_mg_count(fkm_ctx* ctx, const fkm_config* cfg, const void* d_r
     return count_device(ctx, cfg, nullptr, nullptr, 0, out, stats, &pre);
 }
 
+// ------------------------------------------------------------------ N GPUs of one node behind the drop-in call
+// The multi-GPU job of fastkmer_b200/multigpu.py without Python or NCCL: one host thread per GPU, the bin exchange as
+// peer-to-peer copies over NVLink (cudaMemcpyPeerAsync).  Replaces Spark's shuffle between the executors of one job
+// (reduceByKey, SBKC:1035,1042, optionally behind MultiprocessorSchedulingPartitioner, MSP:35-69):
+//   1. the FASTA text is cut at record boundaries into one byte range per GPU; every GPU parses and scans its range
+//   2. the per-bin histograms meet on the host; bins go to GPUs by LPT over the exact k-mer counts (the role of MSP:35-69)
+//   3. every GPU writes its records owner-major, the GPUs copy each other's blocks, regroup them bin-major
+//   4. every GPU counts the bins it owns and writes their files
+#include <thread>
+namespace {
+struct MultiPlan {                              // the part of multigpu.plan_exchange() rank r needs
+    std::vector<uint64_t> send_base;            // [Bi+1] record offset of every bin in r's owner-major send buffer
+    std::vector<uint64_t> send_off;             // [n+1]  where the block for GPU g begins in it
+    std::vector<uint64_t> recv_off;             // [n+1]  where the block from GPU s begins in r's receive buffer
+    std::vector<uint64_t> bin_rec, bin_kmer;    // [Bi]   records / k-mers of the bins r owns (0 elsewhere)
+    std::vector<uint64_t> seg_src, seg_dst;     // received segments (source, bin) -> bin-major place
+};
+}
+extern "C" int fkm_execute_job_multi(const int32_t* devices, int32_t n_devices, const fkm_config* cfg, fkm_stats* stats) {
+    int32_t B = 0; int rc = validate(cfg, &B); if (rc) return rc;
+    if (!devices || n_devices < 1 || n_devices > 64) return fkm_set_error(FKM_EINVAL, "bad device list");
+    if (!cfg->dataset) return fkm_set_error(FKM_EINVAL, "dataset path is NULL");
+    const int n = n_devices;
+    std::vector<fkm_ctx*> ctx((size_t)n, nullptr);
+    auto destroy = [&]() { for (auto* c : ctx) fkm_ctx_destroy(c); };
+    for (int i = 0; i < n; i++) { rc = fkm_ctx_create(devices[i], nullptr, &ctx[(size_t)i]); if (rc) { destroy(); return rc; } }
+    if (n == 1) { rc = fkm_execute_job(ctx[0], cfg, stats); const std::string keep = g_err; destroy(); g_err = keep; return rc; }
+    int split = 1;
+    if (cfg->use_ht) while (split < n && split < 64) split *= 2;               // see multigpu.ShardedJob
+    for (auto* c : ctx) { c->bin_split = (double)split; if (c->count_mode >= 1.0 && c->count_mode < 2.0) c->count_mode = 2.0; }
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++)
+            if (i != j) {
+                cudaSetDevice(devices[i]);
+                cudaError_t e = cudaDeviceEnablePeerAccess(devices[j], 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else if (e != cudaSuccess) { cudaGetLastError(); }              // no peer access: the copies below are staged by the driver
+            }
+    uint8_t* text = nullptr; uint64_t n_text = 0;
+    rc = fkm_read_file_pinned(cfg->dataset, &text, &n_text); if (rc) { destroy(); return rc; }
+    // ---- byte ranges at record boundaries
+    std::vector<uint64_t> cut((size_t)n + 1, n_text);
+    cut[0] = 0;
+    for (int i = 1; i < n; i++) {
+        uint64_t pos = std::max(cut[(size_t)i - 1], n_text / (uint64_t)n * (uint64_t)i), c = n_text;
+        const uint8_t* p0 = text + pos;
+        while (p0 < text + n_text) {
+            p0 = (const uint8_t*)memchr(p0, '>', (size_t)(text + n_text - p0));
+            if (!p0) break;
+            if (p0 == text || p0[-1] == '\n') { c = (uint64_t)(p0 - text); break; }
+            p0++;
+        }
+        cut[(size_t)i] = c;
+    }
+    int32_t Bi = 0;
+    rc = fkm_job_bins(ctx[0], cfg, 0, &Bi); if (rc) { cudaFreeHost(text); destroy(); return rc; }
+    const int sp = Bi / B;                                                        // internal bins per bin
+    std::vector<std::vector<uint64_t>> H_rec((size_t)n, std::vector<uint64_t>((size_t)Bi)), H_kmer((size_t)n, std::vector<uint64_t>((size_t)Bi));
+    std::vector<int> trc((size_t)n, FKM_OK); std::vector<std::string> terr((size_t)n);
+    std::vector<uint64_t> nbases((size_t)n, 0);
+    auto run_all = [&](auto&& fn) -> int {                                        // fn(rank) on one host thread per GPU
+        std::vector<std::thread> th;
+        for (int i = 0; i < n; i++) th.emplace_back([&, i]() { trc[(size_t)i] = fn(i); if (trc[(size_t)i]) terr[(size_t)i] = g_err; });
+        for (auto& t : th) t.join();
+        for (int i = 0; i < n; i++) if (trc[(size_t)i]) { g_err = "GPU " + std::to_string(devices[i]) + ": " + terr[(size_t)i]; return trc[(size_t)i]; }
+        return FKM_OK;
+    };
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<void*> d_send((size_t)n, nullptr), d_recv((size_t)n, nullptr);
+    auto cleanup = [&]() {
+        for (int i = 0; i < n; i++) { cudaSetDevice(devices[i]); cudaDeviceSynchronize(); cudaFree(d_send[(size_t)i]); cudaFree(d_recv[(size_t)i]); }
+        cudaFreeHost(text); destroy();
+    };
+    rc = run_all([&](int i) { return fkm_mg_scan_fasta(ctx[(size_t)i], cfg, text + cut[(size_t)i], cut[(size_t)i + 1] - cut[(size_t)i],
+                                                       H_rec[(size_t)i].data(), H_kmer[(size_t)i].data(), &nbases[(size_t)i]); });
+    if (rc) { const std::string keep = g_err; cleanup(); g_err = keep; return rc; }
+    // ---- owners: LPT over the bins of the configuration (longest first, each to the least loaded GPU; ties by bin id, then rank)
+    std::vector<uint64_t> tot((size_t)B, 0);
+    for (int b = 0; b < Bi; b++) for (int i = 0; i < n; i++) tot[(size_t)(b / sp)] += H_kmer[(size_t)i][(size_t)b];
+    std::vector<int> order((size_t)B); for (int b = 0; b < B; b++) order[(size_t)b] = b;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b2) { return tot[(size_t)a] > tot[(size_t)b2]; });
+    std::vector<uint64_t> load((size_t)n, 0); std::vector<int> owner_bin((size_t)B, 0);
+    for (int b : order) { int g = 0; for (int j = 1; j < n; j++) if (load[(size_t)j] < load[(size_t)g]) g = j; owner_bin[(size_t)b] = g; load[(size_t)g] += tot[(size_t)b]; }
+    auto owner = [&](int bi) { return owner_bin[(size_t)(bi / sp)]; };
+    // ---- the exchange plan of every rank
+    const int rb = fkm_record_bytes(cfg);
+    std::vector<MultiPlan> plan((size_t)n);
+    for (int r = 0; r < n; r++) {
+        MultiPlan& P = plan[(size_t)r];
+        P.send_base.assign((size_t)Bi + 1, 0); P.send_off.assign((size_t)n + 1, 0); P.recv_off.assign((size_t)n + 1, 0);
+        P.bin_rec.assign((size_t)Bi, 0); P.bin_kmer.assign((size_t)Bi, 0);
+        uint64_t o = 0;
+        for (int g = 0; g < n; g++) {                                             // send buffer: bins ordered by (owner, bin)
+            P.send_off[(size_t)g] = o;
+            for (int b = 0; b < Bi; b++) if (owner(b) == g) { P.send_base[(size_t)b] = o; o += H_rec[(size_t)r][(size_t)b]; }
+        }
+        P.send_off[(size_t)n] = o; P.send_base[(size_t)Bi] = o;
+        uint64_t ro = 0;
+        for (int s2 = 0; s2 < n; s2++) { P.recv_off[(size_t)s2] = ro; for (int b = 0; b < Bi; b++) if (owner(b) == r) ro += H_rec[(size_t)s2][(size_t)b]; }
+        P.recv_off[(size_t)n] = ro;
+        std::vector<uint64_t> dst((size_t)Bi + 1, 0);
+        for (int b = 0; b < Bi; b++) {
+            if (owner(b) == r) for (int s2 = 0; s2 < n; s2++) { P.bin_rec[(size_t)b] += H_rec[(size_t)s2][(size_t)b]; P.bin_kmer[(size_t)b] += H_kmer[(size_t)s2][(size_t)b]; }
+            dst[(size_t)b + 1] = dst[(size_t)b] + P.bin_rec[(size_t)b];
+        }
+        P.seg_src.push_back(0);
+        std::vector<uint64_t> before((size_t)Bi, 0);
+        for (int s2 = 0; s2 < n; s2++)
+            for (int b = 0; b < Bi; b++)
+                if (owner(b) == r && H_rec[(size_t)s2][(size_t)b]) {
+                    P.seg_dst.push_back(dst[(size_t)b] + before[(size_t)b]);
+                    P.seg_src.push_back(P.seg_src.back() + H_rec[(size_t)s2][(size_t)b]);
+                    before[(size_t)b] += H_rec[(size_t)s2][(size_t)b];
+                }
+    }
+    // ---- records owner-major, GPU-to-GPU copies, bin-major again, count, write
+    rc = run_all([&](int i) -> int {
+        CK(cudaSetDevice(devices[i]));
+        CK(cudaMalloc(&d_send[(size_t)i], std::max<uint64_t>(plan[(size_t)i].send_off[(size_t)n], 1) * rb));
+        CK(cudaMalloc(&d_recv[(size_t)i], std::max<uint64_t>(plan[(size_t)i].recv_off[(size_t)n], 1) * rb));
+        return fkm_mg_scatter(ctx[(size_t)i], plan[(size_t)i].send_base.data(), d_send[(size_t)i]);
+    });
+    if (rc) { const std::string keep = g_err; cleanup(); g_err = keep; return rc; }
+    auto tx0 = std::chrono::steady_clock::now();
+    rc = run_all([&](int s2) -> int {                                             // rank s2 pushes its blocks to their owners
+        CK(cudaSetDevice(devices[s2]));
+        for (int g = 0; g < n; g++) {
+            const uint64_t cnt = plan[(size_t)s2].send_off[(size_t)g + 1] - plan[(size_t)s2].send_off[(size_t)g];
+            if (!cnt) continue;
+            CK(cudaMemcpyPeerAsync((char*)d_recv[(size_t)g] + plan[(size_t)g].recv_off[(size_t)s2] * rb, devices[g],
+                                   (const char*)d_send[(size_t)s2] + plan[(size_t)s2].send_off[(size_t)g] * rb, devices[s2], cnt * rb, ctx[(size_t)s2]->stream));
+        }
+        CK(cudaStreamSynchronize(ctx[(size_t)s2]->stream));
+        return FKM_OK;
+    });
+    if (rc) { const std::string keep = g_err; cleanup(); g_err = keep; return rc; }
+    const double ms_x = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tx0).count();
+    std::vector<fkm_stats> sts((size_t)n);
+    char dir[4096] = {0};
+    if (cfg->write) { rc = fkm_derive(cfg, nullptr, dir, sizeof dir); if (rc) { cleanup(); return rc; } }
+    rc = run_all([&](int g) -> int {
+        const MultiPlan& P = plan[(size_t)g];
+        void* d_records = nullptr;
+        int r2 = fkm_mg_regroup(ctx[(size_t)g], cfg, d_recv[(size_t)g], P.recv_off[(size_t)n], P.seg_src.data(), P.seg_dst.data(), P.seg_dst.size(), &d_records);
+        if (r2) return r2;
+        fkm_result* res = nullptr;
+        memset(&sts[(size_t)g], 0, sizeof(fkm_stats));
+        r2 = fkm_mg_count(ctx[(size_t)g], cfg, d_records, P.bin_rec.data(), P.bin_kmer.data(), &res, &sts[(size_t)g]);
+        if (r2) return r2;
+        if (cfg->write) r2 = fkm_result_write(res, dir);                          // only the bins this GPU owns hold entries: their files
+        fkm_result_free(res);
+        return r2;
+    });
+    if (rc) { const std::string keep = g_err; cleanup(); g_err = keep; return rc; }
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        for (int g = 0; g < n; g++) {
+            const fkm_stats& a = sts[(size_t)g];
+            stats->n_kmers += a.n_kmers; stats->n_superkmers += a.n_superkmers; stats->superkmer_bytes += a.superkmer_bytes;
+            stats->n_distinct += a.n_distinct; stats->total_count += a.total_count; stats->digest_sum += a.digest_sum; stats->digest_xor ^= a.digest_xor;
+            stats->n_nonempty_bins += a.n_nonempty_bins; stats->gpu_launches += a.gpu_launches; stats->n_batches += a.n_batches;
+            stats->n_fallbacks += a.n_fallbacks; stats->n_mid_bins += a.n_mid_bins; stats->n_slow_bins += a.n_slow_bins;
+            stats->h2d_bytes += a.h2d_bytes + (cut[(size_t)g + 1] - cut[(size_t)g]); stats->d2h_bytes += a.d2h_bytes;
+            stats->n_bases += nbases[(size_t)g];
+            for (int j = 0; j < 8; j++) stats->ms_stage[j] = std::max(stats->ms_stage[j], a.ms_stage[j]);
+            stats->ms_partition = std::max(stats->ms_partition, a.ms_partition); stats->ms_fold = std::max(stats->ms_fold, a.ms_fold);
+        }
+        stats->ms_stage[6] = ms_x;                                                // (the GPU-to-GPU exchange, host clock)
+        stats->ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    cleanup();
+    return FKM_OK;
+}
+
 // ------------------------------------------------------------------ multi-sample distances
 // The reference's prototype (skc.multisequence, MSKC:29-165,300-547) tags super-k-mers with the sample a read came
 // from, keeps per-sample counts of every distinct k-mer of a bin and adds (c_a - c_b)^2 to the distance of every

@@ -110,6 +110,14 @@ int  fkm_derive(const fkm_config* cfg, int32_t* b, char* out_dir, size_t out_dir
  * path).  stats may be NULL.                                                   */
 int  fkm_execute_job(fkm_ctx* ctx, const fkm_config* cfg, fkm_stats* stats);
 
+/* The same job on several GPUs of one node (no Python, no NCCL): the FASTA text is cut at record boundaries into one
+ * byte range per GPU, every GPU scans its range, bins are assigned to GPUs by LPT over the exact histogram (the role of
+ * MultiprocessorSchedulingPartitioner.scala:35-69), the records move GPU to GPU (cudaMemcpyPeerAsync over NVLink: Spark's
+ * shuffle, SBKC:1035,1042), every GPU counts and writes the bins it owns.  devices: n_devices CUDA device ids.  The bin
+ * files are the single-GPU job's (byte for byte for use_ht = 0; the same lines in another order for use_ht = 1, whose
+ * order is unspecified in the reference too, SBKC:723).  A single long record is not cut: it is counted by one GPU.    */
+int  fkm_execute_job_multi(const int32_t* devices, int32_t n_devices, const fkm_config* cfg, fkm_stats* stats);
+
 /* ---- in-memory variants (same path, no file I/O) ---------------------------- */
 /* FASTA text in host memory (pinned if it came from fkm_host_alloc).  The raw
  * text is copied to the GPU and parsed there (record split of SURVEY App. A.1). */

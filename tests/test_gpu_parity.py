@@ -253,6 +253,8 @@ def test_smem_path_tiers(oracle, mode):
     c2 = fk.Context(0)
     try:
         c2.set("count_mode", mode)
+        if mode == 2:
+            c2.set("part_max_subs", 1e9)      # (the tiny tables below need thousands of sub-buckets per bin: keep the size guard out of the way)
         for text, label in ((deep, "deep"), (flat, "flat")):
             for k, m, B in configs:
                 want = oracle.count(text, k, m, 3, B, 1, threads=8)
@@ -452,6 +454,35 @@ def test_execute_job_writes_reference_layout(ctx, oracle, tmp_path, ht):
     tc0 = fk.TestConfiguration(str(inp), str(tmp_path) + "/none/", 28, 10, 3, max_b=2048, useHT=bool(ht), write=False)
     fk.LocalTestKmerCounter.run(tc0)
     assert not (tmp_path / "none").exists()
+
+
+@pytest.mark.parametrize("k,m,ht", [(28, 10, 0), (28, 10, 1), (55, 13, 1)])
+def test_execute_job_on_several_gpus(oracle, tmp_path, k, m, ht):
+    """fkm_execute_job_multi: the drop-in job over the GPUs of the node through the C ABI alone (byte ranges of the file, LPT bin owners,
+    GPU-to-GPU copies): the oracle's bin files.  With one visible GPU the same device is used twice (the exchange is then a local copy)."""
+    import torch
+    from fastkmer_b200 import api
+    n_dev = torch.cuda.device_count()
+    devices = [0, 1] if n_dev >= 2 else [0, 0]
+    fasta = fk.synth_fasta(dict(seeds=(91, 92, 93), genome_len=40000, n_reads=20000, read_len=120)).tobytes()
+    inp = tmp_path / "reads.fasta"
+    inp.write_bytes(fasta)
+    tc = fk.TestConfiguration(str(inp), str(tmp_path) + "/out/", k, m, 3, max_b=512, prefix="mg_", useHT=bool(ht), write=True)
+    st = api.Context.execute_job_multi(tc, devices)
+    want = oracle.count(fasta, k, m, 3, 512, ht, threads=8)
+    assert (st["n_kmers"], st["n_distinct"], st["total_count"]) == (want["stats"]["n_kmers"], want["stats"]["n_distinct"], want["stats"]["n_kmers"])
+    assert (st["digest_sum"], st["digest_xor"]) == (want["stats"]["digest_sum"], want["stats"]["digest_xor"])
+    out = tmp_path / "out" / ("mg_k%d_m%d_x3_b512_s0" % (k, m))
+    by_bin = {}
+    for b, h, l, c in zip(want["bin"], want["hi"], want["lo"], want["cnt"]):
+        by_bin.setdefault(int(b), []).append(b"%s\t%d\n" % (oracle_lib.kmer_str(h, l, k).encode(), int(c)))
+    assert sorted(os.listdir(out)) == sorted("bin%d" % b for b in by_bin)
+    for b, lines in by_bin.items():
+        data = (out / ("bin%d" % b)).read_bytes()
+        if ht:
+            assert sorted(data.splitlines(keepends=True)) == sorted(lines)
+        else:
+            assert data == b"".join(lines) + b"EOF"
 
 
 @pytest.mark.parametrize("k,m,ht", [(28, 10, 0), (55, 13, 1), (33, 9, 0)])
