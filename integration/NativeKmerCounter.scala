@@ -11,6 +11,12 @@ object NativeKmerCounter {
                          useHT: Boolean, write: Boolean, useKryo: Boolean,
                          useCustomPartitioner: Boolean, numPartitionTasks: Int): Int
 
+  /** The same job on the first nGpus GPUs of this node (fkm_execute_job_multi). */
+  @native def executeJobMulti(nGpus: Int, dataset: String, outputDirectory: String, prefix: String,
+                              k: Int, m: Int, x: Int, maxB: Int, sequenceType: Int,
+                              useHT: Boolean, write: Boolean, useKryo: Boolean,
+                              useCustomPartitioner: Boolean, numPartitionTasks: Int): Int
+
   @native def lastError(): String
 
   /** Body for SparkBinKmerCounter.executeJob(spark, configuration) (SparkBinKmerCounter.scala:989). */
