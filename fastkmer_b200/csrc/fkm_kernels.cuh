@@ -383,6 +383,7 @@ struct ScatterParams {
     uint32_t B; int split; int cap; int k;          // bin of an event = split_bin(signature, B, split)
     const unsigned long long* bin_base; void* records;
     unsigned long long* cursor; int cursor_shift;   // write cursor of bin b at cursor[b << cursor_shift]
+    int* overflow;                                  // speculative scatter (bin regions sized from a forecast): set when a bin outgrows its region; else NULL
 };
 template <bool WIDE>
 __global__ void __launch_bounds__(256) k_scatter_events(const ScatterParams P) {
@@ -401,6 +402,7 @@ __global__ void __launch_bounds__(256) k_scatter_events(const ScatterParams P) {
     const uint32_t bin = split_bin(v, P.B, P.split);
     const uint32_t pieces = (n + (uint32_t)P.cap - 1) / (uint32_t)P.cap;
     const unsigned long long slot0 = P.bin_base[bin] + atomicAdd(&P.cursor[(size_t)bin << P.cursor_shift], (unsigned long long)pieces);
+    if (P.overflow && slot0 + pieces > P.bin_base[bin + 1]) { *P.overflow = 1; return; }
     {
         const uint32_t nn = min((uint32_t)P.cap, n);
         uint64_t r[NW - 1];

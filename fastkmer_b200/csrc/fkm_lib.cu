@@ -109,6 +109,8 @@ struct fkm_ctx {
     double part_fill = 0.45;          // partitioned count path (count_mode 2): distinct k-mers per sub-bucket as a share of the table's slots
     double bin_split = 0.0;           // internal bins per bin (hash path, count_mode 0 or 2): 0 = chosen from the input size, else a power of two (a multi-GPU job sets the same value on every rank)
     int job_split = 0;                // log2 of the internal bins per bin of the job in progress (fkm_common.h split_bin)
+    double speculative_scatter = 1.0; // FASTA front end, hash path: scatter the scanned chunks under the PCIe copy into bin regions sized from a forecast
+    double part_two_ctas = 0.0;       // ... 1: k_count_keys as two 512-thread CTAs per SM with half-size tables (experiment)
     double part_max_subs = 768.0;     // ... sub-buckets a bin may need before the job is left to the global-table pipeline
     double part_budget_keys = 1024.0 * 1048576.0;   // ... k-mers per batch of bins (the key buffer holds one batch)
     std::vector<cudaEvent_t> evpool;  // ... per-batch timing events
@@ -196,6 +198,8 @@ extern "C" int fkm_ctx_set(fkm_ctx* c, const char* name, double v) {
     else if (!strcmp(name, "smem_slow_slots")) c->smem_slow_slots = v;
     else if (!strcmp(name, "smem_fill")) c->smem_fill = v;
     else if (!strcmp(name, "part_fill")) c->part_fill = v;
+    else if (!strcmp(name, "speculative_scatter")) c->speculative_scatter = v;
+    else if (!strcmp(name, "part_two_ctas")) c->part_two_ctas = v;
     else if (!strcmp(name, "bin_split")) c->bin_split = v;
     else if (!strcmp(name, "part_max_subs")) c->part_max_subs = v;
     else if (!strcmp(name, "sort_partition")) c->sort_partition = v;
@@ -371,6 +375,13 @@ struct ScanState {
     uint64_t n_pos_total = 0;
     bool valid = false;
     uint64_t gen = 0;                           // job generation of the context the state belongs to
+    // speculative scatter (FASTA front end, hash path): while the text is still on the PCIe bus the chunks already scanned are
+    // scattered into bin regions sized from a forecast of the histogram; h_rec (exact, known at the end) are the bins' record counts
+    struct Spec {
+        bool on = false, failed = false;
+        void* d_records = nullptr; unsigned long long *d_bin_base = nullptr, *d_cursor = nullptr; int cursor_shift = 0; int* d_ovf = nullptr;
+        size_t next_chunk = 0; std::vector<unsigned long long> base;      // [B+1] region offsets
+    } spec;
     // dual scan (shared-memory count path): runs cut by the signature and a second minimizer, histogram per (bin, cell)
     bool dual = false; int cell_bits = 0; uint32_t sample_hi = 0;
     unsigned long long *d_cell_rec = nullptr, *d_cell_kmer = nullptr;
@@ -381,7 +392,7 @@ static void free_scan_state(ScanState* p) { delete p; }
 // n_pos_hint: positions the whole job will scan (sizes the cells of a dual scan)
 static int scan_begin(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, ScanState* S, bool dual = false, uint64_t n_pos_hint = 0) {
     const size_t bB = (size_t)B * 8;
-    S->cfg = *cfg; S->B = B; S->chunks.clear(); S->n_pos_total = 0; S->valid = false; S->gen = ctx->gen;
+    S->cfg = *cfg; S->B = B; S->chunks.clear(); S->n_pos_total = 0; S->valid = false; S->gen = ctx->gen; S->spec = ScanState::Spec();
     S->h_rec.assign((size_t)B, 0); S->h_kmer.assign((size_t)B, 0);
     CK(dmalloc(ctx, &S->d_hist_rec, bB)); CK(dmalloc(ctx, &S->d_hist_kmer, bB));
     CK(cudaMemsetAsync(S->d_hist_rec, 0, bB, ctx->stream)); CK(cudaMemsetAsync(S->d_hist_kmer, 0, bB, ctx->stream));
@@ -445,7 +456,10 @@ static int scan_end(fkm_ctx* ctx, ScanState* S, fkm_stats* st) {
         CK(cudaMemcpyAsync(C.n_events2, C.d_count, 16, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(&C.ev_ovf, C.d_ovf, 4, cudaMemcpyDeviceToHost, s));
     }
+    int spec_ovf = 0;
+    if (S->spec.on) CK(cudaMemcpyAsync(&spec_ovf, S->spec.d_ovf, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    if (S->spec.on && (spec_ovf || S->spec.next_chunk != S->chunks.size())) S->spec.failed = true;
     for (ChunkScan& C : S->chunks) if (!S->dual) C.n_events = C.n_events2[0];
     st->d2h_bytes += 2 * bB + 12 * S->chunks.size();
     S->valid = true;
@@ -477,32 +491,41 @@ static int stage_scan(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const void
 
 // stage 2: run events -> super-k-mer records at d_records[bin_base[bin] + ...] (the "shuffle").  bin_base is any
 // per-bin record offset table: bin-major on one GPU, owner-major for the multi-GPU send buffer.
+// the write cursors of the scatter stage: one per bin, 1 << shift words apart
+static int cursor_shift_for(int32_t B) { int sh = 5; while (sh > 0 && ((uint64_t)B << sh) > (1ull << 20)) sh--; return sh; }
+// one chunk's run events -> records (asynchronous)
+static int scatter_chunk(fkm_ctx* ctx, ScanState* S, const ChunkScan& C, const unsigned long long* d_bin_base, unsigned long long* d_cursor,
+                         int cursor_shift, void* d_records, int* d_overflow) {
+    const fkm_config* cfg = &S->cfg;
+    const bool wide = cfg->k > 32;
+    ScatterParams Q;
+    Q.events = C.d_events; Q.n_events = C.n_events; Q.bases = (const uint64_t*)C.d_bases; Q.n_words = (C.n_pos + 31) / 32;
+    Q.B = (uint32_t)S->B >> ctx->job_split; Q.split = ctx->job_split; Q.cap = wide ? (125 - cfg->k) : (61 - cfg->k); Q.k = cfg->k;
+    Q.bin_base = d_bin_base; Q.cursor = d_cursor; Q.cursor_shift = cursor_shift; Q.records = d_records; Q.overflow = d_overflow;
+    if (C.n_events) {
+        const unsigned grid = (unsigned)((C.n_events + 255) / 256);
+        if (wide) k_scatter_events<true><<<grid, 256, 0, ctx->stream>>>(Q); else k_scatter_events<false><<<grid, 256, 0, ctx->stream>>>(Q);
+        CKL();
+    }
+    return FKM_OK;
+}
+
 static int stage_scatter(fkm_ctx* ctx, ScanState* S, const unsigned long long* d_bin_base,
                          void* d_records, uint64_t n_rec, fkm_stats* st) {
     cudaStream_t s = ctx->stream;
     const fkm_config* cfg = &S->cfg;
-    const bool wide = cfg->k > 32;
     // One write cursor per bin, 256 bytes apart.  The stage does one atomic per run event on these B words; packed
     // densely (16 KB at B = 2048) they are 8 of the 2-KB grains by which addresses are dealt to the two dies and the
     // L2 slices, and the stage took 17, 19 or 23 ms for the same kernel depending on where the allocation had landed.
     // Spread out, the hot words cover all slices whatever the placement.
-    int cursor_shift = 5;
-    while (cursor_shift > 0 && ((uint64_t)S->B << cursor_shift) > (1ull << 20)) cursor_shift--;
+    const int cursor_shift = cursor_shift_for(S->B);
     unsigned long long* d_cursor = nullptr;
     CK(dmalloc(ctx, &d_cursor, ((size_t)S->B << cursor_shift) * 8));
     CK(cudaMemsetAsync(d_cursor, 0, ((size_t)S->B << cursor_shift) * 8, s));
     CK(cudaEventRecord(ctx->ev[1], s));
     for (ChunkScan& C : S->chunks) {
         if (!C.ev_ovf) {
-            ScatterParams Q;
-            Q.events = C.d_events; Q.n_events = C.n_events; Q.bases = (const uint64_t*)C.d_bases; Q.n_words = (C.n_pos + 31) / 32;
-            Q.B = (uint32_t)S->B >> ctx->job_split; Q.split = ctx->job_split; Q.cap = wide ? (125 - cfg->k) : (61 - cfg->k); Q.k = cfg->k;
-            Q.bin_base = d_bin_base; Q.cursor = d_cursor; Q.cursor_shift = cursor_shift; Q.records = d_records;
-            if (C.n_events) {
-                const unsigned grid = (unsigned)((C.n_events + 255) / 256);
-                if (wide) k_scatter_events<true><<<grid, 256, 0, s>>>(Q); else k_scatter_events<false><<<grid, 256, 0, s>>>(Q);
-                CKL();
-            }
+            int rc = scatter_chunk(ctx, S, C, d_bin_base, d_cursor, cursor_shift, d_records, nullptr); if (rc) return rc;
         } else {
             // the event list was too small for this chunk: scan it again, writing the records directly
             st->n_fallbacks++;
@@ -527,7 +550,8 @@ static constexpr int kBinTooBig = 2;            // internal: the sort path met a
 template <bool WIDE>
 static int count_partitioned(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const void* d_records, const unsigned long long* d_bin_base,
                              const std::vector<unsigned long long>& h_rec, const std::vector<unsigned long long>& h_kmer,
-                             fkm_result* res, fkm_stats* st, unsigned long long* d_acc, uint64_t* out_total_p, float* ms_part_p, float* ms_count_p, const bool ordered) {
+                             fkm_result* res, fkm_stats* st, unsigned long long* d_acc, uint64_t* out_total_p, float* ms_part_p, float* ms_count_p, const bool ordered,
+                             const unsigned long long* d_bin_cnt = nullptr) {
     typedef typename Traits<WIDE>::Key Key;
     cudaStream_t s = ctx->stream;
     constexpr uint64_t TR = PartGeom<WIDE>::kTileRecs;
@@ -538,13 +562,16 @@ static int count_partitioned(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, con
     };
     for (int b = 0; b < B; b++) if (h_kmer[(size_t)b] >= 0xFFFFFFF0ull) return retry("a bin of 2^32 k-mers", b);
     // geometry of k_count_keys's table
-    uint32_t cap = WIDE ? 8192u : 16384u;
+    // part_two_ctas: two CTAs of 512 threads per SM, each with a table of half the slots (experiment)
+    const bool two = !ordered && ctx->part_two_ctas >= 1.0;
+    uint32_t cap = (WIDE ? 8192u : 16384u) >> (two ? 1 : 0);
     while (cap > 64u && (size_t)cap * (sizeof(Key) + 6) + 2048 > ctx->smem_optin) cap >>= 1;
     if (ctx->smem_table_slots >= 64.0) while (cap > 64u && (double)cap > ctx->smem_table_slots) cap >>= 1;
     const uint32_t tail = ordered ? 512u : 0u;
     const size_t kc_smem = ordered ? (size_t)(cap + tail) * (sizeof(Key) + 4) : (size_t)cap * (sizeof(Key) + 6);
     const size_t sc_smem = (size_t)PartGeom<WIDE>::kBufKeys * (sizeof(Key) + 2);
-    CK(cudaFuncSetAttribute(k_count_keys<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)cap * (sizeof(Key) + 6))));
+    CK(cudaFuncSetAttribute(k_count_keys<WIDE, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)cap * (sizeof(Key) + 6))));
+    CK(cudaFuncSetAttribute(k_count_keys<WIDE, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)cap * (sizeof(Key) + 6))));
     CK(cudaFuncSetAttribute(k_count_keys_ordered<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)(cap + 512u) * (sizeof(Key) + 4))));
     CK(cudaFuncSetAttribute(k_place_keys<WIDE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
     CK(cudaFuncSetAttribute(k_place_keys<WIDE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
@@ -558,7 +585,7 @@ static int count_partitioned(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, con
     // distinct k-mers a sub-bucket is planned for (key ranges are up to twice as full as the average: canonical k-mers crowd the low end of the key space)
     const double d_target = std::max(16.0, (double)cap * ctx->part_fill * (ordered ? 0.5 : 1.0));
     const uint64_t budget_keys = std::max<uint64_t>(1u << 16, (uint64_t)ctx->part_budget_keys);
-    const unsigned grid = (unsigned)ctx->n_sm;
+    const unsigned grid = (unsigned)ctx->n_sm * (two ? 2u : 1u);
     const size_t bB = (size_t)B * 8;
 
     struct Batch { int lo, hi; size_t o32, o64h, o64k; uint64_t n_tiles, n_sub, hist_elems, n_keys, region_cap; double rho; };
@@ -637,7 +664,7 @@ static int count_partitioned(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, con
             CK(cudaEventRecord(ctx->evpool[3 * (i - b0)], s));
             if (bt.n_keys) {
                 PartParams P;
-                P.records = d_records; P.bin_rec_base = d_bin_base; P.bin_lo = bt.lo; P.bin_hi = bt.hi;
+                P.records = d_records; P.bin_rec_base = d_bin_base; P.bin_rec_cnt = d_bin_cnt; P.bin_lo = bt.lo; P.bin_hi = bt.hi;
                 P.tile_first = d32 + (bt.o32 - lo32); P.sub_first = P.tile_first + nb + 1;
                 P.hist_off = d64 + (bt.o64h - lo64); P.key_base = d64 + (bt.o64k - lo64);
                 P.n_tiles = (uint32_t)bt.n_tiles; P.n_sub = (uint32_t)bt.n_sub; P.tile_hist = d_hist; P.tile_base = d_base; P.keys = d_keys;
@@ -658,7 +685,9 @@ static int count_partitioned(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, con
                 Q.bin_cta = d_bin_cta; Q.bin_off = d_bin_off; Q.acc = d_acc; Q.cap_slots = cap; Q.max_fill = cap * 3 / 4;
                 Q.slow_keys = d_slow_keys; Q.slow_cnt = d_slow_cnt; Q.slow_slots = slow_slots; Q.slow_max_fill = slow_slots * 7 / 10; Q.flags = d_flags; Q.counters = d_counters;
                 Q.k = cfg->k; Q.tail_slots = tail; Q.bin_shift = ctx->job_split;
-                if (ordered) k_count_keys_ordered<WIDE><<<grid, kKcThreads, kc_smem, s>>>(Q); else k_count_keys<WIDE><<<grid, kKcThreads, kc_smem, s>>>(Q);
+                if (ordered) k_count_keys_ordered<WIDE><<<grid, kKcThreads, kc_smem, s>>>(Q);
+                else if (two) k_count_keys<WIDE, 512><<<grid, 512, kc_smem, s>>>(Q);
+                else k_count_keys<WIDE, 1024><<<grid, 1024, kc_smem, s>>>(Q);
                 CKL();
             } else CK(cudaEventRecord(ctx->evpool[3 * (i - b0) + 1], s));
             CK(cudaEventRecord(ctx->evpool[3 * (i - b0) + 2], s));
@@ -793,7 +822,31 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
     st->n_kmers = n_kmers; st->n_superkmers = n_rec; st->superkmer_bytes = n_rec * rec_bytes; st->n_nonempty_bins = nonempty;
     CKC(cudaMemcpyAsync(d_bin_base, h_base.data(), bB + 8, cudaMemcpyHostToDevice, s));
     st->h2d_bytes += bB + 8;
-    if (!pre) {
+    uint64_t out_total = 0;
+    float ms_count = 0, ms_compact = 0, ms_part = 0;
+    bool part_done = false, scattered = false;
+    // ---- the records were scattered while the input was still arriving (speculative scatter of the FASTA front end): the bins'
+    // regions have gaps, which only the partitioned count stage reads around; anything else scatters again below
+    if (!pre && scanned && scanned->spec.on && !scanned->spec.failed && cfg->use_ht && ctx->count_mode >= 2.0 && n_rec) {
+        unsigned long long* d_bin_cnt = nullptr;
+        CKC(dmalloc(ctx, &d_bin_cnt, bB));
+        CKC(cudaMemcpyAsync(d_bin_cnt, h_rec.data(), bB, cudaMemcpyHostToDevice, s));
+        CKC(cudaEventRecord(ctx->ev[1], s)); CKC(cudaEventRecord(ctx->ev[2], s));
+        const Arena::Mark mk = ctx->arena.mark();
+        rc = count_partitioned<WIDE>(ctx, cfg, B, scanned->spec.d_records, scanned->spec.d_bin_base, h_rec, h_kmer, res, st, d_acc, &out_total, &ms_part, &ms_count,
+                                     false, d_bin_cnt);
+        if (rc == FKM_OK) { part_done = true; scattered = true; st->superkmer_bytes = scanned->spec.base[(size_t)B] * rec_bytes; }
+        else if (rc != kRetryGlobal) { cleanup(); return rc; }
+        else {
+            rc = FKM_OK;
+            ctx->arena.release(mk);
+            st->n_batches = 0; st->n_mid_bins = 0; st->n_slow_bins = 0;
+            res->chunks.clear(); out_total = 0; ms_count = 0; ms_part = 0;
+            CKC(cudaMemsetAsync(d_acc, 0, 192 * 8, s));
+        }
+    }
+    if (scattered) {
+    } else if (!pre) {
         CKC(dmalloc(ctx, &d_records, std::max<size_t>(16, (size_t)n_rec * rec_bytes)));
         tr.mark("records allocated", (long long)n_rec);
         rc = stage_scatter(ctx, &scan, d_bin_base, d_records, n_rec, st); if (rc) return rc;
@@ -803,10 +856,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
     }
 
     // ---- hash path, count_mode 2: the partitioned count stage with its tables in shared memory (fkm_part.cuh)
-    uint64_t out_total = 0;
-    float ms_count = 0, ms_compact = 0, ms_part = 0;
-    bool part_done = false;
-    if ((cfg->use_ht ? ctx->count_mode >= 2.0 : (ctx->sort_partition >= 2.0 && ctx->debug_force_lsd < 1.0)) && n_rec) {
+    if (!part_done && (cfg->use_ht ? ctx->count_mode >= 2.0 : (ctx->sort_partition >= 2.0 && ctx->debug_force_lsd < 1.0)) && n_rec) {
         const Arena::Mark mk = ctx->arena.mark();
         rc = count_partitioned<WIDE>(ctx, cfg, B, d_records, d_bin_base, h_rec, h_kmer, res, st, d_acc, &out_total, &ms_part, &ms_count, !cfg->use_ht);
         if (rc == FKM_OK) part_done = true;
@@ -1259,7 +1309,7 @@ static int run_pipeline(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const vo
                 CKC(cudaMemsetAsync(d_ovf, 0, 8, s));
                 st->h2d_bytes += p32.size() * 4 + p64.size() * 8;
                 PartParams PP;
-                PP.records = d_records; PP.bin_rec_base = d_bin_base; PP.bin_lo = lo; PP.bin_hi = hi;
+                PP.records = d_records; PP.bin_rec_base = d_bin_base; PP.bin_rec_cnt = nullptr; PP.bin_lo = lo; PP.bin_hi = hi;
                 PP.tile_first = d_p32; PP.sub_first = d_p32 + nbb + 1; PP.hist_off = d_p64; PP.key_base = d_p64 + nbb + 1;
                 PP.n_tiles = (uint32_t)tiles; PP.n_sub = (uint32_t)subs; PP.tile_hist = d_phist; PP.tile_base = d_pbase;
                 PP.bin_key_cursor = d_pkcur; PP.tile_key_off = d_ptoff; PP.tile_nkeys = d_ptnk; PP.keys_lin = d_keysA; PP.keys = d_keysB;
@@ -1778,7 +1828,7 @@ static void split_fasta(const uint8_t* t, uint64_t n, uint64_t target, std::vect
 // stream while earlier chunks are parsed (fkm_ingest.cuh) and scanned (k_scan) on the compute stream,
 // so the PCIe copy — the longest single step of an end-to-end job — hides the parse and the scan.
 static int front_end_fasta(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const uint8_t* fasta, uint64_t n_bytes,
-                           ScanState* S, uint64_t* n_bases_total, bool dual) {
+                           ScanState* S, uint64_t* n_bases_total, bool dual, bool speculate) {
     std::vector<uint64_t> cuts;
     split_fasta(fasta, n_bytes, (uint64_t)std::max(4096.0, ctx->ingest_chunk_bytes), cuts);
     const size_t nc = cuts.size() - 1;
@@ -1811,6 +1861,43 @@ static int front_end_fasta(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const
         if (rc) return rc;
         *n_bases_total += n_bases;
         rc = scan_chunk(ctx, S, d_b, d_i, n_pos); if (rc) return rc;
+        // ---- speculative scatter: once a quarter of the chunks has been scanned the bins' final sizes are forecast from the
+        // histogram so far (+15 %), and from then on every scanned chunk is scattered while the next ones are still on the bus.
+        // A bin that outgrows its region, or a chunk whose event list overflowed, drops the forecast: the job then scatters
+        // again after the last chunk, with the exact offsets, as it always did.
+        if (speculate && !S->spec.failed && nc >= 4) {
+            ChunkScan& C = S->chunks.back();
+            const size_t bB = (size_t)S->B * 8;
+            CK(cudaMemcpyAsync(C.n_events2, C.d_count, 16, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(&C.ev_ovf, C.d_ovf, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            if (!S->spec.on) CK(cudaMemcpyAsync(S->h_rec.data(), S->d_hist_rec, bB, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            C.n_events = C.n_events2[0];
+            if (C.ev_ovf) S->spec.failed = true;
+            else {
+                if (!S->spec.on && (c + 1) * 4 >= nc) {
+                    const double scale = (double)n_bytes / (double)cuts[c + 1] * 1.15;
+                    S->spec.base.assign((size_t)S->B + 1, 0);
+                    for (int32_t b = 0; b < S->B; b++)
+                        S->spec.base[(size_t)b + 1] = S->spec.base[(size_t)b] + (unsigned long long)((double)S->h_rec[(size_t)b] * scale) + 1024ull;
+                    const int rbytes = cfg->k > 32 ? 32 : 16;
+                    S->spec.cursor_shift = cursor_shift_for(S->B);
+                    CK(dmalloc(ctx, &S->spec.d_records, (size_t)S->spec.base[(size_t)S->B] * rbytes));
+                    CK(dmalloc(ctx, &S->spec.d_bin_base, bB + 8)); CK(dmalloc(ctx, &S->spec.d_ovf, 8));
+                    CK(dmalloc(ctx, &S->spec.d_cursor, ((size_t)S->B << S->spec.cursor_shift) * 8));
+                    CK(cudaMemcpyAsync(S->spec.d_bin_base, S->spec.base.data(), bB + 8, cudaMemcpyHostToDevice, ctx->stream));
+                    CK(cudaMemsetAsync(S->spec.d_cursor, 0, ((size_t)S->B << S->spec.cursor_shift) * 8, ctx->stream));
+                    CK(cudaMemsetAsync(S->spec.d_ovf, 0, 8, ctx->stream));
+                    S->spec.on = true;
+                }
+                if (S->spec.on)
+                    for (; S->spec.next_chunk <= c; S->spec.next_chunk++) {
+                        rc = scatter_chunk(ctx, S, S->chunks[S->spec.next_chunk], S->spec.d_bin_base, S->spec.d_cursor, S->spec.cursor_shift,
+                                           S->spec.d_records, S->spec.d_ovf);
+                        if (rc) return rc;
+                    }
+            }
+        }
     }
     return FKM_OK;
 }
@@ -1825,7 +1912,8 @@ extern "C" int fkm_count_fasta(fkm_ctx* ctx, const fkm_config* cfg, const uint8_
     memset(st, 0, sizeof *st);
     ScanState S; uint64_t n_bases = 0;
     ctx->job_split = choose_split(ctx, cfg, B, n_bytes);
-    rc = front_end_fasta(ctx, cfg, B << ctx->job_split, fasta, n_bytes, &S, &n_bases, want_smem_path(ctx, cfg)); if (rc) return rc;
+    rc = front_end_fasta(ctx, cfg, B << ctx->job_split, fasta, n_bytes, &S, &n_bases, want_smem_path(ctx, cfg),
+                         cfg->use_ht && ctx->count_mode >= 2.0 && ctx->speculative_scatter >= 1.0); if (rc) return rc;
     fkm_stats tmp; memset(&tmp, 0, sizeof tmp);
     rc = scan_end(ctx, &S, &tmp); if (rc) return rc;
     const double ms_in = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -1879,7 +1967,7 @@ extern "C" int fkm_execute_job(fkm_ctx* ctx, const fkm_config* cfg, fkm_stats* s
 
 // ------------------------------------------------------------------ staged entry points (multi-GPU)
 static int front_end_fasta(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, const uint8_t* fasta, uint64_t n_bytes,
-                           ScanState* S, uint64_t* n_bases_total, bool dual);
+                           ScanState* S, uint64_t* n_bases_total, bool dual, bool speculate);
 extern "C" int32_t fkm_record_bytes(const fkm_config* cfg) { return (cfg && cfg->k > 32) ? 32 : 16; }
 
 extern "C" int fkm_mg_scan(fkm_ctx* ctx, const fkm_config* cfg, const void* d_bases, const void* d_inv, uint64_t n_pos,
@@ -1907,7 +1995,7 @@ extern "C" int fkm_mg_scan_fasta(fkm_ctx* ctx, const fkm_config* cfg, const uint
     uint64_t nb = 0;
     ctx->job_split = choose_split(ctx, cfg, B, n_bytes);
     B <<= ctx->job_split;                        // the histograms are per INTERNAL bin (fkm_job_bins entries)
-    rc = front_end_fasta(ctx, cfg, B, fasta, n_bytes, ctx->mg_scan, &nb, false); if (rc) return rc;
+    rc = front_end_fasta(ctx, cfg, B, fasta, n_bytes, ctx->mg_scan, &nb, false, false); if (rc) return rc;
     if (n_bases) *n_bases = nb;
     fkm_stats st; memset(&st, 0, sizeof st);
     rc = scan_end(ctx, ctx->mg_scan, &st); if (rc) return rc;

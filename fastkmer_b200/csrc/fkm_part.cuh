@@ -40,6 +40,7 @@ __device__ __forceinline__ unsigned long long part_lin_base(unsigned long long k
 struct PartParams {
     const void* records;                        // bin-major super-k-mer records
     const unsigned long long* bin_rec_base;     // [B+1] record offset of every bin (global bin ids)
+    const unsigned long long* bin_rec_cnt;      // [B] records of every bin when the bins' regions have gaps (speculative scatter), else NULL
     int bin_lo, bin_hi;                         // bins of this batch; every array below is indexed by b - bin_lo
     const uint32_t* tile_first;                 // [nb+1] first tile of the bin
     const uint32_t* sub_first;                  // [nb+1] first sub-bucket of the bin
@@ -157,16 +158,21 @@ __global__ void __launch_bounds__(PartGeom<WIDE>::kThreads) k_expand_hist(const 
         const uint32_t Pn = P.sub_first[b + 1] - P.sub_first[b];
         const uint32_t tl = tile - P.tile_first[b];
         const unsigned long long r_lo = P.bin_rec_base[P.bin_lo + b] + (unsigned long long)tl * TR;
-        const unsigned long long r_hi = min(r_lo + (unsigned long long)TR, P.bin_rec_base[P.bin_lo + b + 1]);
+        const unsigned long long r_end = P.bin_rec_cnt ? P.bin_rec_base[P.bin_lo + b] + P.bin_rec_cnt[P.bin_lo + b] : P.bin_rec_base[P.bin_lo + b + 1];
+        const unsigned long long r_hi = min(r_lo + (unsigned long long)TR, r_end);
         for (uint32_t i = threadIdx.x; i < Pn; i += kPartThreads) s_hist[i] = 0u;
         const unsigned long long r = r_lo + threadIdx.x;
         const uint32_t nk = part_stage_record<WIDE>(P.records, r, r < r_hi, &s_rec[warp][lane * RB]);
         const uint32_t wt = __reduce_add_sync(0xFFFFFFFFu, nk);
         if (lane == 0) s_wtot[warp] = wt;
         __syncthreads();
-        uint32_t wb = 0, tot = 0;
+        // exclusive prefix of the warps' k-mer counts: one shuffle scan over the (at most 16) totals
+        const uint32_t wv = lane < kPartWarps ? s_wtot[lane] : 0u;
+        uint32_t winc = wv;
 #pragma unroll
-        for (int i = 0; i < kPartWarps; i++) { const uint32_t t = s_wtot[i]; if (i < warp) wb += t; tot += t; }
+        for (int d = 1; d < kPartWarps; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, winc, d); if (lane >= d) winc += t; }
+        const uint32_t tot = __shfl_sync(0xFFFFFFFFu, winc, kPartWarps - 1);
+        const uint32_t wb = __shfl_sync(0xFFFFFFFFu, winc - wv, warp);
         if (threadIdx.x == 0) {
             const uint32_t k0 = atomicAdd(&P.bin_key_cursor[b], (tot + 1u) & ~1u);
             s_key0 = k0; P.tile_key_off[tile] = part_lin_base(P.key_base[b], P.tile_first[b], b) + k0; P.tile_nkeys[tile] = tot;
@@ -409,8 +415,8 @@ __device__ __forceinline__ bool kc_probe(key128* slot, key128 key, bool& hit) {
 // ... (every warp load is one contiguous 256- or 512-byte piece; two loads per thread are in flight), and a thread whose
 // key is done moves on to its next one while its neighbours still probe: the warp makes one probe per lane per round
 // whatever the lengths of the probe chains.
-template <bool WIDE>
-__global__ void __launch_bounds__(kKcThreads, 1) k_count_keys(const KeyCountParams P) {
+template <bool WIDE, int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT) k_count_keys(const KeyCountParams P) {
     typedef typename SmTraits<WIDE>::Key Key;
     extern __shared__ __align__(128) unsigned char kc_raw[];
     Key* const t_keys = reinterpret_cast<Key*>(kc_raw);
@@ -421,7 +427,7 @@ __global__ void __launch_bounds__(kKcThreads, 1) k_count_keys(const KeyCountPara
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const Key empty = sm_empty(Key());
     const uint32_t mask = P.cap_slots - 1u;
-    for (uint32_t i = threadIdx.x; i < P.cap_slots; i += kKcThreads) { t_keys[i] = empty; t_cnt[i] = 0; }
+    for (uint32_t i = threadIdx.x; i < P.cap_slots; i += NT) { t_keys[i] = empty; t_cnt[i] = 0; }
     if (threadIdx.x == 0) {
         s_nclaim = 0; s_pos = 0; s_ovf = 0;
         // this CTA's sub-buckets: [first whose key offset >= c * total / G, the same for c + 1)
@@ -459,9 +465,9 @@ __global__ void __launch_bounds__(kKcThreads, 1) k_count_keys(const KeyCountPara
         {
             const uint32_t K32 = (uint32_t)K;               // (a bin, hence a sub-bucket, has fewer than 2^32 k-mers)
             uint32_t p = threadIdx.x;
-            bool have = p < K32; Key key = Key(); if (have) key = kc_load(kp + p); p += kKcThreads;
-            bool hn = p < K32; Key nxt = Key(); if (hn) nxt = kc_load(kp + p); p += kKcThreads;
-            bool hn2 = p < K32; Key nxt2 = Key(); if (hn2) nxt2 = kc_load(kp + p); p += kKcThreads;     // two loads in flight behind the key at work
+            bool have = p < K32; Key key = Key(); if (have) key = kc_load(kp + p); p += NT;
+            bool hn = p < K32; Key nxt = Key(); if (hn) nxt = kc_load(kp + p); p += NT;
+            bool hn2 = p < K32; Key nxt2 = Key(); if (hn2) nxt2 = kc_load(kp + p); p += NT;     // two loads in flight behind the key at work
             uint32_t slot = part_slot(part_hash(key), mask), probes = 0;
             while (have) {
                 bool hit;
@@ -472,7 +478,7 @@ __global__ void __launch_bounds__(kKcThreads, 1) k_count_keys(const KeyCountPara
                 }
                 if (hit) {
                     atomicAdd(&t_cnt[slot], 1u);             // (cannot wrap: a sub-bucket has fewer than 2^32 k-mers)
-                    have = hn; key = nxt; hn = hn2; nxt = nxt2; hn2 = p < K32; if (hn2) nxt2 = kc_load(kp + p); p += kKcThreads;
+                    have = hn; key = nxt; hn = hn2; nxt = nxt2; hn2 = p < K32; if (hn2) nxt2 = kc_load(kp + p); p += NT;
                     slot = part_slot(part_hash(key), mask); probes = 0;
                 } else {
                     slot = (slot + 1u) & mask;
@@ -486,11 +492,11 @@ __global__ void __launch_bounds__(kKcThreads, 1) k_count_keys(const KeyCountPara
         if (slow) {
             // too many distinct k-mers for the shared-memory table: redo the sub-bucket in this CTA's private global table
             __syncthreads();
-            for (uint32_t i = threadIdx.x; i < P.cap_slots; i += kKcThreads) { t_keys[i] = empty; t_cnt[i] = 0; }
+            for (uint32_t i = threadIdx.x; i < P.cap_slots; i += NT) { t_keys[i] = empty; t_cnt[i] = 0; }
             gkeys = reinterpret_cast<Key*>(P.slow_keys) + (size_t)blockIdx.x * P.slow_slots;
             gcnt = P.slow_cnt + (size_t)blockIdx.x * P.slow_slots;
             if (!slow_ready) {                               // first use by this CTA (the dump below leaves it empty again)
-                for (unsigned long long i = threadIdx.x; i < P.slow_slots; i += kKcThreads) { gkeys[i] = empty; gcnt[i] = 0; }
+                for (unsigned long long i = threadIdx.x; i < P.slow_slots; i += NT) { gkeys[i] = empty; gcnt[i] = 0; }
                 slow_ready = true;
             }
             if (threadIdx.x == 0) { s_nclaim = 0; s_ovf = 0; atomicAdd(&P.counters[0], 1ull); }
@@ -499,7 +505,7 @@ __global__ void __launch_bounds__(kKcThreads, 1) k_count_keys(const KeyCountPara
                 const bool full = s_nclaim > P.slow_max_fill;                        // uniform: read between two barriers
                 unsigned int cl = 0, failed = 0;
                 if (!full)
-                    for (unsigned long long i = c0 + threadIdx.x; i < min(K, c0 + 65536ull); i += kKcThreads) {
+                    for (unsigned long long i = c0 + threadIdx.x; i < min(K, c0 + 65536ull); i += NT) {
                         const int c = gm_insert(gkeys, gcnt, P.slow_slots, kc_load(kp + i), &wrapped);
                         if (c > 0) cl++; else if (c < 0) failed = 1;
                     }
@@ -519,7 +525,7 @@ __global__ void __launch_bounds__(kKcThreads, 1) k_count_keys(const KeyCountPara
         const uint64_t hpre = mix64(hbin);                   // entry_hash's inner term when hi == 0 (64-bit keys)
         auto emit = [&](unsigned long long o, Key kk, uint32_t n) { if (!skip) { okeys[o] = kk; ocnt[o] = n; } };
         if (!slow) {
-            for (unsigned int i = threadIdx.x; i < D; i += kKcThreads) {
+            for (unsigned int i = threadIdx.x; i < D; i += NT) {
                 const uint32_t sl = t_list[i];
                 const Key kk = t_keys[sl]; const uint32_t n = t_cnt[sl];
                 t_keys[sl] = empty; t_cnt[sl] = 0;
@@ -531,7 +537,7 @@ __global__ void __launch_bounds__(kKcThreads, 1) k_count_keys(const KeyCountPara
                 }
             }
         } else {
-            for (unsigned long long s0 = 0; s0 < P.slow_slots; s0 += kKcThreads) {
+            for (unsigned long long s0 = 0; s0 < P.slow_slots; s0 += NT) {
                 const unsigned long long s = s0 + threadIdx.x;
                 Key kk = empty; uint32_t n = 0;
                 if (s < P.slow_slots) {
@@ -553,7 +559,7 @@ __global__ void __launch_bounds__(kKcThreads, 1) k_count_keys(const KeyCountPara
         __syncthreads();                                     // the sub-bucket's entries are in the output region (visible to the whole CTA)
         // digest over the dense entries: every lane busy (the lines were just written and sit in L2)
         if (!skip && slow) {
-            for (unsigned int i = threadIdx.x; i < D; i += kKcThreads) {
+            for (unsigned int i = threadIdx.x; i < D; i += NT) {
                 Key kk; const uint32_t n = __ldcg(&ocnt[off + i]);
                 uint64_t h;                                  // == entry_hash(bin, hi, lo)
                 if constexpr (!WIDE) { kk = __ldcg(&okeys[off + i]); h = mix64(kk ^ hpre); }
@@ -573,7 +579,7 @@ __global__ void __launch_bounds__(kKcThreads, 1) k_count_keys(const KeyCountPara
         dsum += __shfl_xor_sync(0xFFFFFFFFu, dsum, o); dxor ^= __shfl_xor_sync(0xFFFFFFFFu, dxor, o); dcnt += __shfl_xor_sync(0xFFFFFFFFu, dcnt, o);
     }
     if (lane == 0 && dcnt) {
-        const int a = (blockIdx.x * (kKcThreads / 32) + warp) & 63;
+        const int a = (blockIdx.x * (NT / 32) + warp) & 63;
         atomicAdd(&P.acc[a], dsum); atomicXor(&P.acc[64 + a], dxor); atomicAdd(&P.acc[128 + a], dcnt);
     }
 }

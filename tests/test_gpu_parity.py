@@ -619,6 +619,36 @@ def test_streamed_fasta_chunks(oracle):
         c2.close()
 
 
+def test_speculative_scatter_under_the_copy(oracle):
+    """Hash path, FASTA input in several chunks: after a quarter of the chunks the bins' sizes are forecast and every scanned chunk is
+    scattered at once (bin regions with slack; k_expand_hist reads around the gaps).  Same result as the oracle with the forecast
+    in use, with it switched off, and when a bin outgrows its region (the first chunks hold one read over and over: they say nothing
+    about the bins of the later ones), where the job scatters again with the exact offsets."""
+    spec = dict(seeds=(101, 102, 103), genome_len=400000, n_reads=60000, read_len=150)
+    shuffled = fk.synth_fasta(spec).tobytes()
+    rng = random.Random(7)
+    one = "".join(rng.choice("ACGT") for _ in range(150))
+    skewed = ("".join(">same%d\n%s\n" % (i, one) for i in range(30000)).encode() +            # the first third of the text fills a handful of bins ...
+              fk.synth_fasta(dict(seeds=(104, 105, 106), genome_len=3000000, n_reads=300000, read_len=150)).tobytes())   # ... the rest all of them
+    c2 = fk.Context(0)
+    try:
+        c2.set("ingest_chunk_bytes", 400000)
+        for text, label in ((shuffled, "shuffled"), (skewed, "skewed")):
+            for k, m in ((28, 10), (55, 13)):
+                want = oracle.count(text, k, m, 3, 2048, 1, threads=8)
+                rb = 16 if k <= 32 else 32
+                for on in (1, 0):
+                    c2.set("speculative_scatter", on)
+                    res, st = c2.count_fasta(cfg(k, m, 3, 2048, 1), text)
+                    what = "%s k=%d speculative %d" % (label, k, on)
+                    assert_same(res.sorted_arrays(), want, what)
+                    assert (st["digest_sum"], st["digest_xor"], st["n_kmers"]) == (want["stats"]["digest_sum"], want["stats"]["digest_xor"], want["stats"]["n_kmers"]), what
+                    used = st["superkmer_bytes"] > st["n_superkmers"] * rb           # regions with slack
+                    assert used == (on == 1 and label == "shuffled"), what
+    finally:
+        c2.close()
+
+
 # ---------------------------------------------------------------- multi-GPU stages, emulated rank by rank on one GPU
 @pytest.mark.parametrize("world,k,m,ht", [(2, 28, 10, 1), (3, 28, 10, 0), (4, 55, 13, 1), (2, 55, 13, 0)])
 def test_multigpu_stages_emulated(ctx, oracle, world, k, m, ht):
