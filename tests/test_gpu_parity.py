@@ -628,18 +628,18 @@ def test_speculative_scatter_under_the_copy(oracle):
     shuffled = fk.synth_fasta(spec).tobytes()
     rng = random.Random(7)
     one = "".join(rng.choice("ACGT") for _ in range(150))
-    skewed = ("".join(">same%d\n%s\n" % (i, one) for i in range(30000)).encode() +            # the first third of the text fills a handful of bins ...
-              fk.synth_fasta(dict(seeds=(104, 105, 106), genome_len=3000000, n_reads=300000, read_len=150)).tobytes())   # ... the rest all of them
+    skewed = ("".join(">same%d\n%s\n" % (i, one) for i in range(100000)).encode() +           # the first third of the text fills a handful of bins ...
+              fk.synth_fasta(dict(seeds=(104, 105, 106), genome_len=2000000, n_reads=200000, read_len=150)).tobytes())   # ... the rest all of them
     c2 = fk.Context(0)
     try:
         c2.set("ingest_chunk_bytes", 400000)
         for text, label in ((shuffled, "shuffled"), (skewed, "skewed")):
             for k, m in ((28, 10), (55, 13)):
-                want = oracle.count(text, k, m, 3, 2048, 1, threads=8)
+                want = oracle.count(text, k, m, 3, 256, 1, threads=8)
                 rb = 16 if k <= 32 else 32
                 for on in (1, 0):
                     c2.set("speculative_scatter", on)
-                    res, st = c2.count_fasta(cfg(k, m, 3, 2048, 1), text)
+                    res, st = c2.count_fasta(cfg(k, m, 3, 256, 1), text)
                     what = "%s k=%d speculative %d" % (label, k, on)
                     assert_same(res.sorted_arrays(), want, what)
                     assert (st["digest_sum"], st["digest_xor"], st["n_kmers"]) == (want["stats"]["digest_sum"], want["stats"]["digest_xor"], want["stats"]["n_kmers"]), what
