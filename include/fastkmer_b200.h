@@ -91,13 +91,23 @@ const char* fkm_last_error(void);
 int  fkm_ctx_create(int device, void* stream, fkm_ctx** out);
 void fkm_ctx_destroy(fkm_ctx* ctx);
 int  fkm_ctx_sync(fkm_ctx* ctx);
-/* tuning knobs (optional): "count_mode" (use_ht = 1: 0 = tables in global memory, the default; 1 = tables in shared memory,
- * csrc/fkm_smem.cuh: DRAM sees the records once and the result once and the stage does not depend on the input size),
- * "smem_table_slots" / "smem_slow_slots" (test hooks: smaller tables force the slow path / the global-table fallback),
- * and name in {"table_budget_bytes","async_table_bytes","sort_budget_keys","load_factor","ingest_chunk_bytes",
- * "fold_records" (default 1: hash path with k <= 32 folds identical super-k-mer records into one weighted record before
- * counting, unless the sampled first bins show more than "fold_max_ratio" (0.6) distinct records; 0 = never), "fold_table_bytes", "fold_pool" (records per warp in k_fold_insert: 64, 128, 256),
- * "cas_first" (experiment: probe with the CAS itself; slower, see profiles/README.md)} */
+/* tuning knobs (optional).
+ * "count_mode" (use_ht = 1): 2 = the canonical k-mers of a bin are expanded once, hash-partitioned into sub-buckets and counted in
+ *   tables in shared memory (csrc/fkm_part.cuh; the default: DRAM sees the records once, the keys twice and the result once, and
+ *   the stage does not depend on the input size); 1 = dual-minimizer mid bins, tables in shared memory (csrc/fkm_smem.cuh);
+ *   0 = tables in global memory with record folding (round 1; also the fallback of mode 2).
+ * "sort_partition" (use_ht = 0): 1 = k-mers expanded once, sub-buckets by their top bits, chunk sort in shared memory (default);
+ *   2 = ordered shared-memory tables (k_count_keys_ordered, opt-in); 0 = the round-1 passes.
+ * "bin_split": internal bins per bin on the hash path (0 = chosen from the input size; a power of two otherwise, the same on every
+ *   rank of a multi-GPU job), see fkm_job_bins.  "speculative_scatter" (default 1): the FASTA front end scatters every scanned
+ *   chunk under the PCIe copy into bin regions sized from a forecast.  "part_fill" (0.45), "part_budget_keys" (2^30),
+ *   "part_max_subs" (768), "part_two_ctas" (0): planning of the partitioned stage.
+ * "smem_table_slots" / "smem_slow_slots" / "debug_rho_scale" / "debug_event_scale" / "debug_force_lsd": test hooks (smaller tables
+ *   force the slow path / the global-table fallback, wrong estimates force the overflow paths).
+ * Also {"table_budget_bytes","async_table_bytes","sort_budget_keys","load_factor","ingest_chunk_bytes","smem_fill",
+ * "fold_records" (hash path in global tables with k <= 32: fold identical super-k-mer records into one weighted record before
+ * counting, unless the sampled first bins show more than "fold_max_ratio" (0.6) distinct records; 0 = never), "fold_table_bytes",
+ * "fold_pool", "cas_first" (experiment: probe with the CAS itself; slower, see profiles/README.md)} */
 int  fkm_ctx_set(fkm_ctx* ctx, const char* name, double value);
 
 /* b = min(4^m, max_b) and outputDir = outputDirectory + prefix + "k"+k+"_m"+m+"_x"+x+"_b"+b+"_s"+sequenceType
