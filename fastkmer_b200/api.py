@@ -310,6 +310,13 @@ class Context:
 
     # ---- the drop-in call (SparkBinKmerCounter.scala:989)
     def execute_job(self, configuration) -> Stats:
+        if getattr(configuration, "debug", False) and configuration.write:
+            # debug = true moves the output to /tmp/<stem> without the _s<type> suffix (test/package.scala:33): count here, write there
+            with open(configuration.dataset, "rb") as f:
+                text = f.read()
+            res, st = self.count_fasta(configuration, text)
+            res.write(configuration.outputDir)
+            return st
         st = fkm_stats()
         cfg = _cfg(configuration)
         _check(load_library().fkm_execute_job(self._h, C.byref(cfg), C.byref(st)))
