@@ -2237,30 +2237,58 @@ extern "C" int fkm_multiseq_fasta(fkm_ctx* ctx, const fkm_config* cfg, const uin
     if (!ctx || !n_samples || !dist || max_samples < 1) return fkm_set_error(FKM_EINVAL, "bad argument");
     int32_t B = 0; int rc = validate(cfg, &B); if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
-    // ---- split the records by sample tag (first run of [A-Za-z0-9_] of the header)
+    // ---- split the records by sample tag (first run of [A-Za-z0-9_] of the header).  Two passes: the record boundaries
+    // (memchr for '>' at a line start) and their samples first, then every sample's text is gathered by its own host thread.
     std::vector<std::string> tags; std::vector<std::vector<uint8_t>> texts;
     {
-        const uint8_t* t = fasta; uint64_t i = 0; bool bol = true;
-        while (i < n_bytes && !(bol && t[i] == '>')) { bol = (t[i] == '\n'); i++; }
-        while (i < n_bytes) {
-            const uint64_t rec0 = i;
+        const uint8_t* t = fasta;
+        struct Rec { uint64_t lo, hi; uint32_t sample; };
+        std::vector<Rec> recs;
+        auto next_header = [&](uint64_t from) -> uint64_t {         // first '>' at the start of a line at or after `from`
+            while (from < n_bytes) {
+                const uint8_t* p0 = (const uint8_t*)memchr(t + from, '>', (size_t)(n_bytes - from));
+                if (!p0) return n_bytes;
+                const uint64_t at = (uint64_t)(p0 - t);
+                if (at == 0 || t[at - 1] == '\n') return at;
+                from = at + 1;
+            }
+            return n_bytes;
+        };
+        auto isw = [](uint8_t c) { return (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z') || (c >= '0' && c <= '9') || c == '_'; };
+        size_t last = 0;
+        for (uint64_t i = next_header(0); i < n_bytes;) {
             uint64_t j = i + 1;
-            auto isw = [](uint8_t c) { return (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z') || (c >= '0' && c <= '9') || c == '_'; };
             while (j < n_bytes && t[j] != '\n' && !isw(t[j])) j++;
             uint64_t e = j; while (e < n_bytes && isw(t[e])) e++;
-            std::string tag((const char*)t + j, (size_t)(e - j));
-            while (i < n_bytes && t[i] != '\n') i++;
-            if (i < n_bytes) i++;
-            bol = true;
-            while (i < n_bytes && !(bol && t[i] == '>')) { bol = (t[i] == '\n'); i++; }
-            size_t sidx = 0; while (sidx < tags.size() && tags[sidx] != tag) sidx++;
-            if (sidx == tags.size()) {
-                if ((int32_t)tags.size() == max_samples) return fkm_set_error(FKM_EINVAL, "more than %d samples in the input", max_samples);
-                tags.push_back(tag); texts.emplace_back();
+            const size_t len = (size_t)(e - j);
+            const uint64_t nxt = next_header(i + 1);
+            size_t sidx = last;                                       // the records of a sample usually follow each other
+            if (!(sidx < tags.size() && tags[sidx].size() == len && !memcmp(tags[sidx].data(), t + j, len))) {
+                for (sidx = 0; sidx < tags.size(); sidx++) if (tags[sidx].size() == len && !memcmp(tags[sidx].data(), t + j, len)) break;
+                if (sidx == tags.size()) {
+                    if ((int32_t)tags.size() == max_samples) return fkm_set_error(FKM_EINVAL, "more than %d samples in the input", max_samples);
+                    tags.emplace_back((const char*)t + j, len);
+                }
             }
-            texts[sidx].insert(texts[sidx].end(), t + rec0, t + i);
-            if (texts[sidx].empty() || texts[sidx].back() != '\n') texts[sidx].push_back('\n');
+            last = sidx;
+            recs.push_back(Rec{i, nxt, (uint32_t)sidx});
+            i = nxt;
         }
+        texts.resize(tags.size());
+        std::vector<uint64_t> bytes(tags.size(), 0);
+        for (const Rec& r : recs) bytes[r.sample] += r.hi - r.lo + 1;
+        std::vector<std::thread> th;
+        for (size_t a = 0; a < tags.size(); a++)
+            th.emplace_back([&, a]() {
+                std::vector<uint8_t>& out = texts[a];
+                out.reserve((size_t)bytes[a]);
+                for (const Rec& r : recs)
+                    if (r.sample == a) {
+                        out.insert(out.end(), t + r.lo, t + r.hi);
+                        if (out.back() != '\n') out.push_back('\n');
+                    }
+            });
+        for (auto& x : th) x.join();
     }
     const int S = (int)tags.size();
     *n_samples = S;
