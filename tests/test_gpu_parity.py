@@ -645,6 +645,11 @@ def test_speculative_scatter_under_the_copy(oracle):
                     assert (st["digest_sum"], st["digest_xor"], st["n_kmers"]) == (want["stats"]["digest_sum"], want["stats"]["digest_xor"], want["stats"]["n_kmers"]), what
                     used = st["superkmer_bytes"] > st["n_superkmers"] * rb           # regions with slack
                     assert used == (on == 1 and label == "shuffled"), what
+                c2.set("speculative_scatter", 1)
+                c2.set("bin_split", 4)                                               # the forecast is per internal bin
+                res, st = c2.count_fasta(cfg(k, m, 3, 256, 1), text)
+                assert_same(res.sorted_arrays(), want, "%s k=%d speculative, 4 internal bins per bin" % (label, k))
+                c2.set("bin_split", 0)
     finally:
         c2.close()
 
