@@ -570,8 +570,8 @@ static int count_partitioned(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, con
     const uint32_t tail = ordered ? 512u : 0u;
     const size_t kc_smem = ordered ? (size_t)(cap + tail) * (sizeof(Key) + 4) : (size_t)cap * (sizeof(Key) + 6);
     const size_t sc_smem = (size_t)PartGeom<WIDE>::kBufKeys * (sizeof(Key) + 2);
-    CK(cudaFuncSetAttribute(k_count_keys<WIDE, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)cap * (sizeof(Key) + 6))));
-    CK(cudaFuncSetAttribute(k_count_keys<WIDE, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)cap * (sizeof(Key) + 6))));
+    CK(cudaFuncSetAttribute(k_count_keys<WIDE, 1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)cap * (sizeof(Key) + 6))));
+    CK(cudaFuncSetAttribute(k_count_keys<WIDE, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)cap * (sizeof(Key) + 6))));
     CK(cudaFuncSetAttribute(k_count_keys_ordered<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)(cap + 512u) * (sizeof(Key) + 4))));
     CK(cudaFuncSetAttribute(k_place_keys<WIDE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
     CK(cudaFuncSetAttribute(k_place_keys<WIDE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem));
@@ -682,12 +682,14 @@ static int count_partitioned(fkm_ctx* ctx, const fkm_config* cfg, int32_t B, con
                 KeyCountParams Q;
                 Q.keys = d_keys; Q.mid_key_base = d_mid_key; Q.mid_bin = d_mid_bin; Q.sub_first = P.sub_first; Q.bin_lo = bt.lo; Q.n_sub = (uint32_t)bt.n_sub;
                 Q.out_keys = ok[i - b0]; Q.out_cnt = oc[i - b0]; Q.region_cap = bt.region_cap; Q.cta_total = d_cta_total + (i - b0) * grid;
-                Q.bin_cta = d_bin_cta; Q.bin_off = d_bin_off; Q.acc = d_acc; Q.cap_slots = cap; Q.max_fill = cap * 3 / 4;
+                Q.bin_cta = d_bin_cta; Q.bin_off = d_bin_off; Q.acc = d_acc; Q.cap_slots = cap;
+                Q.max_fill = cap > 4096u ? cap - 2048u : cap > 64u ? cap / 2 : 0u;        // (tiny test tables: the threads' claims in flight can exceed the table, see k_count_keys)
                 Q.slow_keys = d_slow_keys; Q.slow_cnt = d_slow_cnt; Q.slow_slots = slow_slots; Q.slow_max_fill = slow_slots * 7 / 10; Q.flags = d_flags; Q.counters = d_counters;
                 Q.k = cfg->k; Q.tail_slots = tail; Q.bin_shift = ctx->job_split;
                 if (ordered) k_count_keys_ordered<WIDE><<<grid, kKcThreads, kc_smem, s>>>(Q);
-                else if (two) k_count_keys<WIDE, 512><<<grid, 512, kc_smem, s>>>(Q);
-                else k_count_keys<WIDE, 1024><<<grid, 1024, kc_smem, s>>>(Q);
+                else if (cap < 4096u) k_count_keys<WIDE, 1024, true><<<grid, 1024, kc_smem, s>>>(Q);      // (test tables)
+                else if (two) k_count_keys<WIDE, 512, false><<<grid, 512, kc_smem, s>>>(Q);
+                else k_count_keys<WIDE, 1024, false><<<grid, 1024, kc_smem, s>>>(Q);
                 CKL();
             } else CK(cudaEventRecord(ctx->evpool[3 * (i - b0) + 1], s));
             CK(cudaEventRecord(ctx->evpool[3 * (i - b0) + 2], s));

@@ -415,7 +415,7 @@ __device__ __forceinline__ bool kc_probe(key128* slot, key128 key, bool& hit) {
 // ... (every warp load is one contiguous 256- or 512-byte piece; two loads per thread are in flight), and a thread whose
 // key is done moves on to its next one while its neighbours still probe: the warp makes one probe per lane per round
 // whatever the lengths of the probe chains.
-template <bool WIDE, int NT>
+template <bool WIDE, int NT, bool GUARD>
 __global__ void __launch_bounds__(NT, 1024 / NT) k_count_keys(const KeyCountParams P) {
     typedef typename SmTraits<WIDE>::Key Key;
     extern __shared__ __align__(128) unsigned char kc_raw[];
@@ -468,6 +468,10 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_count_keys(const KeyCountPara
             bool have = p < K32; Key key = Key(); if (have) key = kc_load(kp + p); p += NT;
             bool hn = p < K32; Key nxt = Key(); if (hn) nxt = kc_load(kp + p); p += NT;
             bool hn2 = p < K32; Key nxt2 = Key(); if (hn2) nxt2 = kc_load(kp + p); p += NT;     // two loads in flight behind the key at work
+            // The table never fills up: a lane whose claim is number max_fill or later (max_fill = slots - 2 * threads: every thread
+            // has at most one claim in flight) raises the overflow flag and stops, so a probe sequence always meets its key or an
+            // empty slot and the miss path is one increment.
+            // (Tables of fewer than 4096 slots — test knob — can fill up under 1024 concurrent claims: GUARD counts the probes.)
             uint32_t slot = part_slot(part_hash(key), mask), probes = 0;
             while (have) {
                 bool hit;
@@ -475,6 +479,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_count_keys(const KeyCountPara
                     unsigned int pos;                        // (plain per-lane ATOMS: the compiler's warp-aggregated form costs 15 more instructions a round)
                     asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(smem_addr(&s_nclaim)) : "memory");
                     t_list[pos] = (unsigned short)slot;
+                    if (pos >= P.max_fill) { s_ovf = 1; have = false; hit = false; }
                 }
                 if (hit) {
                     atomicAdd(&t_cnt[slot], 1u);             // (cannot wrap: a sub-bucket has fewer than 2^32 k-mers)
@@ -482,7 +487,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_count_keys(const KeyCountPara
                     slot = part_slot(part_hash(key), mask); probes = 0;
                 } else {
                     slot = (slot + 1u) & mask;
-                    if (++probes > kKcMaxProbe) { s_ovf = 1; have = false; }
+                    if constexpr (GUARD) { if (++probes > kKcMaxProbe) { s_ovf = 1; have = false; } }
                 }
             }
         }
