@@ -94,6 +94,7 @@ def load_library():
         "fkm_debug_window_bins": (C.c_int, [vp, cfgp, vp, vp, u64, vp]),
         "fkm_record_bytes": (i32, [cfgp]),
         "fkm_job_bins": (C.c_int, [vp, cfgp, u64, C.POINTER(i32)]),
+        "fkm_debug_multi_plan": (C.c_int, [i32, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, u64, C.POINTER(u64)]),
         "fkm_mg_scan": (C.c_int, [vp, cfgp, vp, vp, u64, vp, vp]),
         "fkm_mg_scan_fasta": (C.c_int, [vp, cfgp, vp, u64, vp, vp, C.POINTER(u64)]),
         "fkm_mg_scatter": (C.c_int, [vp, vp, vp]),

@@ -2070,6 +2070,73 @@ struct MultiPlan {                              // the part of multigpu.plan_exc
     std::vector<uint64_t> bin_rec, bin_kmer;    // [Bi]   records / k-mers of the bins r owns (0 elsewhere)
     std::vector<uint64_t> seg_src, seg_dst;     // received segments (source, bin) -> bin-major place
 };
+// Owners (LPT over the bins of the configuration: longest first, each to the least loaded GPU; ties by bin id, then rank — the same
+// map as multigpu.assign_owners) and every rank's exchange plan.  H_rec / H_kmer: [n][B * sp] records / k-mers every rank puts
+// into every internal bin; the sp internal bins of a bin share its owner.
+void multi_plan(int n, int B, int sp, const std::vector<std::vector<uint64_t>>& H_rec, const std::vector<std::vector<uint64_t>>& H_kmer,
+                std::vector<int>& owner_bin, std::vector<MultiPlan>& plan) {
+    const int Bi = B * sp;
+    std::vector<uint64_t> tot((size_t)B, 0);
+    for (int b = 0; b < Bi; b++) for (int i = 0; i < n; i++) tot[(size_t)(b / sp)] += H_kmer[(size_t)i][(size_t)b];
+    std::vector<int> order((size_t)B); for (int b = 0; b < B; b++) order[(size_t)b] = b;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b2) { return tot[(size_t)a] > tot[(size_t)b2]; });
+    std::vector<uint64_t> load((size_t)n, 0);
+    owner_bin.assign((size_t)B, 0);
+    for (int b : order) { int g = 0; for (int j = 1; j < n; j++) if (load[(size_t)j] < load[(size_t)g]) g = j; owner_bin[(size_t)b] = g; load[(size_t)g] += tot[(size_t)b]; }
+    auto owner = [&](int bi) { return owner_bin[(size_t)(bi / sp)]; };
+    plan.assign((size_t)n, MultiPlan());
+    for (int r = 0; r < n; r++) {
+        MultiPlan& P = plan[(size_t)r];
+        P.send_base.assign((size_t)Bi + 1, 0); P.send_off.assign((size_t)n + 1, 0); P.recv_off.assign((size_t)n + 1, 0);
+        P.bin_rec.assign((size_t)Bi, 0); P.bin_kmer.assign((size_t)Bi, 0);
+        uint64_t o = 0;
+        for (int g = 0; g < n; g++) {                                             // send buffer: bins ordered by (owner, bin)
+            P.send_off[(size_t)g] = o;
+            for (int b = 0; b < Bi; b++) if (owner(b) == g) { P.send_base[(size_t)b] = o; o += H_rec[(size_t)r][(size_t)b]; }
+        }
+        P.send_off[(size_t)n] = o; P.send_base[(size_t)Bi] = o;
+        uint64_t ro = 0;
+        for (int s2 = 0; s2 < n; s2++) { P.recv_off[(size_t)s2] = ro; for (int b = 0; b < Bi; b++) if (owner(b) == r) ro += H_rec[(size_t)s2][(size_t)b]; }
+        P.recv_off[(size_t)n] = ro;
+        std::vector<uint64_t> dst((size_t)Bi + 1, 0);
+        for (int b = 0; b < Bi; b++) {
+            if (owner(b) == r) for (int s2 = 0; s2 < n; s2++) { P.bin_rec[(size_t)b] += H_rec[(size_t)s2][(size_t)b]; P.bin_kmer[(size_t)b] += H_kmer[(size_t)s2][(size_t)b]; }
+            dst[(size_t)b + 1] = dst[(size_t)b] + P.bin_rec[(size_t)b];
+        }
+        P.seg_src.push_back(0);
+        std::vector<uint64_t> before((size_t)Bi, 0);
+        for (int s2 = 0; s2 < n; s2++)
+            for (int b = 0; b < Bi; b++)
+                if (owner(b) == r && H_rec[(size_t)s2][(size_t)b]) {
+                    P.seg_dst.push_back(dst[(size_t)b] + before[(size_t)b]);
+                    P.seg_src.push_back(P.seg_src.back() + H_rec[(size_t)s2][(size_t)b]);
+                    before[(size_t)b] += H_rec[(size_t)s2][(size_t)b];
+                }
+    }
+}
+}
+// test hook (no GPU needed): the plan fkm_execute_job_multi makes for rank `rank` of n, from host histograms [n][bins * split]
+extern "C" int fkm_debug_multi_plan(int32_t n, int32_t bins, int32_t split, const uint64_t* h_rec, const uint64_t* h_kmer, int32_t rank,
+                                    int32_t* owner, uint64_t* send_base, uint64_t* send_off, uint64_t* recv_off, uint64_t* bin_rec, uint64_t* bin_kmer,
+                                    uint64_t* seg_src, uint64_t* seg_dst, uint64_t seg_cap, uint64_t* n_seg) {
+    if (n < 1 || bins < 1 || split < 1 || rank < 0 || rank >= n || !h_rec || !h_kmer) return fkm_set_error(FKM_EINVAL, "bad argument");
+    const int Bi = bins * split;
+    std::vector<std::vector<uint64_t>> R((size_t)n), K((size_t)n);
+    for (int i = 0; i < n; i++) { R[(size_t)i].assign(h_rec + (size_t)i * Bi, h_rec + (size_t)(i + 1) * Bi); K[(size_t)i].assign(h_kmer + (size_t)i * Bi, h_kmer + (size_t)(i + 1) * Bi); }
+    std::vector<int> ob; std::vector<MultiPlan> plan;
+    multi_plan(n, bins, split, R, K, ob, plan);
+    const MultiPlan& P = plan[(size_t)rank];
+    if (P.seg_dst.size() > seg_cap) return fkm_set_error(FKM_EINVAL, "segment arrays too small");
+    if (owner) for (int b = 0; b < Bi; b++) owner[b] = ob[(size_t)(b / split)];
+    if (send_base) memcpy(send_base, P.send_base.data(), ((size_t)Bi + 1) * 8);
+    if (send_off) memcpy(send_off, P.send_off.data(), ((size_t)n + 1) * 8);
+    if (recv_off) memcpy(recv_off, P.recv_off.data(), ((size_t)n + 1) * 8);
+    if (bin_rec) memcpy(bin_rec, P.bin_rec.data(), (size_t)Bi * 8);
+    if (bin_kmer) memcpy(bin_kmer, P.bin_kmer.data(), (size_t)Bi * 8);
+    if (seg_src) memcpy(seg_src, P.seg_src.data(), P.seg_src.size() * 8);
+    if (seg_dst) memcpy(seg_dst, P.seg_dst.data(), P.seg_dst.size() * 8);
+    if (n_seg) *n_seg = P.seg_dst.size();
+    return FKM_OK;
 }
 extern "C" int fkm_execute_job_multi(const int32_t* devices, int32_t n_devices, const fkm_config* cfg, fkm_stats* stats) {
     int32_t B = 0; int rc = validate(cfg, &B); if (rc) return rc;
@@ -2129,45 +2196,10 @@ extern "C" int fkm_execute_job_multi(const int32_t* devices, int32_t n_devices, 
     rc = run_all([&](int i) { return fkm_mg_scan_fasta(ctx[(size_t)i], cfg, text + cut[(size_t)i], cut[(size_t)i + 1] - cut[(size_t)i],
                                                        H_rec[(size_t)i].data(), H_kmer[(size_t)i].data(), &nbases[(size_t)i]); });
     if (rc) { const std::string keep = g_err; cleanup(); g_err = keep; return rc; }
-    // ---- owners: LPT over the bins of the configuration (longest first, each to the least loaded GPU; ties by bin id, then rank)
-    std::vector<uint64_t> tot((size_t)B, 0);
-    for (int b = 0; b < Bi; b++) for (int i = 0; i < n; i++) tot[(size_t)(b / sp)] += H_kmer[(size_t)i][(size_t)b];
-    std::vector<int> order((size_t)B); for (int b = 0; b < B; b++) order[(size_t)b] = b;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b2) { return tot[(size_t)a] > tot[(size_t)b2]; });
-    std::vector<uint64_t> load((size_t)n, 0); std::vector<int> owner_bin((size_t)B, 0);
-    for (int b : order) { int g = 0; for (int j = 1; j < n; j++) if (load[(size_t)j] < load[(size_t)g]) g = j; owner_bin[(size_t)b] = g; load[(size_t)g] += tot[(size_t)b]; }
-    auto owner = [&](int bi) { return owner_bin[(size_t)(bi / sp)]; };
-    // ---- the exchange plan of every rank
+    // ---- owners and the exchange plan of every rank
     const int rb = fkm_record_bytes(cfg);
-    std::vector<MultiPlan> plan((size_t)n);
-    for (int r = 0; r < n; r++) {
-        MultiPlan& P = plan[(size_t)r];
-        P.send_base.assign((size_t)Bi + 1, 0); P.send_off.assign((size_t)n + 1, 0); P.recv_off.assign((size_t)n + 1, 0);
-        P.bin_rec.assign((size_t)Bi, 0); P.bin_kmer.assign((size_t)Bi, 0);
-        uint64_t o = 0;
-        for (int g = 0; g < n; g++) {                                             // send buffer: bins ordered by (owner, bin)
-            P.send_off[(size_t)g] = o;
-            for (int b = 0; b < Bi; b++) if (owner(b) == g) { P.send_base[(size_t)b] = o; o += H_rec[(size_t)r][(size_t)b]; }
-        }
-        P.send_off[(size_t)n] = o; P.send_base[(size_t)Bi] = o;
-        uint64_t ro = 0;
-        for (int s2 = 0; s2 < n; s2++) { P.recv_off[(size_t)s2] = ro; for (int b = 0; b < Bi; b++) if (owner(b) == r) ro += H_rec[(size_t)s2][(size_t)b]; }
-        P.recv_off[(size_t)n] = ro;
-        std::vector<uint64_t> dst((size_t)Bi + 1, 0);
-        for (int b = 0; b < Bi; b++) {
-            if (owner(b) == r) for (int s2 = 0; s2 < n; s2++) { P.bin_rec[(size_t)b] += H_rec[(size_t)s2][(size_t)b]; P.bin_kmer[(size_t)b] += H_kmer[(size_t)s2][(size_t)b]; }
-            dst[(size_t)b + 1] = dst[(size_t)b] + P.bin_rec[(size_t)b];
-        }
-        P.seg_src.push_back(0);
-        std::vector<uint64_t> before((size_t)Bi, 0);
-        for (int s2 = 0; s2 < n; s2++)
-            for (int b = 0; b < Bi; b++)
-                if (owner(b) == r && H_rec[(size_t)s2][(size_t)b]) {
-                    P.seg_dst.push_back(dst[(size_t)b] + before[(size_t)b]);
-                    P.seg_src.push_back(P.seg_src.back() + H_rec[(size_t)s2][(size_t)b]);
-                    before[(size_t)b] += H_rec[(size_t)s2][(size_t)b];
-                }
-    }
+    std::vector<int> owner_bin; std::vector<MultiPlan> plan;
+    multi_plan(n, B, sp, H_rec, H_kmer, owner_bin, plan);
     // ---- records owner-major, GPU-to-GPU copies, bin-major again, count, write
     rc = run_all([&](int i) -> int {
         CK(cudaSetDevice(devices[i]));

@@ -128,6 +128,12 @@ int  fkm_execute_job(fkm_ctx* ctx, const fkm_config* cfg, fkm_stats* stats);
  * order is unspecified in the reference too, SBKC:723).  A single long record is not cut: it is counted by one GPU.    */
 int  fkm_execute_job_multi(const int32_t* devices, int32_t n_devices, const fkm_config* cfg, fkm_stats* stats);
 
+/* test hook, needs no GPU: the bin owners and the exchange plan fkm_execute_job_multi makes for rank `rank` of n GPUs from the ranks'
+ * histograms h_rec / h_kmer [n][bins * split] (the layout of fastkmer_b200.multigpu.plan_exchange, which it must equal).           */
+int  fkm_debug_multi_plan(int32_t n, int32_t bins, int32_t split, const uint64_t* h_rec, const uint64_t* h_kmer, int32_t rank,
+                          int32_t* owner, uint64_t* send_base, uint64_t* send_off, uint64_t* recv_off, uint64_t* bin_rec, uint64_t* bin_kmer,
+                          uint64_t* seg_src, uint64_t* seg_dst, uint64_t seg_cap, uint64_t* n_seg);
+
 /* ---- in-memory variants (same path, no file I/O) ---------------------------- */
 /* FASTA text in host memory (pinned if it came from fkm_host_alloc).  The raw
  * text is copied to the GPU and parsed there (record split of SURVEY App. A.1). */

@@ -46,6 +46,39 @@ def test_internal_bins_share_an_owner():
     assert (mg.plan_exchange(Hr, Hk, 0, G, owner=fixed, split=split)["owner"] == np.repeat(fixed, split)).all()
 
 
+def test_cpp_plan_of_the_multi_gpu_job_equals_the_python_plan():
+    """fkm_execute_job_multi plans its exchange in C++ (owners by LPT, owner-major send offsets, source-major receive offsets,
+    segments back to bin-major); the hook fkm_debug_multi_plan needs no GPU: every field must equal multigpu.plan_exchange's."""
+    import ctypes as C
+    from fastkmer_b200 import api
+    lib = api.load_library()
+    rng = np.random.default_rng(11)
+    for G, B, split in ((2, 64, 1), (3, 17, 1), (4, 96, 8), (8, 2048, 8), (5, 1, 4)):
+        Bi = B * split
+        Hr = rng.integers(0, 40, (G, Bi)).astype(np.uint64)
+        Hr[:, rng.integers(0, Bi, max(1, Bi // 4))] = 0
+        Hk = Hr * rng.integers(1, 30, (G, Bi)).astype(np.uint64)
+        for r in range(G):
+            want = mg.plan_exchange(Hr, Hk, r, G, split=split)
+            owner = np.zeros(Bi, dtype=np.int32)
+            send_base = np.zeros(Bi + 1, dtype=np.uint64); send_off = np.zeros(G + 1, dtype=np.uint64); recv_off = np.zeros(G + 1, dtype=np.uint64)
+            bin_rec = np.zeros(Bi, dtype=np.uint64); bin_kmer = np.zeros(Bi, dtype=np.uint64)
+            cap = G * Bi + 1
+            seg_src = np.zeros(cap + 1, dtype=np.uint64); seg_dst = np.zeros(cap, dtype=np.uint64)
+            n_seg = C.c_uint64()
+            hr, hk = np.ascontiguousarray(Hr), np.ascontiguousarray(Hk)
+            rc = lib.fkm_debug_multi_plan(G, B, split, hr.ctypes.data, hk.ctypes.data, r, owner.ctypes.data, send_base.ctypes.data, send_off.ctypes.data,
+                                          recv_off.ctypes.data, bin_rec.ctypes.data, bin_kmer.ctypes.data, seg_src.ctypes.data, seg_dst.ctypes.data, cap, C.byref(n_seg))
+            assert rc == 0
+            what = "G=%d B=%d split=%d rank %d" % (G, B, split, r)
+            assert owner.tolist() == want["owner"].tolist(), what
+            assert send_base.tolist() == want["send_base"].tolist(), what
+            assert np.diff(send_off).tolist() == want["send_splits"] and np.diff(recv_off).tolist() == want["recv_splits"], what
+            assert bin_rec.tolist() == want["bin_rec"].tolist() and bin_kmer.tolist() == want["bin_kmer"].tolist(), what
+            n = n_seg.value
+            assert n == want["seg_dst"].size and seg_dst[:n].tolist() == want["seg_dst"].tolist() and seg_src[:n + 1].tolist() == want["seg_src"].tolist(), what
+
+
 def test_plan_is_consistent_across_ranks():
     rng = np.random.default_rng(3)
     for G, B in ((2, 64), (3, 17), (8, 2048)):
