@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <vector>
 #include <algorithm>
 #include <random>
 #include "fkm_common.h"
@@ -105,6 +106,40 @@ int main() {
     // SURVEY App. C.1 known answers of hash_to_bucket (UTIL:686-695)
     CHECK(hash_to_bucket(0, 2048) == 362 && hash_to_bucket(12345, 2048) == 1043 && hash_to_bucket(1048576, 2048) == 1821 &&
           hash_to_bucket(4194303, 4096) == 382, "hash_to_bucket KAT");
+    // internal bins: split_bin keeps the configuration's bin in the high bits (a bin's internal bins are consecutive) and adds a
+    // second hash of the signature below it; split 0 is hash_to_bucket itself
+    {
+        std::vector<unsigned> seen(16, 0);
+        for (int it = 0; it < 200000; it++) {
+            const uint32_t sig = (uint32_t)(g() & 0x3FFFFFFFu), B = 1 + (uint32_t)(g() % 5000);
+            const int sp = (int)(g() % 7);
+            const uint32_t ib = split_bin(sig, B, sp);
+            CHECK((ib >> sp) == hash_to_bucket(sig, B) && ib < (B << sp), "split_bin B %u split %d", B, sp);
+            CHECK(split_bin(sig, B, 0) == hash_to_bucket(sig, B), "split_bin split 0");
+            if (sp == 4) seen[ib & 15u]++;
+        }
+        unsigned lo = ~0u, hi = 0;
+        for (unsigned c : seen) { lo = std::min(lo, c); hi = std::max(hi, c); }
+        CHECK(hi < 2 * lo, "split_bin spreads signatures over the internal bins (%u..%u)", lo, hi);
+    }
+    // the partitioned count stage: sub-bucket (high bits of part_hash) and table slot (folded low bits) are independent enough that the
+    // k-mers of ONE sub-bucket of 111 fill a 16384-slot table evenly (no 64-slot block more than 4x as full as the average)
+    {
+        std::vector<unsigned> blocks(256, 0);
+        unsigned n_in = 0;
+        for (int it = 0; it < 3000000; it++) {
+            const uint64_t key = g() >> 8;                                    // a 56-bit canonical 28-mer stand-in
+            const uint32_t h = part_hash(key);
+            if (umulhi32(h, 111u) != 5u) continue;
+            blocks[part_slot(h, 16383u) >> 6]++; n_in++;
+        }
+        unsigned hi = 0;
+        for (unsigned c : blocks) hi = std::max(hi, c);
+        CHECK(n_in > 20000 && hi * 256u < 4u * n_in * 2u, "part_slot spread inside a sub-bucket (max block %u of %u keys)", hi, n_in);
+        key128 w; w.lo = 0x0123456789ABCDEFull; w.hi = 0x0FEDCBA987654321ull;
+        key128 w2 = w; w2.hi ^= 1ull << 40;
+        CHECK(part_hash(w) != part_hash(w2), "part_hash(key128) depends on the high word");
+    }
     if (g_fail) { printf("%d checks failed\n", g_fail); return 1; }
     printf("ok\n");
     return 0;
