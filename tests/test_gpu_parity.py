@@ -456,6 +456,20 @@ def test_execute_job_writes_reference_layout(ctx, oracle, tmp_path, ht):
     assert not (tmp_path / "none").exists()
 
 
+def test_debug_configuration_writes_to_the_debug_directory(ctx, oracle, tmp_path, monkeypatch):
+    """TestConfiguration.debug moves the output to debugDirectory + stem, without the _s<type> suffix (test/package.scala:33)."""
+    from fastkmer_b200 import config
+    monkeypatch.setattr(config, "debugDirectory", str(tmp_path) + "/dbg_")
+    fasta = oracle.gen_lcg_fasta(7, 3000, 150, 90)
+    inp = tmp_path / "r.fasta"
+    inp.write_bytes(fasta)
+    tc = fk.TestConfiguration(str(inp), str(tmp_path) + "/out/", 20, 6, 3, max_b=64, useHT=True, write=True, debug=True)
+    st = fk.SparkBinKmerCounter.executeJob(ctx, tc)
+    assert tc.outputDir == str(tmp_path) + "/dbg_k20_m6_x3_b64" and os.path.isdir(tc.outputDir) and not (tmp_path / "out").exists()
+    want = oracle.count(fasta, 20, 6, 3, 64, 1)
+    assert st["n_kmers"] == want["stats"]["n_kmers"] and len(os.listdir(tc.outputDir)) == np.unique(want["bin"]).size
+
+
 @pytest.mark.parametrize("k,m,ht", [(28, 10, 0), (28, 10, 1), (55, 13, 1)])
 def test_execute_job_on_several_gpus(oracle, tmp_path, k, m, ht):
     """fkm_execute_job_multi: the drop-in job over the GPUs of the node through the C ABI alone (byte ranges of the file, LPT bin owners,
