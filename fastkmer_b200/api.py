@@ -75,6 +75,7 @@ def load_library():
         "fkm_count_packed_host": (C.c_int, [vp, cfgp, vp, vp, u64, C.POINTER(vp), stp]),
         "fkm_count_packed_device": (C.c_int, [vp, cfgp, vp, vp, u64, C.POINTER(vp), stp]),
         "fkm_pack_fasta": (C.c_int, [vp, u64, vp, vp, u64, C.POINTER(u64), C.POINTER(u64)]),
+        "fkm_pack_fasta_mt": (C.c_int, [vp, u64, vp, vp, u64, C.POINTER(u64), C.POINTER(u64), i32]),
         "fkm_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
         "fkm_host_free": (None, [vp]),
         "fkm_result_size": (u64, [vp]),

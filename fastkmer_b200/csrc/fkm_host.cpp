@@ -20,8 +20,8 @@
 // the next header with '\n' removed (SBKC:63-64 replaceAll("\n","")) and nothing
 // else stripped.  Bytes before the first header are ignored.  Each record is laid
 // out as its bytes followed by ONE invalid separator position.
-extern "C" int fkm_pack_fasta(const uint8_t* t, uint64_t n, uint64_t* bases, uint32_t* invalid,
-                              uint64_t cap_positions, uint64_t* n_positions, uint64_t* n_bases) {
+static int pack_fasta_serial(const uint8_t* t, uint64_t n, uint64_t* bases, uint32_t* invalid,
+                             uint64_t cap_positions, uint64_t* n_positions, uint64_t* n_bases) {
     static int8_t code[256]; static bool init = false;
     if (!init) { for (int i = 0; i < 256; i++) code[i] = -1; code['A'] = 0; code['C'] = 1; code['G'] = 2; code['T'] = 3; init = true; }
     uint64_t p = 0, nb = 0;
@@ -59,6 +59,93 @@ extern "C" int fkm_pack_fasta(const uint8_t* t, uint64_t n, uint64_t* bases, uin
     if (n_positions) *n_positions = p;
     if (n_bases) *n_bases = nb;
     return FKM_OK;
+}
+
+// The same layout from `threads` host threads: the text is cut at record starts, a first pass counts every range's positions
+// (so that every range knows its first position), a second pass packs the ranges in place; the words two ranges share are
+// merged afterwards.  threads <= 0: one per hardware thread (small inputs stay on the calling thread).
+extern "C" int fkm_pack_fasta_mt(const uint8_t* t, uint64_t n, uint64_t* bases, uint32_t* invalid,
+                                 uint64_t cap_positions, uint64_t* n_positions, uint64_t* n_bases, int32_t threads) {
+    unsigned T = threads > 0 ? (unsigned)threads : std::max(1u, std::thread::hardware_concurrency());
+    T = (unsigned)std::min<uint64_t>(T, std::max<uint64_t>(1, n >> 16));              // at least 64 KB of text per thread
+    if (T <= 1) return pack_fasta_serial(t, n, bases, invalid, cap_positions, n_positions, n_bases);
+    static int8_t code[256]; static bool init = false;
+    if (!init) { for (int i = 0; i < 256; i++) code[i] = -1; code['A'] = 0; code['C'] = 1; code['G'] = 2; code['T'] = 3; init = true; }
+    auto next_header = [&](uint64_t from) -> uint64_t {                                // first '>' at the start of a line at or after `from`
+        while (from < n) {
+            const uint8_t* q = (const uint8_t*)memchr(t + from, '>', (size_t)(n - from));
+            if (!q) return n;
+            const uint64_t at = (uint64_t)(q - t);
+            if (at == 0 || t[at - 1] == '\n') return at;
+            from = at + 1;
+        }
+        return n;
+    };
+    std::vector<uint64_t> cut(T + 1, n);
+    cut[0] = next_header(0);                                                           // bytes before the first header are ignored
+    for (unsigned i = 1; i < T; i++) cut[i] = next_header(std::max(cut[i - 1], n / T * i));
+    // walks the records of [lo, hi): f(c) for every value byte (c = its code, -1 when invalid), f(-1) once more after every record
+    auto walk = [&](uint64_t lo, uint64_t hi, auto&& f, uint64_t& nb) {
+        uint64_t i = lo;
+        while (i < hi) {
+            const uint8_t* e = (const uint8_t*)memchr(t + i, '\n', (size_t)(hi - i));  // header line
+            i = e ? (uint64_t)(e - t) + 1 : hi;
+            bool bol = true;
+            while (i < hi && !(bol && t[i] == '>')) {
+                const uint8_t c = t[i];
+                bol = (c == '\n');
+                if (c != '\n') { f((int)code[c]); nb++; }
+                i++;
+            }
+            f(-1);
+        }
+    };
+    std::vector<uint64_t> cnt(T, 0), nbs(T, 0), first(T + 1, 0);
+    {
+        std::vector<std::thread> th;
+        for (unsigned i = 0; i < T; i++) th.emplace_back([&, i]() { uint64_t c = 0, nb = 0; walk(cut[i], cut[i + 1], [&](int) { c++; }, nb); cnt[i] = c; nbs[i] = nb; });
+        for (auto& x : th) x.join();
+    }
+    uint64_t nb_total = 0;
+    for (unsigned i = 0; i < T; i++) { first[i + 1] = first[i] + cnt[i]; nb_total += nbs[i]; }
+    const uint64_t P = first[T];
+    if (n_positions) *n_positions = P;
+    if (n_bases) *n_bases = nb_total;
+    if (!bases) return FKM_OK;
+    if (P > cap_positions) return fkm_set_error(FKM_EINVAL, "packed buffer too small");
+    struct Part { uint64_t word; uint64_t b; uint32_t v; };                            // bits of a word shared with a neighbouring range
+    std::vector<std::vector<Part>> parts(T);
+    {
+        std::vector<std::thread> th;
+        for (unsigned i = 0; i < T; i++)
+            th.emplace_back([&, i]() {
+                const uint64_t p0 = first[i], p1 = first[i + 1];
+                uint64_t p = p0, bw = 0, nb = 0; uint32_t iw = 0;
+                auto flush = [&](uint64_t word) {                                      // the word `word` is complete as far as this range goes
+                    const bool mine = (word << 5) >= p0 && ((word + 1) << 5) <= p1;    // all 32 positions belong to this range
+                    if (mine) { bases[word] = bw; invalid[word] = iw; } else parts[i].push_back(Part{word, bw, iw});
+                    bw = 0; iw = 0;
+                };
+                walk(cut[i], cut[i + 1], [&](int c) {
+                    const unsigned sh = 31u - (unsigned)(p & 31);
+                    if (c < 0) iw |= 1u << sh; else bw |= (uint64_t)c << (2 * sh);
+                    if ((p & 31) == 31) flush(p >> 5);
+                    p++;
+                }, nb);
+                if (p & 31) flush(p >> 5);
+            });
+        for (auto& x : th) x.join();
+    }
+    // shared words: zero them, then OR every range's share in; the unused tail of the last word is invalid
+    for (unsigned i = 0; i < T; i++) for (const Part& q : parts[i]) { bases[q.word] = 0; invalid[q.word] = 0; }
+    for (unsigned i = 0; i < T; i++) for (const Part& q : parts[i]) { bases[q.word] |= q.b; invalid[q.word] |= q.v; }
+    if (P & 31) invalid[P >> 5] |= (1u << (32 - (unsigned)(P & 31))) - 1u;
+    return FKM_OK;
+}
+
+extern "C" int fkm_pack_fasta(const uint8_t* t, uint64_t n, uint64_t* bases, uint32_t* invalid,
+                              uint64_t cap_positions, uint64_t* n_positions, uint64_t* n_bases) {
+    return fkm_pack_fasta_mt(t, n, bases, invalid, cap_positions, n_positions, n_bases, 0);
 }
 
 static int mkdir_p(const std::string& dir) {

@@ -155,6 +155,11 @@ int  fkm_count_packed_device(fkm_ctx* ctx, const fkm_config* cfg, const void* d_
  * number of positions; call with bases==NULL to size (words = (n+31)/32).      */
 int  fkm_pack_fasta(const uint8_t* fasta, uint64_t n_bytes, uint64_t* bases, uint32_t* invalid,
                     uint64_t cap_positions, uint64_t* n_positions, uint64_t* n_bases);
+/* the same with `threads` host threads (<= 0: one per hardware thread; 1: the plain loop); bit-identical output.  fkm_pack_fasta
+ * is fkm_pack_fasta_mt(…, 0).  Measured: profiles/README.md (the packer does not beat the PCIe bus on 16 threads, so the
+ * end-to-end path ships the text and parses it on the device).                                                             */
+int  fkm_pack_fasta_mt(const uint8_t* fasta, uint64_t n_bytes, uint64_t* bases, uint32_t* invalid,
+                       uint64_t cap_positions, uint64_t* n_positions, uint64_t* n_bases, int32_t threads);
 
 /* pinned host memory for inputs (so H2D runs at PCIe speed) */
 int  fkm_host_alloc(size_t bytes, void** out);

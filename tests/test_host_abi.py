@@ -177,3 +177,40 @@ def test_jni_shim_builds_and_reports_errors(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120).stdout.strip()
     rc = int(out.split()[0].split("=")[1])
     assert rc != 0 and "live=0" in out and len(out.split("err=", 1)[1]) > 0, out
+
+
+def test_threaded_packer_equals_the_plain_loop():
+    """fkm_pack_fasta_mt cuts the text at record starts, counts, packs the ranges in place and merges the words two ranges share:
+    bit-identical to the one-thread loop for any thread count, on ragged records, junk before the first header, CRLF, no final newline."""
+    import ctypes as C
+    import random
+    import numpy as np
+    from fastkmer_b200 import api
+    lib = api.load_library()
+
+    def pack(text, threads):
+        arr = np.frombuffer(text, dtype=np.uint8)
+        n_pos, n_bases = C.c_uint64(), C.c_uint64()
+        assert lib.fkm_pack_fasta_mt(arr.ctypes.data, arr.size, None, None, 0, C.byref(n_pos), C.byref(n_bases), threads) == 0
+        nw = (n_pos.value + 31) // 32
+        bases = np.full(max(nw, 1), 0xDEADBEEF, dtype=np.uint64); inv = np.full(max(nw, 1), 0xABCD, dtype=np.uint32)
+        assert lib.fkm_pack_fasta_mt(arr.ctypes.data, arr.size, bases.ctypes.data, inv.ctypes.data, nw * 32, C.byref(n_pos), C.byref(n_bases), threads) == 0
+        return bases[:nw].tolist(), inv[:nw].tolist(), n_pos.value, n_bases.value
+
+    rng = random.Random(2026)
+    for case in range(6):
+        recs = []
+        for r in range(rng.choice([3, 50, 4000, 20000])):
+            n = rng.choice([0, 1, 31, 32, 33, 100, 150, 1000]) if case % 2 else rng.randrange(0, 300)
+            seq = "".join(rng.choice("ACGTNacgt-" if case == 3 else "ACGT") for _ in range(n))
+            width = rng.choice([0, 60, 70])
+            body = seq if not width else "\n".join(seq[i:i + width] for i in range(0, len(seq), width))
+            recs.append(">r%d some text > inside\n%s%s" % (r, body, "\r\n" if case == 4 else "\n"))
+        text = ("junk before the first header\nACGT\n" if case >= 2 else "") + "".join(recs)
+        if case == 5:
+            text = text.rstrip("\n")
+        text = text.encode()
+        want = pack(text, 1)
+        for threads in (2, 3, 7, 16, 0):
+            assert pack(text, threads) == want, (case, threads)
+    assert pack(b"", 4) == ([], [], 0, 0) and pack(b"no header at all\nACGT\n" * 10000, 4) == ([], [], 0, 0)
