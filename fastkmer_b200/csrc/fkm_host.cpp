@@ -84,26 +84,30 @@ extern "C" int fkm_pack_fasta_mt(const uint8_t* t, uint64_t n, uint64_t* bases, 
     std::vector<uint64_t> cut(T + 1, n);
     cut[0] = next_header(0);                                                           // bytes before the first header are ignored
     for (unsigned i = 1; i < T; i++) cut[i] = next_header(std::max(cut[i - 1], n / T * i));
-    // walks the records of [lo, hi): f(c) for every value byte (c = its code, -1 when invalid), f(-1) once more after every record
-    auto walk = [&](uint64_t lo, uint64_t hi, auto&& f, uint64_t& nb) {
+    // walks the records of [lo, hi) line by line: line(p, len) for every line of a record's value (without its '\n'), sep() after every record
+    auto walk = [&](uint64_t lo, uint64_t hi, auto&& line, auto&& sep) {
         uint64_t i = lo;
         while (i < hi) {
             const uint8_t* e = (const uint8_t*)memchr(t + i, '\n', (size_t)(hi - i));  // header line
             i = e ? (uint64_t)(e - t) + 1 : hi;
-            bool bol = true;
-            while (i < hi && !(bol && t[i] == '>')) {
-                const uint8_t c = t[i];
-                bol = (c == '\n');
-                if (c != '\n') { f((int)code[c]); nb++; }
-                i++;
+            while (i < hi && t[i] != '>') {                                            // (a '>' starts a record only at the start of a line)
+                e = (const uint8_t*)memchr(t + i, '\n', (size_t)(hi - i));
+                const uint64_t le = e ? (uint64_t)(e - t) : hi;
+                if (le > i) line(t + i, le - i);
+                i = e ? le + 1 : hi;
             }
-            f(-1);
+            sep();
         }
     };
     std::vector<uint64_t> cnt(T, 0), nbs(T, 0), first(T + 1, 0);
     {
         std::vector<std::thread> th;
-        for (unsigned i = 0; i < T; i++) th.emplace_back([&, i]() { uint64_t c = 0, nb = 0; walk(cut[i], cut[i + 1], [&](int) { c++; }, nb); cnt[i] = c; nbs[i] = nb; });
+        for (unsigned i = 0; i < T; i++)
+            th.emplace_back([&, i]() {
+                uint64_t c = 0, nb = 0;
+                walk(cut[i], cut[i + 1], [&](const uint8_t*, uint64_t len) { c += len; nb += len; }, [&]() { c++; });
+                cnt[i] = c; nbs[i] = nb;
+            });
         for (auto& x : th) x.join();
     }
     uint64_t nb_total = 0;
@@ -120,19 +124,25 @@ extern "C" int fkm_pack_fasta_mt(const uint8_t* t, uint64_t n, uint64_t* bases, 
         for (unsigned i = 0; i < T; i++)
             th.emplace_back([&, i]() {
                 const uint64_t p0 = first[i], p1 = first[i + 1];
-                uint64_t p = p0, bw = 0, nb = 0; uint32_t iw = 0;
-                auto flush = [&](uint64_t word) {                                      // the word `word` is complete as far as this range goes
+                // bw / iw hold the positions of the current word seen so far, right-aligned; `fill` of them (the range's first word
+                // starts at position p0 & 31)
+                uint64_t p = p0, bw = 0; uint32_t iw = 0;
+                auto flush = [&](uint64_t word, uint64_t b, uint32_t v) {               // word `word` as far as this range goes, bits in place
                     const bool mine = (word << 5) >= p0 && ((word + 1) << 5) <= p1;    // all 32 positions belong to this range
-                    if (mine) { bases[word] = bw; invalid[word] = iw; } else parts[i].push_back(Part{word, bw, iw});
-                    bw = 0; iw = 0;
+                    if (mine) { bases[word] = b; invalid[word] = v; } else parts[i].push_back(Part{word, b, v});
                 };
-                walk(cut[i], cut[i + 1], [&](int c) {
-                    const unsigned sh = 31u - (unsigned)(p & 31);
-                    if (c < 0) iw |= 1u << sh; else bw |= (uint64_t)c << (2 * sh);
-                    if ((p & 31) == 31) flush(p >> 5);
+                auto put = [&](int c) {
+                    bw = (bw << 2) | (uint64_t)(c < 0 ? 0 : c); iw = (iw << 1) | (c < 0 ? 1u : 0u);
+                    if ((p & 31) == 31) { flush(p >> 5, bw, iw); bw = 0; iw = 0; }
                     p++;
-                }, nb);
-                if (p & 31) flush(p >> 5);
+                };
+                walk(cut[i], cut[i + 1],
+                     [&](const uint8_t* q, uint64_t len) { for (uint64_t j = 0; j < len; j++) put((int)code[q[j]]); },
+                     [&]() { put(-1); });
+                if (p & 31) {                                                          // the range ends inside a word: shift its bits into place
+                    const unsigned rem = 32u - (unsigned)(p & 31);
+                    flush(p >> 5, bw << (2 * rem), iw << rem);
+                }
             });
         for (auto& x : th) x.join();
     }
